@@ -1,0 +1,278 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY (torch-CPU restatement of the in-tree part of the path).
+
+Restates, with torch CPU ops (so that `grid_sample`, `inverse`, `bmm` quirks are inherited
+rather than re-derived), the PGDVS functions on the hot path:
+
+  get_batched_rays          /root/reference/pgdvs/renderers/pgdvs_renderer_base.py:17-57
+  compute_dyn_pcl           /root/reference/pgdvs/renderers/pgdvs_renderer_dyn.py:275-457
+  render_dyn_pcl            /root/reference/pgdvs/renderers/pgdvs_renderer_dyn.py:671-724
+  dyn/track merge           /root/reference/pgdvs/renderers/pgdvs_renderer_dyn.py:229-235
+  static/dynamic blend      /root/reference/pgdvs/renderers/pgdvs_renderer.py:169-172
+  camera conversion         /root/reference/pgdvs/utils/pytorch3d_utils.py:5-47
+  compute_projections       /root/reference/pgdvs/models/gnt/projector.py:41-73
+  track -> point cloud      /root/reference/pgdvs/renderers/pgdvs_renderer_dyn_track.py:98-284
+
+and the pytorch3d 0.7.4 glue they call (PointsRasterizer.transform, PointsRenderer.forward,
+knn_points) from the published algorithm (parity unpinned for those; see raster_cpu.cpp).
+
+The in-tree functions ARE pinned: tests/golden/make_golden.py imports the real reference
+modules (with stub packages for the absent third-party imports) and stores their outputs;
+tests/test_oracle_golden.py checks this file against those fixtures.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import raster as _raster
+
+
+# ----------------------------------------------------------------------------- cameras
+def split_flat_cam(flat_cam):
+    """flat_cam[34] = [h, w, K(4x4 row-major), c2w(4x4 row-major)] (datasets/nvidia_eval.py:827-832)."""
+    flat_cam = flat_cam.reshape(-1)
+    h, w = int(flat_cam[0]), int(flat_cam[1])
+    K = flat_cam[2:18].reshape(4, 4)
+    c2w = flat_cam[18:34].reshape(4, 4)
+    return h, w, K, c2w
+
+
+def get_batched_rays(H, W, K44, c2w44):
+    """pgdvs_renderer_base.py:17-57 for batch_size=1, render_stride=1.
+
+    Pixel grid u=col, v=row with NO half-pixel offset; rays_d = (c2w[:3,:3] @ K^-1) @ [u,v,1].
+    """
+    u, v = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
+    u = u.reshape(-1).float()
+    v = v.reshape(-1).float()
+    pix = torch.stack((u, v, torch.ones_like(u)), dim=0)[None]  # [1,3,HW]
+    K44 = K44.reshape(1, 4, 4)
+    c2w44 = c2w44.reshape(1, 4, 4)
+    rays_d = c2w44[:, :3, :3].bmm(torch.inverse(K44[:, :3, :3])).bmm(pix).transpose(1, 2)
+    rays_o = c2w44[:, :3, 3].unsqueeze(1).repeat(1, rays_d.shape[1], 1)
+    uvs = pix[:, :2, :].permute(0, 2, 1).reshape(-1, 2)
+    return rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), uvs
+
+
+def cameras_from_opencv_projection(R, tvec, camera_matrix, image_size_hw):
+    """pytorch3d.utils.cameras_from_opencv_projection as restated in-tree at
+    pgdvs/utils/pytorch3d_utils.py:5-47.  Returns a dict instead of PerspectiveCameras:
+    R_p3d [3,3] (row-vector convention), T_p3d [3], focal [2], p0 [2] (NDC)."""
+    R = R.reshape(1, 3, 3).float()
+    tvec = tvec.reshape(1, 3).float()
+    camera_matrix = camera_matrix.reshape(1, 3, 3).float()
+    image_size = torch.as_tensor(image_size_hw).reshape(1, 2)
+    focal_length = torch.stack([camera_matrix[:, 0, 0], camera_matrix[:, 1, 1]], dim=-1)
+    principal_point = camera_matrix[:, :2, 2]
+    image_size_wh = image_size.to(R).flip(dims=(1,))
+    scale = image_size_wh.min(dim=1, keepdim=True)[0] / 2.0
+    scale = scale.expand(-1, 2)
+    c0 = image_size_wh / 2.0
+    focal_p3d = focal_length / scale
+    p0_p3d = -(principal_point - c0) / scale
+    R_p3d = R.clone().permute(0, 2, 1).contiguous()
+    T_p3d = tvec.clone()
+    R_p3d[:, :, :2] *= -1
+    T_p3d[:, :2] *= -1
+    return {"R": R_p3d[0], "T": T_p3d[0], "focal": focal_p3d[0], "p0": p0_p3d[0]}
+
+
+def world_to_ndc(points_world, cam):
+    """PointsRasterizer.transform for PerspectiveCameras(in_ndc=True):
+    view = [p,1] @ [[R,0],[T,1]]; proj = [view,1] @ K^T with
+    K = [[fx,0,px,0],[0,fy,py,0],[0,0,0,1],[0,0,1,0]]; xy / w; z := view z."""
+    P = points_world.shape[0]
+    M = torch.eye(4)
+    M[:3, :3] = cam["R"]
+    M[3, :3] = cam["T"]
+    ph = torch.cat([points_world.float(), torch.ones(P, 1)], dim=1)
+    view = ph @ M
+    view = view[:, :3] / view[:, 3:]
+    Kp = torch.zeros(4, 4)
+    Kp[0, 0], Kp[1, 1] = cam["focal"][0], cam["focal"][1]
+    Kp[0, 2], Kp[1, 2] = cam["p0"][0], cam["p0"][1]
+    Kp[3, 2] = 1.0
+    Kp[2, 3] = 1.0
+    vh = torch.cat([view, torch.ones(P, 1)], dim=1)
+    proj = vh @ Kp.t().contiguous()
+    ndc = proj[:, :3] / proj[:, 3:]
+    ndc[:, 2] = view[:, 2]
+    return ndc
+
+
+def camera_from_flat_cam(flat_cam):
+    """render_dyn_pcl's camera set-up, pgdvs_renderer_dyn.py:674-687."""
+    h, w, K, c2w = split_flat_cam(flat_cam)
+    w2c = torch.inverse(c2w)
+    return cameras_from_opencv_projection(w2c[:3, :3], w2c[:3, 3], K[:3, :3], (h, w))
+
+
+def compute_projections(xyz, flat_cam):
+    """Projector.compute_projections (models/gnt/projector.py:41-73) for one camera.
+    xyz [P,3] -> (uv [P,2] clamped to +-1e6, mask [P] = z>0)."""
+    _, _, K, c2w = split_flat_cam(flat_cam)
+    xyz_h = torch.cat([xyz, torch.ones_like(xyz[:, :1])], dim=-1)
+    proj = K[None].bmm(torch.inverse(c2w[None])).bmm(xyz_h.t()[None])
+    proj = proj.permute(0, 2, 1)[0]
+    uv = proj[:, :2] / torch.clamp(proj[:, 2:3], min=1e-8)
+    uv = torch.clamp(uv, min=-1e6, max=1e6)
+    return uv, proj[:, 2] > 0
+
+
+# ------------------------------------------------------------------ unproject/warp/lerp
+def knn_outlier_flags(pcl, knn=50, std_thres=0.1, chunk=2048):
+    """pgdvs_renderer_dyn.py:405-427: pytorch3d knn_points(K=knn+1) brute force (squared L2,
+    ascending), drop the self match, avg; keep iff avg < median + std*thres (unbiased std)."""
+    P = pcl.shape[0]
+    k = min(knn + 1, P)
+    avg = torch.empty(P)
+    for s in range(0, P, chunk):
+        q = pcl[s:s + chunk]
+        d2 = ((q[:, None, :] - pcl[None, :, :]) ** 2).sum(-1)
+        nn = torch.topk(d2, k, dim=1, largest=False, sorted=True).values
+        avg[s:s + chunk] = nn[:, 1:].mean(dim=1)
+    thres = torch.median(avg) + torch.std(avg) * std_thres
+    return avg < thres, thres, avg
+
+
+def compute_dyn_pcl(*, dyn_mask_1, rgb_1, depth_1, flow_12, flow_12_occ_mask, rgb_2, depth_2,
+                    K_1, c2w_1, K_2, c2w_2, time_1, time_2, time_tgt,
+                    use_flow_consistency=False, flag_not_outlier=None):
+    """pgdvs_renderer_dyn.py:275-457 up to (and including) the outlier compaction.
+
+    Inputs are the [H,W,C] channels-last maps of the reference's data dict.
+    Returns dict(pcl [P,3] world, rgb [P,3], src_pix [P] (flat row-major source pixel index),
+    n_masked, n_valid).  `flag_not_outlier` (bool [P_valid]) replaces the KNN statistics when
+    given; None keeps every point (dyn_pcl_remove_outlier=False, :453-457).
+    """
+    H, W, _ = dyn_mask_1.shape
+    raw_shape = torch.FloatTensor((W, H)).reshape(1, 2)
+    rays_o, rays_d, uvs = get_batched_rays(H, W, K_1, c2w_1)
+
+    flat_mask = dyn_mask_1.reshape(-1).bool()
+    if use_flow_consistency:
+        flat_mask = ~(flow_12_occ_mask > 0).reshape(-1) & flat_mask
+    uv1 = uvs[flat_mask, :2]
+    uv2 = uv1 + flow_12.reshape(-1, 2)[flat_mask, :]
+    valid = torch.all((uv2 >= 0) & (uv2 <= raw_shape - 1), dim=1)
+
+    pcl_1 = (rays_o + rays_d * depth_1.reshape(-1, 1))[flat_mask, :][valid, :]
+    src_pix = torch.arange(H * W)[flat_mask][valid]
+
+    if float(time_1) == float(time_2):
+        pcl = pcl_1
+        rgb = rgb_1.reshape(-1, 3)[flat_mask, :][valid, :]
+    else:
+        uv2 = uv2[valid, :]
+        grid = 2 * uv2 / raw_shape - 1.0
+        depth_w = torch.nn.functional.grid_sample(
+            depth_2[None].permute(0, 3, 1, 2), grid[None, None], mode="nearest",
+            align_corners=False)[0, 0, 0, :]
+        rgb = torch.nn.functional.grid_sample(
+            rgb_2[None].permute(0, 3, 1, 2), grid[None, None], mode="bilinear",
+            align_corners=False)[0, :, 0, :].T
+        uv2_h = torch.cat((uv2, torch.ones_like(uv2[:, :1])), dim=1)
+        rays_d2 = torch.matmul(c2w_2[:3, :3], torch.matmul(torch.inverse(K_2[:3, :3]), uv2_h.T)).T
+        rays_o2 = c2w_2[:3, 3][None, :].expand(rays_d2.shape[0], -1)
+        pcl_2 = rays_o2 + rays_d2 * depth_w[:, None]
+        w1 = (time_2 - time_tgt) / (time_2 - time_1)
+        w2 = (time_tgt - time_1) / (time_2 - time_1)
+        pcl = w1 * pcl_1 + w2 * pcl_2
+
+    n_valid = int(pcl.shape[0])
+    if flag_not_outlier is not None:
+        pcl = pcl[flag_not_outlier, :]
+        rgb = rgb[flag_not_outlier, :]
+        src_pix = src_pix[flag_not_outlier]
+    return {"pcl": pcl, "rgb": rgb, "src_pix": src_pix, "n_masked": int(flat_mask.sum()),
+            "n_valid": n_valid}
+
+
+# ------------------------------------------------------------------------------ render
+def render_dyn_pcl(*, H, W, dyn_pcl, rgbs, flat_cam, radius, points_per_pixel,
+                   compositor="norm", n_threads=1, banded=False, return_fragments=False):
+    """pgdvs_renderer_dyn.py:671-724: camera conversion -> PointsRasterizer(bin_size=0) ->
+    PointsRenderer(NormWeightedCompositor(bg 0)) twice (rgb features, then ones for the mask)."""
+    if dyn_pcl.shape[0] == 0:
+        img = torch.zeros(H, W, 3)
+        mask = torch.zeros(H, W, 1)
+        return (img, mask, None) if return_fragments else (img, mask)
+    cam = camera_from_flat_cam(flat_cam)
+    ndc = world_to_ndc(dyn_pcl, cam).numpy()
+    P = ndc.shape[0]
+    fi = np.zeros(1, dtype=np.int64)
+    npc = np.full(1, P, dtype=np.int64)
+    img, frags = _raster.render_points(ndc, fi, npc, rgbs.numpy(), (H, W), radius,
+                                       points_per_pixel, compositor, background=(0, 0, 0),
+                                       n_threads=n_threads, banded=banded)
+    ones, _ = _raster.render_points(ndc, fi, npc, np.ones((P, 3), np.float32), (H, W), radius,
+                                    points_per_pixel, compositor, background=(0, 0, 0),
+                                    n_threads=n_threads, banded=banded)
+    img_t = torch.from_numpy(img[0, :, :, :3])
+    mask_t = torch.from_numpy((ones[0, :, :, :1] > 0.0).astype(np.float32))
+    if return_fragments:
+        return img_t, mask_t, (ndc,) + frags
+    return img_t, mask_t
+
+
+def merge_dyn_track(dyn_rgb, dyn_mask, track_rgb, track_mask):
+    """pgdvs_renderer_dyn.py:229-235."""
+    m = ((~(dyn_mask > 0)) & (track_mask > 0)).float()
+    rgb = (1 - m) * dyn_rgb + m * track_rgb
+    mask = ((dyn_mask > 0) | (track_mask > 0)).float()
+    return rgb, mask
+
+
+def blend_static_dynamic(static_rgb, dyn_rgb, dyn_mask):
+    """pgdvs_renderer.py:169-172."""
+    return (1 - dyn_mask) * static_rgb + dyn_mask * dyn_rgb
+
+
+# ------------------------------------------------------------------------------ tracks
+def compute_pcl_for_tgt(*, tracks, visibles, rgbs, depths, flat_cams, times, time_tgt,
+                        idx_temporal_closest, idx_real_track):
+    """pgdvs_renderer_dyn_track.py:98-284 (before the KNN filters).
+
+    tracks [Q,F,2] (col,row), visibles [Q,F] bool, rgbs [F,H,W,3], depths [F,H,W,1],
+    flat_cams [F,34], times [F], time_tgt scalar tensor.
+    Returns (pcl [P,3], rgb [P,3], track_id [P])."""
+    vis_closest = visibles[:, idx_temporal_closest]
+    flag_invis = torch.all(~vis_closest, dim=1)
+    flag_enough = torch.sum(visibles[:, idx_real_track].float(), dim=1) >= 2
+    flag_valid = flag_invis & flag_enough
+    n_valid = int(flag_valid.sum())
+    if n_valid == 0:
+        return torch.zeros(0, 3), torch.zeros(0, 3), torch.zeros(0, dtype=torch.long)
+    v_tracks = tracks[flag_valid]
+    v_vis = visibles[flag_valid]
+    t_all = times[None, :].expand(n_valid, -1)
+    t_diff = (t_all - time_tgt).masked_fill_(~v_vis, float("inf"))
+    order = torch.argsort(t_diff.abs(), dim=1, descending=False)[:, :2]
+    ar = torch.arange(n_valid)[:, None].expand(-1, 2)
+    t_use = t_all[ar, order]
+    uv_use = v_tracks[ar, order, :]  # [n_valid,2,2]
+    _, H, W, _ = rgbs.shape
+    wh = torch.FloatTensor((W, H))[None, :]
+    pts = torch.zeros(n_valid, 2, 3)
+    cols = torch.zeros(n_valid, 2, 3)
+    for f in torch.unique(order).tolist():
+        sel = order == f  # [n_valid,2]
+        uv = uv_use[sel]  # [#,2]
+        grid = 2 * uv / wh - 1
+        c = torch.nn.functional.grid_sample(rgbs[f:f + 1].permute(0, 3, 1, 2), grid[None, None],
+                                            mode="bilinear", align_corners=True)[0, :, 0, :].permute(1, 0)
+        d = torch.nn.functional.grid_sample(depths[f:f + 1].permute(0, 3, 1, 2), grid[None, None],
+                                            mode="nearest", align_corners=False)[0, 0, 0, :]
+        Kf = flat_cams[f, 2:18].reshape(4, 4)
+        c2w = flat_cams[f, 18:34].reshape(4, 4)
+        uvh = torch.nn.functional.pad(uv, (0, 1), value=1).permute(1, 0)
+        rd = (c2w[None, :3, :3].bmm(torch.inverse(Kf[None, :3, :3])).bmm(uvh[None])).transpose(1, 2)[0]
+        ro = c2w[None, :3, 3].repeat(rd.shape[0], 1)
+        pts[sel] = ro + rd * d[:, None]
+        cols[sel] = c
+    rgb = torch.mean(cols, dim=1)
+    ratio = (time_tgt - t_use[:, :1]) / (t_use[:, 1:2] - t_use[:, :1] + 1e-8)
+    pcl = pts[:, 0, :] + (pts[:, 1, :] - pts[:, 0, :]) * ratio
+    return pcl, rgb, torch.nonzero(flag_valid)[:, 0]
