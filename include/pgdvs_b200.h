@@ -1,0 +1,197 @@
+/*
+ * pgdvs_b200.h — C ABI of the B200-native PGDVS dynamic-content point-splat path.
+ *
+ * Drop-in boundary.  The reference (apple/ml-pgdvs) is pure Python and has no FFI layer of
+ * its own; the seam it crosses is the pytorch3d C++ extension (`pytorch3d._C`), reached from
+ *   pgdvs/renderers/pgdvs_renderer_dyn.py:684-722   (render_dyn_pcl -> PointsRenderer)
+ *   pgdvs/renderers/st_geo_renderer.py:85-120
+ * Each entry point below names the reference (or pytorch3d) interface it replaces.  All
+ * pointers are DEVICE pointers unless stated otherwise; all work is enqueued on `stream`
+ * (a cudaStream_t passed as void*); nothing is allocated behind the caller's back — scratch
+ * comes from a caller-provided workspace whose size is queried first.  Every function
+ * returns 0 on success, a negative PGDVS_E_* code for argument errors, or a positive
+ * cudaError_t value if a launch failed.  No function throws, none synchronises the device.
+ *
+ * There is no CPU fallback: the library contains sm_100a code only.
+ */
+#ifndef PGDVS_B200_H_
+#define PGDVS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGDVS_B200_ABI_VERSION 1
+
+/* error codes (negative = argument / capacity errors detected on the host side) */
+#define PGDVS_OK 0
+#define PGDVS_E_BADARG (-1)      /* null pointer, non-positive size, unknown mode */
+#define PGDVS_E_K_TOO_LARGE (-2) /* points_per_pixel > PGDVS_MAX_POINTS_PER_PIXEL */
+#define PGDVS_E_WORKSPACE (-3)   /* workspace smaller than *_workspace_bytes() */
+#define PGDVS_E_CHANNELS (-4)    /* fused compositing supports C <= PGDVS_MAX_FUSED_CHANNELS */
+#define PGDVS_E_ALIGN (-5)       /* pointer not aligned as documented */
+
+/* pytorch3d's kMaxPointsPerPixel (rasterize_points.py): hard cap on K */
+#define PGDVS_MAX_POINTS_PER_PIXEL 150
+#define PGDVS_MAX_FUSED_CHANNELS 4
+
+/* compositor selector — pytorch3d.renderer.compositing.{alpha_composite,norm_weighted_sum,
+ * weighted_sum}; PGDVS uses NORM_WEIGHTED (pgdvs_renderer_dyn.py:707-709), ALPHA is the
+ * commented-out alternative (:704-706). */
+#define PGDVS_COMPOSITE_NONE 0
+#define PGDVS_COMPOSITE_ALPHA 1
+#define PGDVS_COMPOSITE_NORM_WEIGHTED 2
+#define PGDVS_COMPOSITE_WEIGHTED_SUM 3
+
+int pgdvs_abi_version(void);
+const char* pgdvs_error_string(int code);
+/* out[0..3] = sizeof(PgdvsCamera), sizeof(PgdvsUwpJob), offsetof(PgdvsUwpJob, M1),
+ * offsetof(PgdvsUwpJob, view): lets a foreign-language binding verify its struct mirror. */
+int pgdvs_struct_layout(int32_t out[4]);
+
+/* --------------------------------------------------------------------------------------
+ * 1. Binning: cell-sort a packed batch of NDC point clouds.
+ *
+ * Replaces nothing in the reference (it forces bin_size=0, pgdvs_renderer_dyn.py:689-695,
+ * because pytorch3d's fixed-capacity bins overflow); this is the exact, overflow-free
+ * count -> scan -> fill that makes the tiled rasterizer possible.
+ *
+ *  points        f32 [P,3]   NDC x, NDC y, view-space z  (PointsRasterizer.transform output)
+ *  features      f32 [P,C]   per-point features, C <= 4, or NULL (raster-only)
+ *  first_idx     i64 [N]     cloud_to_packed_first_idx
+ *  num_points    i64 [N]     num_points_per_cloud
+ *  radius        f32 [P] or NULL; radius_max = scalar radius (NULL case) or max(radius)
+ *  workspace     >= pgdvs_bin_workspace_bytes(N,H,W,P,radius_max), 256-byte aligned
+ * ------------------------------------------------------------------------------------ */
+int pgdvs_bin_workspace_bytes(int N, int H, int W, int64_t P, float radius_max, size_t* bytes);
+
+int pgdvs_bin_points(const float* points, const float* features, int C, const int64_t* first_idx,
+                     const int64_t* num_points, int N, int64_t P, const float* radius,
+                     float radius_max, int H, int W, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * 2. Tiled rasterize-and-composite over a binned workspace.
+ *
+ * Replaces `pytorch3d._C.rasterize_points(points, cloud_to_packed_first_idx,
+ * num_points_per_cloud, image_size, radius, points_per_pixel, bin_size=0, ...)`
+ * + `PointsRenderer.forward` weights (1 - dists/(r*r)) + the compositor
+ * + `_add_background_color_to_images`, and the second all-ones render that PGDVS uses for
+ * the mask (pgdvs_renderer_dyn.py:717-722), in one pass.
+ *
+ *  K             points_per_pixel (1..150)
+ *  radius_max / per_point_radius   must repeat what pgdvs_bin_points was given (scalar radius,
+ *                or 1 if a per-point radius tensor was binned)
+ *  rr_weight     the fp32 value of (r*r) that PointsRenderer divides by (r*r evaluated in
+ *                double, then rounded); ignored when compositor == NONE
+ *  background    f32 [C] HOST pointer or NULL (zeros)
+ *  idx/zbuf/dists  i32/f32/f32 [N,H,W,K] or NULL (skip writing fragments), -1 filled
+ *  image         f32 [N,H,W,C] or NULL
+ *  mask          f32 [N,H,W,1] or NULL: 1.0 where the same compositor applied to all-ones
+ *                features is > 0
+ *  static_rgb    f32 [N,H,W,C] or NULL.  If given (with image and mask non-NULL) `image`
+ *                receives the blend (1-mask)*static + mask*dyn of pgdvs_renderer.py:169-172.
+ * ------------------------------------------------------------------------------------ */
+int pgdvs_rasterize_composite(const void* workspace, size_t workspace_bytes, int N, int64_t P,
+                              int H, int W, int K, float radius_max, int per_point_radius, int C,
+                              int compositor,
+                              float rr_weight, const float* background, const float* static_rgb,
+                              int32_t* idx, float* zbuf, float* dists, float* image, float* mask,
+                              void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * 3. Stand-alone compositors (pytorch3d `_C.accum_alphacomposite`, `_C.accum_weightedsumnorm`,
+ *    `_C.accum_weightedsum` forward):  idx i64 [N,K,H,W], alphas f32 [N,K,H,W],
+ *    features f32 [C,P]  ->  out f32 [N,C,H,W].
+ * ------------------------------------------------------------------------------------ */
+int pgdvs_composite(const int64_t* idx, const float* alphas, const float* features, int N, int K,
+                    int H, int W, int C, int64_t P, int mode, float* out, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * 4. Fused unproject -> flow-warp -> time-lerp -> project.
+ *
+ * Replaces PGDVSBaseRenderer.get_batched_rays (pgdvs_renderer_base.py:17-57),
+ * PGDVSDynamicRenderer.compute_dyn_pcl's geometry (pgdvs_renderer_dyn.py:304-388) and
+ * PointsRasterizer.transform for the camera built at pgdvs_renderer_dyn.py:684-687,
+ * for a batch of (target view, source-frame pair) jobs.  Output order is the reference's:
+ * view-major, job-major, then row-major source pixels (stable compaction).
+ * ------------------------------------------------------------------------------------ */
+typedef struct PgdvsCamera { /* pytorch3d PerspectiveCameras(in_ndc=True), row-vector convention */
+  float R[9];                /* X_view = X_world @ R + T */
+  float T[3];
+  float focal[2];
+  float p0[2];
+} PgdvsCamera;
+
+typedef struct PgdvsUwpJob {
+  const float* depth1;  /* [H,W]   source frame 1 depth           */
+  const float* rgb1;    /* [H,W,3]                                 */
+  const float* mask1;   /* [H,W]   dynamic mask (non-zero = keep)  */
+  const float* flow12;  /* [H,W,2] pixels, +u right / +v down      */
+  const float* occ12;   /* [H,W] or NULL: >0 = occluded (dyn_render_use_flow_consistency) */
+  const float* depth2;  /* [H,W]   frame 2 (nearest-sampled at uv2-0.5) */
+  const float* rgb2;    /* [H,W,3] frame 2 (bilinear)              */
+  const uint8_t* keep;  /* [H*W] or NULL: per-SOURCE-PIXEL outlier verdict (0 = drop), applied
+                           after the validity test (pgdvs_renderer_dyn.py:438-440) */
+  float M1[9];          /* c2w_1[:3,:3] @ inv(K_1[:3,:3])  (base.py:40-45) */
+  float o1[3];          /* c2w_1[:3,3]                              */
+  float K2inv[9];       /* inv(K_2[:3,:3])                         (dyn.py:362-365) */
+  float R2[9];          /* c2w_2[:3,:3]                             */
+  float o2[3];
+  float w1, w2;         /* (t2-t)/(t2-t1), (t-t1)/(t2-t1)          (dyn.py:385-386) */
+  int32_t same_time;    /* t1 == t2 -> pcl = pcl_1, rgb = rgb_1     (dyn.py:333-337) */
+  int32_t view;         /* index into cameras[] and the per-view outputs; non-decreasing */
+} PgdvsUwpJob;
+
+int pgdvs_uwp_workspace_bytes(int n_jobs, int H, int W, size_t* bytes);
+
+/*  jobs          device array [n_jobs], sorted by view
+ *  cameras       device array [n_views]
+ *  xyz_ndc       f32 [n_jobs*H*W, 3] capacity; packed NDC points (x, y, view z)
+ *  rgb           f32 [n_jobs*H*W, 3] capacity
+ *  xyz_world     f32 [.,3] or NULL;  src_pix i32 [.] or NULL (flat source pixel of each point)
+ *  first_idx/num_points  i64 [n_views] outputs (cloud_to_packed_first_idx / num_points_per_cloud)
+ *  total_points  i64 [1] device output
+ */
+int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras,
+                                 int n_views, int H, int W, float* xyz_ndc, float* rgb,
+                                 float* xyz_world, int32_t* src_pix, int64_t* first_idx,
+                                 int64_t* num_points, int64_t* total_points, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+/* World -> NDC only (PointsRasterizer.transform) for an already-built cloud, e.g. the one
+ * handed to render_dyn_pcl (pgdvs_renderer_dyn.py:671-724) or StaticGeoPointRenderer. */
+int pgdvs_project_points(const float* xyz_world, int64_t P, const PgdvsCamera* camera_dev,
+                         float* xyz_ndc, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * 5. dyn/track merge + static blend, channels-first like the reference:
+ *    mask_for_track = ~(dyn_mask>0) & (track_mask>0); rgb = (1-m)*dyn + m*track;
+ *    mask = dyn|track  (pgdvs_renderer_dyn.py:229-235);  then, if static_rgb != NULL,
+ *    combined = (1-mask)*static + mask*rgb (pgdvs_renderer.py:169-172).
+ *    dyn_rgb/track_rgb/static_rgb [B,3,H,W]; masks [B,1,H,W]; track_* may be NULL.
+ * ------------------------------------------------------------------------------------ */
+int pgdvs_merge_blend(const float* dyn_rgb, const float* dyn_mask, const float* track_rgb,
+                      const float* track_mask, const float* static_rgb, int B, int H, int W,
+                      float* out_rgb, float* out_mask, float* out_combined, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * 6. Statistical outlier support ("next" row 1 of the scope table): mean squared distance
+ *    from each query point to its K nearest reference points, dropping the first
+ *    `skip_first` of them.  Replaces `pytorch3d.ops.knn_points(q, r, K, return_nn=True)` +
+ *    `torch.mean(nn_dists[:, skip_first:], dim=1)` at pgdvs_renderer_dyn.py:405-419 and
+ *    pgdvs_renderer_dyn_track.py:303-318, 345-361.  K <= 64.
+ *    query f32 [Q,3], ref f32 [R,3] -> mean_out f32 [Q].
+ * ------------------------------------------------------------------------------------ */
+int pgdvs_knn_workspace_bytes(int64_t Q, int64_t R, size_t* bytes);
+int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* ref, int64_t R, int K,
+                        int skip_first, float* mean_out, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGDVS_B200_H_ */

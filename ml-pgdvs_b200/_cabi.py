@@ -1,0 +1,106 @@
+"""ctypes binding of include/pgdvs_b200.h (the drop-in C ABI).  No torch types cross this
+boundary: only raw device pointers, sizes and a CUDA stream handle.
+
+There is deliberately no CPU fallback: if the shared library is missing, importing any op
+raises immediately with the build command."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpgdvs_b200.so"
+
+COMPOSITE_NONE, COMPOSITE_ALPHA, COMPOSITE_NORM_WEIGHTED, COMPOSITE_WEIGHTED_SUM = 0, 1, 2, 3
+MAX_POINTS_PER_PIXEL = 150
+MAX_FUSED_CHANNELS = 4
+
+# every symbol include/pgdvs_b200.h declares (tests check the library exports each one)
+EXPORTED_SYMBOLS = (
+    "pgdvs_abi_version", "pgdvs_error_string", "pgdvs_struct_layout", "pgdvs_bin_workspace_bytes", "pgdvs_bin_points",
+    "pgdvs_rasterize_composite", "pgdvs_composite", "pgdvs_uwp_workspace_bytes",
+    "pgdvs_unproject_warp_project", "pgdvs_project_points", "pgdvs_merge_blend",
+    "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist",
+)
+
+
+class PgdvsCamera(ctypes.Structure):
+    _fields_ = [("R", c_float * 9), ("T", c_float * 3), ("focal", c_float * 2), ("p0", c_float * 2)]
+
+
+class PgdvsUwpJob(ctypes.Structure):
+    _fields_ = [
+        ("depth1", c_void_p), ("rgb1", c_void_p), ("mask1", c_void_p), ("flow12", c_void_p),
+        ("occ12", c_void_p), ("depth2", c_void_p), ("rgb2", c_void_p), ("keep", c_void_p),
+        ("M1", c_float * 9), ("o1", c_float * 3), ("K2inv", c_float * 9), ("R2", c_float * 9),
+        ("o2", c_float * 3), ("w1", c_float), ("w2", c_float), ("same_time", c_int32),
+        ("view", c_int32),
+    ]
+
+
+class PgdvsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing. pgdvs_b200 has no CPU fallback: build the sm_100a library first "
+            "with `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
+    L = ctypes.CDLL(str(LIB_PATH))
+    L.pgdvs_abi_version.restype = c_int
+    L.pgdvs_abi_version.argtypes = []
+    L.pgdvs_error_string.restype = c_char_p
+    L.pgdvs_error_string.argtypes = [c_int]
+    L.pgdvs_struct_layout.restype = c_int
+    L.pgdvs_struct_layout.argtypes = [POINTER(c_int32)]
+    L.pgdvs_bin_workspace_bytes.restype = c_int
+    L.pgdvs_bin_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int64, c_float, POINTER(c_size_t)]
+    L.pgdvs_bin_points.restype = c_int
+    L.pgdvs_bin_points.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int64,
+                                   c_void_p, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]
+    L.pgdvs_rasterize_composite.restype = c_int
+    L.pgdvs_rasterize_composite.argtypes = [
+        c_void_p, c_size_t, c_int, c_int64, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+        c_float, POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+        c_void_p]
+    L.pgdvs_composite.restype = c_int
+    L.pgdvs_composite.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_int64, c_int, c_void_p, c_void_p]
+    L.pgdvs_uwp_workspace_bytes.restype = c_int
+    L.pgdvs_uwp_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
+    L.pgdvs_unproject_warp_project.restype = c_int
+    L.pgdvs_unproject_warp_project.argtypes = [
+        c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.pgdvs_project_points.restype = c_int
+    L.pgdvs_project_points.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    L.pgdvs_merge_blend.restype = c_int
+    L.pgdvs_merge_blend.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.pgdvs_knn_workspace_bytes.restype = c_int
+    L.pgdvs_knn_workspace_bytes.argtypes = [c_int64, c_int64, POINTER(c_size_t)]
+    L.pgdvs_knn_mean_dist.restype = c_int
+    L.pgdvs_knn_mean_dist.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]
+    if L.pgdvs_abi_version() != 1:
+        raise ImportError("libpgdvs_b200.so ABI version mismatch; rebuild it")
+    lay = (c_int32 * 4)()
+    L.pgdvs_struct_layout(lay)
+    mine = [ctypes.sizeof(PgdvsCamera), ctypes.sizeof(PgdvsUwpJob), PgdvsUwpJob.M1.offset, PgdvsUwpJob.view.offset]
+    if list(lay) != mine:
+        raise ImportError(f"struct layout mismatch between _cabi.py {mine} and libpgdvs_b200.so {list(lay)}")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().pgdvs_error_string(rc).decode()
+        raise PgdvsError(f"{what} failed: {msg} (code {rc})")

@@ -1,0 +1,258 @@
+// Binning pass: exact count -> scan -> fill cell sort of a packed batch of NDC point clouds.
+//
+// The reference forces bin_size=0 (pgdvs_renderer_dyn.py:689-695) because pytorch3d's
+// coarse binning has a fixed max_points_per_bin that overflows on real clouds; here the
+// per-cell lists are sized exactly by a counting sort, so nothing can overflow.
+//
+//   k_count : one atomicAdd per point on its cell counter; the returned rank is kept so the
+//             fill pass needs no second atomic.
+//   k_scan  : single-pass chained scan (decoupled look-back) over the cell counters,
+//             warp-shuffle prefix sums inside a tile, int4-vectorised loads/stores.
+//   k_fill  : scatter (x,y,z,idx) and the feature record to start[cell] + rank.
+#include "common.cuh"
+
+namespace pgdvs {
+
+struct BinParams {
+  const float* points;
+  const float* features;
+  const float* radius;
+  const int64_t* first_idx;
+  const int64_t* num_points;
+  int C;
+  int H, W, halo, GW, GH;
+  float xf0, yf0;  // NDC centre of output column 0 / row 0
+  float inv_pix;   // pixels per NDC unit = min(H,W)/2
+  int* cell_start;
+  int2* rank;
+  float4* recA;
+  float4* recB;
+};
+
+// cell of the nearest pixel centre, in extended-grid coordinates; -1 if the point can
+// never be rasterized (behind the camera, or further than `halo` cells outside the image)
+__device__ __forceinline__ int point_cell(const BinParams& p, int n, float x, float y, float z) {
+  if (z < 0.0f) return -1;  // pytorch3d: `if (pz < 0) continue;`
+  // pixel centres: xf(col) = xf0 - col / inv_pix  ->  col = (xf0 - x) * inv_pix
+  const float colf = (p.xf0 - x) * p.inv_pix;
+  const float rowf = (p.yf0 - y) * p.inv_pix;
+  // NaN / huge coordinates fail these comparisons and are dropped (they can never satisfy
+  // dist2 < r2 either)
+  if (!(colf > -(float)p.halo - 1.0f && colf < (float)(p.W + p.halo))) return -1;
+  if (!(rowf > -(float)p.halo - 1.0f && rowf < (float)(p.H + p.halo))) return -1;
+  const int gx = __float2int_rn(colf) + p.halo;
+  const int gy = __float2int_rn(rowf) + p.halo;
+  if (gx < 0 || gx >= p.GW || gy < 0 || gy >= p.GH) return -1;
+  return (n * p.GH + gy) * p.GW + gx;
+}
+
+__global__ void __launch_bounds__(256) k_count(BinParams p) {
+  const int n = blockIdx.y;
+  const int64_t first = p.first_idx[n];
+  const int64_t num = p.num_points[n];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = first + i;
+    const float x = __ldg(p.points + q * 3 + 0);
+    const float y = __ldg(p.points + q * 3 + 1);
+    const float z = __ldg(p.points + q * 3 + 2);
+    const int cell = point_cell(p, n, x, y, z);
+    int rank = 0;
+    if (cell >= 0) rank = atomicAdd(p.cell_start + cell, 1);
+    p.rank[q] = make_int2(cell, rank);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fill(BinParams p) {
+  const int n = blockIdx.y;
+  const int64_t first = p.first_idx[n];
+  const int64_t num = p.num_points[n];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = first + i;
+    const int2 cr = p.rank[q];
+    if (cr.x < 0) continue;
+    const int pos = __ldg(p.cell_start + cr.x) + cr.y;
+    float4 a;
+    a.x = __ldg(p.points + q * 3 + 0);
+    a.y = __ldg(p.points + q * 3 + 1);
+    a.z = __ldg(p.points + q * 3 + 2);
+    a.w = __int_as_float((int)q);
+    p.recA[pos] = a;
+    if (p.features != nullptr || p.radius != nullptr) {
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.features != nullptr) {
+        for (int c = 0; c < p.C; ++c) f[c] = __ldg(p.features + q * p.C + c);
+      }
+      if (p.radius != nullptr) f[3] = __ldg(p.radius + q);
+      p.recB[pos] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// In-place exclusive scan, single pass with decoupled look-back.
+// state[t] = (flag << 32) | value; flag 1 = tile aggregate, 2 = inclusive prefix.
+// Tiles take their index from an atomic ticket so a tile's predecessors are always
+// already running (forward progress without relying on block scheduling order).
+// ---------------------------------------------------------------------------------------
+constexpr unsigned long long kFlagAgg = 1ull << 32;
+constexpr unsigned long long kFlagPrefix = 2ull << 32;
+
+__global__ void __launch_bounds__(1024) k_scan(int* data, unsigned long long* state, int* ticket) {
+  __shared__ int s_tile;
+  __shared__ int s_warp[32];
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = s_tile;
+  int4* base = reinterpret_cast<int4*>(data + (int64_t)tile * kScanTile);
+  int4 v = base[threadIdx.x];
+  const int t_sum = v.x + v.y + v.z + v.w;
+  // warp inclusive scan of per-thread sums
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = t_sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+    int winc = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += o;
+    }
+    s_warp[lane] = winc - w;  // exclusive offset of each warp
+    const int aggregate = __shfl_sync(0xffffffffu, winc, 31);
+    // publish the aggregate, then look back for the exclusive prefix of this tile
+    int prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(state + tile, kFlagPrefix | (unsigned int)aggregate);
+    } else {
+      if (lane == 0) atomicExch(state + tile, kFlagAgg | (unsigned int)aggregate);
+      int look = tile - 1;
+      while (true) {
+        const int idx = look - lane;
+        unsigned long long st = kFlagPrefix;  // lanes past the start behave like a zero prefix
+        if (idx >= 0) {
+          do {
+            st = *reinterpret_cast<volatile unsigned long long*>(state + idx);
+          } while ((st >> 32) == 0);
+        }
+        const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+        int val = (int)(unsigned int)(st & 0xffffffffull);
+        if (has_prefix) {
+          const int firstp = __ffs(has_prefix) - 1;  // nearest tile that has a full prefix
+          if (lane > firstp) val = 0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+        prefix += val;
+        if (has_prefix) break;
+        look -= 32;
+      }
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(state + tile, kFlagPrefix | (unsigned int)(prefix + aggregate));
+      }
+    }
+    if (lane == 0) s_prefix = prefix;
+  }
+  __syncthreads();
+  const int excl = s_prefix + s_warp[warp] + (inc - t_sum);
+  int4 o;
+  o.x = excl;
+  o.y = excl + v.x;
+  o.z = o.y + v.y;
+  o.w = o.z + v.z;
+  base[threadIdx.x] = o;
+}
+
+}  // namespace pgdvs
+
+using namespace pgdvs;
+
+extern "C" int pgdvs_bin_workspace_bytes(int N, int H, int W, int64_t P, float radius_max,
+                                         size_t* bytes) {
+  if (bytes == nullptr || N < 0 || H <= 0 || W <= 0 || P < 0 || !(radius_max >= 0.0f))
+    return PGDVS_E_BADARG;
+  BinLayout L = make_bin_layout(N, H, W, P, radius_max);
+  if (L.cells + kScanTile >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  *bytes = L.total;
+  return PGDVS_OK;
+}
+
+extern "C" int pgdvs_bin_points(const float* points, const float* features, int C,
+                                const int64_t* first_idx, const int64_t* num_points, int N,
+                                int64_t P, const float* radius, float radius_max, int H, int W,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (N < 0 || H <= 0 || W <= 0 || P < 0 || !(radius_max >= 0.0f) || workspace == nullptr)
+    return PGDVS_E_BADARG;
+  if (P >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  if (features != nullptr && (C < 1 || C > PGDVS_MAX_FUSED_CHANNELS)) return PGDVS_E_CHANNELS;
+  if (features != nullptr && radius != nullptr && C > 3) return PGDVS_E_CHANNELS;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;
+  BinLayout L = make_bin_layout(N, H, W, P, radius_max);
+  if (L.cells + kScanTile >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  if (workspace_bytes < L.total) return PGDVS_E_WORKSPACE;
+  if (N == 0) return PGDVS_OK;
+  if (P > 0 && (points == nullptr || first_idx == nullptr || num_points == nullptr))
+    return PGDVS_E_BADARG;
+
+  char* ws = static_cast<char*>(workspace);
+  BinParams p;
+  p.points = points;
+  p.features = features;
+  p.radius = radius;
+  p.first_idx = first_idx;
+  p.num_points = num_points;
+  p.C = features ? C : 0;
+  p.H = H;
+  p.W = W;
+  p.halo = L.halo;
+  p.GW = L.GW;
+  p.GH = L.GH;
+  const NdcAxis ax = make_ndc_axis(W, H), ay = make_ndc_axis(H, W);
+  // centre of output column 0 is PixToNonSquareNdc(W-1, W, H) (host evaluation, fp32)
+  p.xf0 = -ax.offset + (ax.range * (float)(W - 1) + ax.offset) / (float)W;
+  p.yf0 = -ay.offset + (ay.range * (float)(H - 1) + ay.offset) / (float)H;
+  p.inv_pix = 0.5f * (float)(H < W ? H : W);
+  p.cell_start = reinterpret_cast<int*>(ws + L.off_start);
+  p.rank = reinterpret_cast<int2*>(ws + L.off_rank);
+  p.recA = reinterpret_cast<float4*>(ws + L.off_recA);
+  p.recB = reinterpret_cast<float4*>(ws + L.off_recB);
+
+  // counters, scan state and ticket are contiguous at the front of the workspace
+  cudaError_t e = cudaMemsetAsync(ws + L.off_start, 0, L.off_rank - L.off_start, stream);
+  if (e != cudaSuccess) return (int)e;
+  if (P > 0) {
+    // enough blocks to fill the machine even for one cloud; grid-stride inside
+    int64_t per_cloud = (P + (N > 0 ? N : 1) - 1) / (N > 0 ? N : 1);
+    int gx = (int)((per_cloud + 255) / 256);
+    if (gx < 1) gx = 1;
+    if (gx > 148 * 16) gx = 148 * 16;
+    dim3 grid(gx, N);
+    k_count<<<grid, 256, 0, stream>>>(p);
+    if (int rc = check_launch()) return rc;
+  }
+  k_scan<<<(unsigned)L.n_tiles, 1024, 0, stream>>>(
+      p.cell_start, reinterpret_cast<unsigned long long*>(ws + L.off_state),
+      reinterpret_cast<int*>(ws + L.off_ticket));
+  if (int rc = check_launch()) return rc;
+  if (P > 0) {
+    int64_t per_cloud = (P + N - 1) / N;
+    int gx = (int)((per_cloud + 255) / 256);
+    if (gx < 1) gx = 1;
+    if (gx > 148 * 16) gx = 148 * 16;
+    dim3 grid(gx, N);
+    k_fill<<<grid, 256, 0, stream>>>(p);
+    if (int rc = check_launch()) return rc;
+  }
+  return PGDVS_OK;
+}

@@ -1,0 +1,128 @@
+// Shared device/host helpers for the PGDVS point-splat kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/pgdvs_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "pgdvs_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace pgdvs {
+
+// ---------------------------------------------------------------------------------------
+// Pixel-centre NDC coordinates, bit-identical to pytorch3d's PixToNonSquareNdc
+// (rasterization_utils.cuh; restated in oracle/raster_cpu.cpp).  Every operation is an
+// explicitly rounded fp32 op so that nvcc cannot contract a*b+c into an FMA.
+// ---------------------------------------------------------------------------------------
+struct NdcAxis {
+  float range;   // NonSquareNdcRange(S1, S2)
+  float offset;  // range / 2
+  int S1;
+};
+
+inline NdcAxis make_ndc_axis(int S1, int S2) {
+  NdcAxis a;
+  float range = 2.0f;
+  if (S1 > S2) range = ((float)S1 * range) / (float)S2;
+  a.range = range;
+  a.offset = range / 2.0f;
+  a.S1 = S1;
+  return a;
+}
+
+// centre of pixel `pix` (0 = left/top of the OUTPUT image; pytorch3d flips both axes)
+__device__ __forceinline__ float pixel_center_ndc(const NdcAxis& a, int pix) {
+  const int i = a.S1 - 1 - pix;
+  const float t = __fadd_rn(__fmul_rn(a.range, (float)i), a.offset);
+  return __fadd_rn(-a.offset, __fdiv_rn(t, (float)a.S1));
+}
+
+// squared NDC distance exactly as the x86 build of pytorch3d evaluates it:
+// dx*dx + dy*dy with two roundings (no FMA)
+__device__ __forceinline__ float dist2_rn(float px, float py, float xf, float yf) {
+  const float dx = __fsub_rn(px, xf);
+  const float dy = __fsub_rn(py, yf);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+// ---------------------------------------------------------------------------------------
+// Workspace layout of the binning pass (all offsets 256-byte aligned).
+//
+// The image is covered by 1-pixel cells; the grid is extended by `halo` cells on every
+// side so that a pixel's candidate window [x-halo, x+halo] never needs clamping.  A point
+// is filed under the cell of its NEAREST pixel centre, so every pixel it can hit lies
+// within halo = floor(r_px + 0.5 + 1/64) cells of that cell (r_px = radius in pixels; the
+// 1/64 absorbs the fp32 error of the cell computation for images up to 16k pixels wide).
+// Cells are numbered view-major, row-major: one image row of a tile (plus halo) is ONE
+// contiguous run of the cell-sorted record arrays — that is what lets the rasterizer
+// fetch tile rows with 1-D bulk copies.
+// ---------------------------------------------------------------------------------------
+struct BinLayout {
+  int halo, GW, GH;
+  int64_t cells;      // N * GH * GW
+  int64_t n_tiles;    // scan tiles
+  size_t off_start;   // int32 [cells + 1]   counts, then exclusive starts (in place)
+  size_t off_state;   // uint64 [n_tiles]    decoupled look-back state
+  size_t off_ticket;  // int32 [4]           scan ticket counter (+pad)
+  size_t off_rank;    // int2  [P]           (cell, rank within cell) per packed point
+  size_t off_recA;    // float4 [P]          (x_ndc, y_ndc, z, packed idx as int bits)
+  size_t off_recB;    // float4 [P]          features (C<=4) or (f0,f1,f2,radius)
+  size_t total;
+};
+
+constexpr int kScanTile = 4096;  // ints per scan tile (1024 threads x int4)
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+inline int halo_cells(float radius_max, int H, int W) {
+  const float s = 0.5f * (float)(H < W ? H : W);
+  const float r_px = fabsf(radius_max) * s;
+  return (int)floorf(r_px + 0.5f + 1.0f / 64.0f);
+}
+
+inline BinLayout make_bin_layout(int N, int H, int W, int64_t P, float radius_max) {
+  BinLayout L;
+  L.halo = halo_cells(radius_max, H, W);
+  L.GW = W + 2 * L.halo;
+  L.GH = H + 2 * L.halo;
+  L.cells = (int64_t)N * L.GH * L.GW;
+  L.n_tiles = (L.cells + 1 + kScanTile - 1) / kScanTile;
+  size_t o = 0;
+  L.off_start = o;
+  o = align256(o + sizeof(int32_t) * (size_t)(L.n_tiles * kScanTile));
+  L.off_state = o;
+  o = align256(o + sizeof(uint64_t) * (size_t)L.n_tiles);
+  L.off_ticket = o;
+  o = align256(o + 256);
+  L.off_rank = o;
+  o = align256(o + sizeof(int2) * (size_t)(P > 0 ? P : 1));
+  L.off_recA = o;
+  o = align256(o + sizeof(float4) * (size_t)(P > 0 ? P : 1));
+  L.off_recB = o;
+  o = align256(o + sizeof(float4) * (size_t)(P > 0 ? P : 1));
+  L.total = o;
+  return L;
+}
+
+// PointsRasterizer.transform for PerspectiveCameras(in_ndc=True):
+//   view = p @ R + T ; x = (fx*X + px*Z)/Z ; y = (fy*Y + py*Z)/Z ; z = Z (view depth)
+__device__ __forceinline__ float3 world_to_ndc(const PgdvsCamera& c, float wx, float wy, float wz) {
+  const float X = wx * c.R[0] + wy * c.R[3] + wz * c.R[6] + c.T[0];
+  const float Y = wx * c.R[1] + wy * c.R[4] + wz * c.R[7] + c.T[1];
+  const float Z = wx * c.R[2] + wy * c.R[5] + wz * c.R[8] + c.T[2];
+  float3 o;
+  o.x = (c.focal[0] * X + c.p0[0] * Z) / Z;
+  o.y = (c.focal[1] * Y + c.p0[1] * Z) / Z;
+  o.z = Z;
+  return o;
+}
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace pgdvs

@@ -1,0 +1,101 @@
+// Statistical-outlier support: mean squared distance to the K nearest neighbours.
+//
+// Replaces `pytorch3d.ops.knn_points(p1, p2, K=knn+1, return_nn=True)` followed by
+// `torch.mean(nn_dists[..., skip:], dim=1)` at pgdvs_renderer_dyn.py:405-419 and
+// pgdvs_renderer_dyn_track.py:303-318, 345-361 (squared L2, ascending, brute force).
+// Only the K smallest squared distances are needed (not the indices / neighbours, which the
+// reference computes and discards), so each query keeps a sorted K-list of distances in
+// registers while reference points stream through shared memory in float4 tiles.
+#include "common.cuh"
+
+namespace pgdvs {
+
+constexpr int kKnnThreads = 128;
+constexpr int kKnnTile = 1024;
+constexpr int kKnnMaxK = 64;
+
+__global__ void __launch_bounds__(kKnnThreads) k_knn_mean(const float* __restrict__ query, int64_t Q,
+                                                          const float* __restrict__ ref, int64_t R,
+                                                          int K, int skip, float* __restrict__ out) {
+  __shared__ float4 tile[kKnnTile];
+  const int64_t qi = (int64_t)blockIdx.x * kKnnThreads + threadIdx.x;
+  const bool active = qi < Q;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (active) {
+    qx = __ldg(query + qi * 3 + 0);
+    qy = __ldg(query + qi * 3 + 1);
+    qz = __ldg(query + qi * 3 + 2);
+  }
+  float best[kKnnMaxK];
+#pragma unroll
+  for (int i = 0; i < kKnnMaxK; ++i) best[i] = __int_as_float(0x7f800000);
+  // only the first K slots matter; kth = best[K-1] is tracked in a scalar
+  float kth = __int_as_float(0x7f800000);
+
+  for (int64_t base = 0; base < R; base += kKnnTile) {
+    const int n = (int)((R - base) < kKnnTile ? (R - base) : kKnnTile);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kKnnThreads) {
+      const float* r = ref + (base + i) * 3;
+      tile[i] = make_float4(__ldg(r), __ldg(r + 1), __ldg(r + 2), 0.f);
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int i = 0; i < n; ++i) {
+      const float4 r = tile[i];
+      const float dx = qx - r.x, dy = qy - r.y, dz = qz - r.z;
+      const float d = dx * dx + dy * dy + dz * dz;
+      if (d < kth) {
+        // sorted insert into best[0..K-1]
+        float c = d;
+#pragma unroll
+        for (int j = 0; j < kKnnMaxK; ++j) {
+          if (j < K) {
+            const float b = best[j];
+            const bool lt = c < b;
+            best[j] = lt ? c : b;
+            c = lt ? b : c;
+          }
+        }
+        // kth = best[K-1]
+        float k2 = best[0];
+#pragma unroll
+        for (int j = 1; j < kKnnMaxK; ++j)
+          if (j == K - 1) k2 = best[j];
+        kth = k2;
+      }
+    }
+  }
+  if (!active) return;
+  const int kk = (int)(R < (int64_t)K ? R : (int64_t)K);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kKnnMaxK; ++j)
+    if (j >= skip && j < kk) sum += best[j];
+  const int cnt = kk - skip;
+  out[qi] = cnt > 0 ? sum / (float)cnt : 0.f;
+}
+
+}  // namespace pgdvs
+
+using namespace pgdvs;
+
+extern "C" int pgdvs_knn_workspace_bytes(int64_t Q, int64_t R, size_t* bytes) {
+  if (!bytes || Q < 0 || R < 0) return PGDVS_E_BADARG;
+  *bytes = 256;  // brute-force version needs no scratch; kept for ABI stability
+  return PGDVS_OK;
+}
+
+extern "C" int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* ref, int64_t R, int K,
+                                   int skip_first, float* mean_out, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  if (Q < 0 || R < 0 || K < 1 || skip_first < 0) return PGDVS_E_BADARG;
+  if (K > kKnnMaxK) return PGDVS_E_K_TOO_LARGE;
+  if (Q == 0) return PGDVS_OK;
+  if (!query || !mean_out || (R > 0 && !ref)) return PGDVS_E_BADARG;
+  const unsigned grid = (unsigned)((Q + kKnnThreads - 1) / kKnnThreads);
+  k_knn_mean<<<grid, kKnnThreads, 0, (cudaStream_t)stream>>>(query, Q, ref, R, K, skip_first, mean_out);
+  return check_launch();
+}

@@ -1,0 +1,290 @@
+"""L1 operators: the pytorch3d `_C`-level call surface the PGDVS dynamic renderer reaches
+(/root/reference/pgdvs/renderers/pgdvs_renderer_dyn.py:684-722), backed by the sm_100a C ABI.
+
+    rasterize_points_packed(...)  ~ pytorch3d._C.rasterize_points        -> idx, zbuf, dists
+    alpha_composite / norm_weighted_sum / weighted_sum                   -> [N,C,H,W]
+    render_packed(...)            fused bin + rasterize + composite (+mask, +blend)
+    project_points / knn_mean_dist / merge_blend
+
+torch is used for device memory and streams only; every computation happens in
+libpgdvs_b200.so.  CPU tensors are rejected: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _cabi
+
+_COMPOSITORS = {
+    None: _cabi.COMPOSITE_NONE, "none": _cabi.COMPOSITE_NONE,
+    "alpha": _cabi.COMPOSITE_ALPHA, "alpha_composite": _cabi.COMPOSITE_ALPHA,
+    "norm": _cabi.COMPOSITE_NORM_WEIGHTED, "norm_weighted_sum": _cabi.COMPOSITE_NORM_WEIGHTED,
+    "wsum": _cabi.COMPOSITE_WEIGHTED_SUM, "weighted_sum": _cabi.COMPOSITE_WEIGHTED_SUM,
+}
+
+kMaxPointsPerPixel = _cabi.MAX_POINTS_PER_PIXEL
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"pgdvs_b200: `{name}` must be a CUDA tensor — this package is CUDA-only (sm_100a) and "
+            "has no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.float32).contiguous()
+
+
+def parse_image_size(image_size) -> Tuple[int, int]:
+    """pytorch3d.renderer.utils.parse_image_size: int or (H, W)."""
+    if not isinstance(image_size, (tuple, list)):
+        return (int(image_size), int(image_size))
+    if len(image_size) != 2:
+        raise ValueError("Image size can only be a tuple/list of (H, W)")
+    if not all(i > 0 for i in image_size):
+        raise ValueError("Image sizes must be greater than 0; got %d, %d" % tuple(image_size))
+    if not all(isinstance(i, int) for i in image_size):
+        raise ValueError("Image sizes must be integers; got %r, %r" % tuple(image_size))
+    return tuple(image_size)
+
+
+class _Workspace:
+    """Per-device scratch arena, grown geometrically and reused across calls (no per-call
+    cudaMalloc on the hot path)."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, device, nbytes: int, tag: str = "bin") -> torch.Tensor:
+        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        buf = self._buf.get(key)
+        if buf is None or buf.numel() < nbytes:
+            cap = max(nbytes, int(1.25 * buf.numel()) if buf is not None else 0)
+            buf = torch.empty(cap + 256, dtype=torch.uint8, device=device)
+            self._buf[key] = buf
+        return buf
+
+
+_WS = _Workspace()
+
+
+def _aligned_ptr(buf: torch.Tensor) -> int:
+    p = buf.data_ptr()
+    return (p + 255) & ~255
+
+
+def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
+                  first_idx: torch.Tensor, num_points: torch.Tensor, image_size,
+                  radius: Union[float, torch.Tensor], points_per_pixel: int,
+                  compositor: Optional[str] = "norm", background: Optional[Sequence[float]] = None,
+                  static_rgb: Optional[torch.Tensor] = None, return_fragments: bool = True,
+                  return_mask: bool = True, rr_weight: Optional[float] = None):
+    """Fused bin -> rasterize -> composite of a packed batch of NDC clouds.
+
+    points_ndc [P,3] (NDC x, NDC y, view z), features [P,C] (C<=4) or None, first_idx /
+    num_points int64 [N].  Returns a dict with idx/zbuf/dists [N,H,W,K] (if requested),
+    image [N,H,W,C] and mask [N,H,W,1] (if a compositor is selected).
+    """
+    _require_cuda(points_ndc, "points")
+    dev = points_ndc.device
+    H, W = parse_image_size(image_size)
+    K = int(points_per_pixel)
+    if K > kMaxPointsPerPixel:
+        raise ValueError("Must have points_per_pixel <= %d" % kMaxPointsPerPixel)
+    if K < 1:
+        raise ValueError("points_per_pixel must be >= 1")
+    points_ndc = _f32c(points_ndc).reshape(-1, 3)
+    P = points_ndc.shape[0]
+    first_idx = first_idx.to(device=dev, dtype=torch.int64).contiguous()
+    num_points = num_points.to(device=dev, dtype=torch.int64).contiguous()
+    N = first_idx.shape[0]
+    mode = _COMPOSITORS[compositor]
+    radius_t = None
+    if torch.is_tensor(radius):
+        if radius.shape != (P,):
+            raise ValueError("Radius must be of shape (P,): got %s" % repr(tuple(radius.shape)))
+        radius_t = _f32c(radius.to(dev))
+        radius_max = float(radius_t.max().item()) if P > 0 else 0.0
+        if rr_weight is None and mode != _cabi.COMPOSITE_NONE:
+            raise ValueError("fused compositing with a per-point radius needs an explicit rr_weight")
+    else:
+        radius_max = float(radius)
+    C = 0
+    feats = None
+    if mode != _cabi.COMPOSITE_NONE:
+        if features is None:
+            raise ValueError("a compositor needs per-point features")
+        feats = _f32c(features.to(dev))
+        if feats.ndim != 2 or feats.shape[0] != P:
+            raise ValueError("features must be [P, C]")
+        C = feats.shape[1]
+        if C > _cabi.MAX_FUSED_CHANNELS or (radius_t is not None and C > 3):
+            raise ValueError("fused compositing supports at most 4 channels (3 with per-point radii); "
+                             "use rasterize_points + a stand-alone compositor")
+        if rr_weight is None:
+            # PointsRenderer: weights = 1 - dists2 / (r * r) with a Python-float r
+            rr_weight = float(radius) * float(radius)
+    L = _cabi.lib()
+    nbytes = ctypes.c_size_t(0)
+    _cabi.check(L.pgdvs_bin_workspace_bytes(N, H, W, P, radius_max, ctypes.byref(nbytes)),
+                "pgdvs_bin_workspace_bytes")
+    ws = _WS.get(dev, nbytes.value)
+    ws_ptr = _aligned_ptr(ws)
+    stream = _stream_ptr(dev)
+    with torch.cuda.device(dev):
+        _cabi.check(L.pgdvs_bin_points(
+            points_ndc.data_ptr(), feats.data_ptr() if feats is not None else None, C,
+            first_idx.data_ptr(), num_points.data_ptr(), N, P,
+            radius_t.data_ptr() if radius_t is not None else None, radius_max, H, W, ws_ptr,
+            nbytes.value, stream), "pgdvs_bin_points")
+        out = {}
+        idx = zbuf = dists = image = mask = None
+        if return_fragments:
+            idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
+            zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+            dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        if mode != _cabi.COMPOSITE_NONE:
+            image = torch.empty((N, H, W, C), dtype=torch.float32, device=dev)
+            if return_mask or static_rgb is not None:
+                mask = torch.empty((N, H, W, 1), dtype=torch.float32, device=dev)
+        bg = None
+        if background is not None and mode != _cabi.COMPOSITE_NONE:
+            vals = [float(b) for b in background][:C]
+            if len(vals) != C:
+                raise ValueError("background color must have %d channels" % C)
+            bg = (ctypes.c_float * 4)(*(vals + [0.0] * (4 - C)))
+        st = None
+        if static_rgb is not None:
+            _require_cuda(static_rgb, "static_rgb")
+            st = _f32c(static_rgb)
+            if tuple(st.shape) != (N, H, W, C):
+                raise ValueError("static_rgb must be [N,H,W,C]")
+        _cabi.check(L.pgdvs_rasterize_composite(
+            ws_ptr, nbytes.value, N, P, H, W, K, radius_max, 1 if radius_t is not None else 0, C, mode,
+            float(rr_weight) if rr_weight is not None else 1.0, bg,
+            st.data_ptr() if st is not None else None,
+            idx.data_ptr() if idx is not None else None,
+            zbuf.data_ptr() if zbuf is not None else None,
+            dists.data_ptr() if dists is not None else None,
+            image.data_ptr() if image is not None else None,
+            mask.data_ptr() if mask is not None else None, stream), "pgdvs_rasterize_composite")
+    out.update(idx=idx, zbuf=zbuf, dists=dists, image=image, mask=mask)
+    return out
+
+
+def rasterize_points_packed(points_packed, cloud_to_packed_first_idx, num_points_per_cloud,
+                            image_size, radius, points_per_pixel: int = 8, bin_size=None,
+                            max_points_per_bin=None):
+    """pytorch3d `_C.rasterize_points` surface.  `bin_size` / `max_points_per_bin` are accepted
+    for signature compatibility (PGDVS passes bin_size=0); the tiled kernel is exact for any
+    value, so they only undergo pytorch3d's argument validation."""
+    H, W = parse_image_size(image_size)
+    if bin_size is not None and bin_size != 0:
+        if bin_size < 0:
+            raise ValueError("bin_size must be >= 0")
+        if 1 + (max(H, W) - 1) // bin_size >= 22:  # kMaxPointsPerBin
+            raise ValueError("bin_size too small, number of bins must be less than 22; got %d"
+                             % (1 + (max(H, W) - 1) // bin_size))
+    out = render_packed(points_packed, None, cloud_to_packed_first_idx, num_points_per_cloud,
+                        (H, W), radius, points_per_pixel, compositor=None)
+    return out["idx"], out["zbuf"], out["dists"]
+
+
+def _composite(pointsidx, alphas, pt_clds, mode):
+    _require_cuda(alphas, "alphas")
+    dev = alphas.device
+    idx = pointsidx.to(device=dev, dtype=torch.int64).contiguous()
+    alphas = _f32c(alphas)
+    feats = _f32c(pt_clds.to(dev))
+    if idx.shape != alphas.shape or idx.ndim != 4:
+        raise ValueError("pointsidx and alphas must both be [N,K,H,W]")
+    N, K, H, W = idx.shape
+    C, P = feats.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().pgdvs_composite(idx.data_ptr(), alphas.data_ptr(), feats.data_ptr(),
+                                                N, K, H, W, C, P, mode, out.data_ptr(),
+                                                _stream_ptr(dev)), "pgdvs_composite")
+    return out
+
+
+def alpha_composite(pointsidx, alphas, pt_clds):
+    """pytorch3d.renderer.compositing.alpha_composite (forward)."""
+    return _composite(pointsidx, alphas, pt_clds, _cabi.COMPOSITE_ALPHA)
+
+
+def norm_weighted_sum(pointsidx, alphas, pt_clds):
+    """pytorch3d.renderer.compositing.norm_weighted_sum (forward)."""
+    return _composite(pointsidx, alphas, pt_clds, _cabi.COMPOSITE_NORM_WEIGHTED)
+
+
+def weighted_sum(pointsidx, alphas, pt_clds):
+    """pytorch3d.renderer.compositing.weighted_sum (forward)."""
+    return _composite(pointsidx, alphas, pt_clds, _cabi.COMPOSITE_WEIGHTED_SUM)
+
+
+def camera_struct_tensor(R_p3d, T_p3d, focal, p0, device) -> torch.Tensor:
+    """Pack pytorch3d-convention camera(s) into device PgdvsCamera structs: f32 [n,16]."""
+    R = torch.as_tensor(R_p3d, dtype=torch.float32).reshape(-1, 9)
+    T = torch.as_tensor(T_p3d, dtype=torch.float32).reshape(-1, 3)
+    f = torch.as_tensor(focal, dtype=torch.float32).reshape(-1, 2)
+    p = torch.as_tensor(p0, dtype=torch.float32).reshape(-1, 2)
+    return torch.cat([R.cpu(), T.cpu(), f.cpu(), p.cpu()], dim=1).contiguous().to(device)
+
+
+def project_points(xyz_world: torch.Tensor, camera_dev: torch.Tensor) -> torch.Tensor:
+    """PointsRasterizer.transform: world -> (x_ndc, y_ndc, z_view) for one camera struct [16]."""
+    _require_cuda(xyz_world, "xyz_world")
+    dev = xyz_world.device
+    xyz = _f32c(xyz_world).reshape(-1, 3)
+    out = torch.empty_like(xyz)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().pgdvs_project_points(xyz.data_ptr(), xyz.shape[0],
+                                                     camera_dev.data_ptr(), out.data_ptr(),
+                                                     _stream_ptr(dev)), "pgdvs_project_points")
+    return out
+
+
+def knn_mean_dist(query: torch.Tensor, ref: torch.Tensor, K: int, skip_first: int = 0) -> torch.Tensor:
+    """mean_k d2(query, kNN_k(ref)) over k in [skip_first, K) — knn_points + mean of the reference."""
+    _require_cuda(query, "query")
+    dev = query.device
+    q = _f32c(query).reshape(-1, 3)
+    r = _f32c(ref.to(dev)).reshape(-1, 3)
+    out = torch.empty((q.shape[0],), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().pgdvs_knn_mean_dist(q.data_ptr(), q.shape[0], r.data_ptr(), r.shape[0],
+                                                    int(K), int(skip_first), out.data_ptr(), None, 0,
+                                                    _stream_ptr(dev)), "pgdvs_knn_mean_dist")
+    return out
+
+
+def merge_blend(dyn_rgb, dyn_mask, track_rgb=None, track_mask=None, static_rgb=None):
+    """pgdvs_renderer_dyn.py:229-235 (+ pgdvs_renderer.py:169-172 when static_rgb is given).
+    Channels-first [B,3,H,W] / [B,1,H,W].  Returns (rgb, mask, combined-or-None)."""
+    _require_cuda(dyn_rgb, "dyn_rgb")
+    dev = dyn_rgb.device
+    dyn_rgb, dyn_mask = _f32c(dyn_rgb), _f32c(dyn_mask)
+    B, _, H, W = dyn_rgb.shape
+    tr = _f32c(track_rgb) if track_rgb is not None else None
+    tm = _f32c(track_mask) if track_mask is not None else None
+    st = _f32c(static_rgb) if static_rgb is not None else None
+    out_rgb = torch.empty_like(dyn_rgb)
+    out_mask = torch.empty_like(dyn_mask)
+    out_comb = torch.empty_like(dyn_rgb) if st is not None else None
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().pgdvs_merge_blend(
+            dyn_rgb.data_ptr(), dyn_mask.data_ptr(), tr.data_ptr() if tr is not None else None,
+            tm.data_ptr() if tm is not None else None, st.data_ptr() if st is not None else None,
+            B, H, W, out_rgb.data_ptr(), out_mask.data_ptr(),
+            out_comb.data_ptr() if out_comb is not None else None, _stream_ptr(dev)),
+            "pgdvs_merge_blend")
+    return out_rgb, out_mask, out_comb

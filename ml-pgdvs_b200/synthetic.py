@@ -1,0 +1,190 @@
+"""Synthetic workloads of the five BASELINE.json configs.
+
+Shapes, dtypes and layouts follow the reference's data dict
+(/root/reference/pgdvs/datasets/nvidia_eval.py:545-604): channels-last fp32 maps, flow in
+pixels (+u right / +v down), OpenCV K / c2w, frame ids as float times.  Data generation is
+not part of the measured path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .dyn_renderer import SourcePair
+
+CONFIGS: Dict[str, dict] = {
+    # name: H, W, frames, sources per view (S), K, radius, default #views
+    "c1_nvidia_1view": dict(H=288, W=544, frames=2, S=2, K=8, radius=0.01, views=1),
+    "c2_nvidia_seq": dict(H=288, W=544, frames=12, S=2, K=8, radius=0.01, views=144),
+    "c3_iphone": dict(H=360, W=480, frames=8, S=6, K=16, radius=0.01, views=16),
+    "c4_davis": dict(H=480, W=854, frames=80, S=2, K=8, radius=0.01, views=80),
+    "c5_stress": dict(H=1080, W=1920, frames=9, S=8, K=8, radius=0.01, views=8),
+    "tiny": dict(H=24, W=40, frames=3, S=2, K=4, radius=0.06, views=3),
+}
+
+
+@dataclass
+class Scene:
+    H: int
+    W: int
+    rgb: torch.Tensor        # [F,H,W,3]
+    depth: torch.Tensor      # [F,H,W,1]
+    mask: torch.Tensor       # [F,H,W,1]
+    flow_next: torch.Tensor  # [F,H,W,2] flow frame f -> f+1 (last: -> f-1)
+    flow_prev: torch.Tensor  # [F,H,W,2] flow frame f -> f-1 (first: -> f+1)
+    K: np.ndarray            # [4,4]
+    c2w: np.ndarray          # [F,4,4]
+    times: np.ndarray        # [F]
+
+
+@dataclass
+class Workload:
+    name: str
+    H: int
+    W: int
+    K: int
+    radius: float
+    scene: Scene
+    view_pairs: List[List[SourcePair]]          # per view: S source pairs (view index = 0 in each)
+    view_cams: List[Tuple[np.ndarray, np.ndarray]]  # per view (K44, c2w44)
+    static_rgb: Optional[torch.Tensor] = None   # [V,H,W,3] stand-in for the GNT static render
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_views(self):
+        return len(self.view_pairs)
+
+    def jobs(self, views: Sequence[int]):
+        """Flatten the selected views into (pairs sorted by local view index, cams)."""
+        pairs, cams = [], []
+        for local, v in enumerate(views):
+            for p in self.view_pairs[v]:
+                q = SourcePair.__new__(SourcePair)
+                q.__dict__.update(p.__dict__)
+                q.view = local
+                pairs.append(q)
+            cams.append(self.view_cams[v])
+        return pairs, cams
+
+    def points_per_view(self):
+        return len(self.view_pairs[0]) * self.H * self.W
+
+
+def _box_smooth(x: torch.Tensor, k: int = 9) -> torch.Tensor:
+    # x [F,H,W,1] -> 9x9 box filter (plausible surfaces keep z-ties / KNN realistic)
+    y = x.permute(0, 3, 1, 2)
+    y = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(y, (k // 2,) * 4, mode="replicate"), k, stride=1)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _rot_y(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32)
+
+
+def _rot_x(a):
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]], np.float32)
+
+
+def make_scene(H, W, frames, device, seed=1234, mask_mode="full", flow_std=3.0, smooth=True) -> Scene:
+    g = torch.Generator(device=device).manual_seed(seed)
+    rgb = torch.rand((frames, H, W, 3), generator=g, device=device)
+    depth = 1.0 + 9.0 * torch.rand((frames, H, W, 1), generator=g, device=device)
+    if smooth:
+        depth = _box_smooth(depth)
+    if mask_mode == "full":
+        mask = torch.ones((frames, H, W, 1), device=device)
+    elif mask_mode == "ellipse":  # centred ellipse covering ~15 % of the pixels
+        yy, xx = torch.meshgrid(torch.arange(H, device=device), torch.arange(W, device=device), indexing="ij")
+        a, b = 0.31 * W / 2 * 1.4, 0.31 * H / 2 * 1.4
+        m = (((xx - W / 2) / a) ** 2 + ((yy - H / 2) / b) ** 2) < 1.0
+        mask = m.float()[None, :, :, None].repeat(frames, 1, 1, 1)
+    else:
+        raise ValueError(mask_mode)
+
+    def flow():
+        f = flow_std * torch.randn((frames, H, W, 2), generator=g, device=device)
+        uu = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
+        vv = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
+        # clip so that uv + flow stays inside the image (most points survive the validity test)
+        f[..., 0] = torch.minimum(torch.maximum(f[..., 0], -uu), (W - 1) - uu)
+        f[..., 1] = torch.minimum(torch.maximum(f[..., 1], -vv), (H - 1) - vv)
+        return f.contiguous()
+
+    Kmat = np.eye(4, dtype=np.float32)
+    Kmat[0, 0] = Kmat[1, 1] = 0.9 * W
+    Kmat[0, 2], Kmat[1, 2] = W / 2.0, H / 2.0
+    c2w = np.tile(np.eye(4, dtype=np.float32), (frames, 1, 1))
+    for f in range(frames):
+        c2w[f, :3, :3] = _rot_y(0.004 * (f - frames / 2))
+        c2w[f, :3, 3] = np.array([0.05 * (f - frames / 2), 0.01 * math.sin(f), 0.0], np.float32)
+    times = np.arange(frames, dtype=np.float32)
+    return Scene(H, W, rgb, depth, mask, flow(), flow(), Kmat, c2w, times)
+
+
+def _target_cam(scene: Scene, t: float, k: int, n_cams: int):
+    """novel camera: small rotation (<= 3 deg) + translation on an ellipse around the
+    interpolated source pose (cf. create_bt_poses, datasets/nvidia_vis.py:692-722)."""
+    f0 = int(min(max(math.floor(t), 0), scene.c2w.shape[0] - 1))
+    c2w = scene.c2w[f0].copy()
+    ang = 2 * math.pi * k / max(n_cams, 1)
+    c2w[:3, :3] = c2w[:3, :3] @ _rot_y(math.radians(2.0) * math.cos(ang)) @ _rot_x(math.radians(1.5) * math.sin(ang))
+    c2w[:3, 3] += np.array([0.15 * math.cos(ang), 0.08 * math.sin(ang), 0.05 * math.sin(2 * ang)], np.float32)
+    return scene.K.copy(), c2w
+
+
+def _pair(scene: Scene, a: int, b: int, t_tgt: float) -> SourcePair:
+    flow = scene.flow_next[a] if b == a + 1 else scene.flow_prev[a]
+    return SourcePair(depth_1=scene.depth[a], rgb_1=scene.rgb[a], mask_1=scene.mask[a], flow_12=flow,
+                      depth_2=scene.depth[b], rgb_2=scene.rgb[b], K_1=scene.K, c2w_1=scene.c2w[a],
+                      K_2=scene.K, c2w_2=scene.c2w[b], time_1=scene.times[a], time_2=scene.times[b],
+                      time_tgt=t_tgt, view=0)
+
+
+def make_workload(name: str, device, n_views: Optional[int] = None, seed: int = 1234,
+                  K: Optional[int] = None, radius: Optional[float] = None, mask_mode: str = "full",
+                  with_static: bool = True) -> Workload:
+    cfg = dict(CONFIGS[name])
+    H, W, F, S = cfg["H"], cfg["W"], cfg["frames"], cfg["S"]
+    V = n_views if n_views is not None else cfg["views"]
+    K = K if K is not None else cfg["K"]
+    radius = radius if radius is not None else cfg["radius"]
+    scene = make_scene(H, W, F, device, seed=seed, mask_mode=mask_mode)
+    view_pairs, view_cams = [], []
+    n_cams = 12 if name.startswith("c2") else max(V, 1)
+    for v in range(V):
+        if name.startswith("c2"):
+            step, cam_k = v // 12, v % 12           # 12 time steps x 12 cameras (N_CAMS, nvidia_eval.py:53)
+        else:
+            step, cam_k = v, v
+        a = step % max(F - 1, 1)                     # temporally closest source frames a, a+1
+        b = a + 1
+        t_tgt = float(scene.times[a]) + 0.5 if not name.startswith("c4") else float(scene.times[a]) + (v % 7 + 1) / 8.0
+        pairs = []
+        # S source segments: the two closest frames in both directions first, then +-2, +-3 ...
+        order = []
+        d = 0
+        while len(order) < S:
+            lo, hi = a - d, b + d
+            if lo >= 0:
+                order.append((lo, lo + 1))           # forward pair  lo -> lo+1
+            if len(order) < S and hi < F:
+                order.append((hi, hi - 1))           # backward pair hi -> hi-1
+            if lo < 0 and hi >= F:
+                order.append((a, b))                 # short scene: repeat (keeps P = S*H*W)
+            d += 1
+        for (i, j) in order[:S]:
+            pairs.append(_pair(scene, i, j, t_tgt))
+        view_pairs.append(pairs)
+        view_cams.append(_target_cam(scene, t_tgt, cam_k, n_cams))
+    static = None
+    if with_static:
+        g = torch.Generator(device=device).manual_seed(seed + 1)
+        static = torch.rand((V, H, W, 3), generator=g, device=device)
+    return Workload(name, H, W, K, radius, scene, view_pairs, view_cams, static,
+                    meta=dict(S=S, frames=F, mask_mode=mask_mode, seed=seed))

@@ -1,0 +1,299 @@
+"""GPU parity for the stages around the rasterizer: fused unproject->warp->project, the
+stand-alone compositors, merge/blend, KNN statistics and the PGDVS-shaped L2 API, against the
+torch-CPU oracle (oracle/pgdvs_ref.py) and the golden fixtures generated from the real
+reference code."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pgdvs_ref as ref
+from oracle import raster as oracle
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+PTS_RTOL, PTS_ATOL = 1e-5, 2e-5   # world / NDC coordinates (fp32 matmul association differs)
+RGB_ATOL = 2e-6                   # bilinear colour
+IMG_ATOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _golden_pair(g, dev, use_occ):
+    from pgdvs_b200.dyn_renderer import SourcePair
+    fs = g["flat_cam_src"]
+    return SourcePair(
+        depth_1=T(g["depth"][0]).to(dev), rgb_1=T(g["rgb"][0]).to(dev), mask_1=T(g["mask"][0]).to(dev),
+        flow_12=T(g["flow"]).to(dev), depth_2=T(g["depth"][1]).to(dev), rgb_2=T(g["rgb"][1]).to(dev),
+        K_1=fs[0, 2:18], c2w_1=fs[0, 18:34], K_2=fs[1, 2:18], c2w_2=fs[1, 18:34],
+        time_1=float(g["t1"]), time_2=float(g["t2"]), time_tgt=float(g["tt"]), view=0,
+        occ_12=T(g["occ"]).to(dev) if use_occ else None)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_uwp_matches_reference_golden(golden_dir, case):
+    """The fused kernel vs what the REAL reference computed (fixtures) for compute_dyn_pcl's
+    geometry: same survivors in the same order, world points / colours within tolerance."""
+    from pgdvs_b200.dyn_renderer import opencv_to_p3d_camera, unproject_warp_project
+    g = np.load(golden_dir / f"dyn_pcl_case{case}.npz")
+    H, W = int(g["H"]), int(g["W"])
+    dev = _dev()
+    pair = _golden_pair(g, dev, bool(g["consist"]))
+    ft = g["flat_cam_tgt"]
+    cam = opencv_to_p3d_camera(ft[2:18], ft[18:34], H, W)
+    cloud = unproject_warp_project([pair], [cam], H, W, dev, want_world=True, want_src_pix=True)
+    torch.cuda.synchronize()
+    P = int(cloud["total"].item())
+    assert int(cloud["num_points"][0]) == P and int(cloud["first_idx"][0]) == 0
+    # oracle (pinned to the fixtures by tests/test_oracle_golden.py) without outlier removal
+    fs = T(g["flat_cam_src"])
+    o = ref.compute_dyn_pcl(
+        dyn_mask_1=T(g["mask"][0]), rgb_1=T(g["rgb"][0]), depth_1=T(g["depth"][0]), flow_12=T(g["flow"]),
+        flow_12_occ_mask=T(g["occ"]), rgb_2=T(g["rgb"][1]), depth_2=T(g["depth"][1]),
+        K_1=fs[0, 2:18].reshape(4, 4), c2w_1=fs[0, 18:34].reshape(4, 4), K_2=fs[1, 2:18].reshape(4, 4),
+        c2w_2=fs[1, 18:34].reshape(4, 4), time_1=torch.tensor(float(g["t1"])),
+        time_2=torch.tensor(float(g["t2"])), time_tgt=torch.tensor(float(g["tt"])),
+        use_flow_consistency=bool(g["consist"]))
+    assert P == o["pcl"].shape[0]
+    assert np.array_equal(cloud["src_pix"][:P].cpu().numpy(), o["src_pix"].numpy())  # exact order
+    np.testing.assert_allclose(cloud["xyz_world"][:P].cpu().numpy(), o["pcl"].numpy(), rtol=PTS_RTOL, atol=PTS_ATOL)
+    np.testing.assert_allclose(cloud["rgb"][:P].cpu().numpy(), o["rgb"].numpy(), atol=RGB_ATOL, rtol=0)
+    ndc = ref.world_to_ndc(o["pcl"], ref.camera_from_flat_cam(T(ft)))
+    np.testing.assert_allclose(cloud["xyz_ndc"][:P].cpu().numpy(), ndc.numpy(), rtol=PTS_RTOL, atol=PTS_ATOL)
+    if not bool(g["rm"]):
+        # no outlier removal in this fixture: the reference's own cloud must match directly
+        np.testing.assert_allclose(cloud["xyz_world"][:P].cpu().numpy(), g["out_pcl"], rtol=PTS_RTOL, atol=PTS_ATOL)
+        np.testing.assert_allclose(cloud["rgb"][:P].cpu().numpy(), g["out_rgb"], atol=RGB_ATOL, rtol=0)
+
+
+def test_uwp_batched_views_order_and_nearest_sampling():
+    """Several jobs per view, several views, odd image size (scalar-load path), integer flows
+    (grid_sample's half-pixel / round-half-even behaviour must match torch exactly)."""
+    from pgdvs_b200.dyn_renderer import SourcePair, opencv_to_p3d_camera, unproject_warp_project
+    dev = _dev()
+    H, W = 13, 19  # H*W odd -> no float4 path
+    gen = torch.Generator().manual_seed(5)
+    F = 3
+    rgb = torch.rand(F, H, W, 3, generator=gen)
+    depth = 1 + 4 * torch.rand(F, H, W, 1, generator=gen)
+    mask = (torch.rand(F, H, W, 1, generator=gen) < 0.7).float()
+    flow = torch.round(2 * torch.randn(F, H, W, 2, generator=gen))  # integers: exact .5 sampling points
+    Kc = torch.eye(4)
+    Kc[0, 0] = Kc[1, 1] = 0.9 * W
+    Kc[0, 2], Kc[1, 2] = W / 2, H / 2
+    c2w = [torch.eye(4) for _ in range(F + 1)]
+    for i in range(F + 1):
+        c2w[i][:3, 3] = torch.tensor([0.05 * i, 0.02 * i, 0.0])
+    jobs, exp = [], []
+    spec = [(0, 1, 0.5, 0), (1, 0, 0.5, 0), (1, 2, 1.25, 1), (2, 2, 2.0, 2)]  # (a, b, t, view); last: same time
+    for (a, b, tt, v) in spec:
+        t1, t2 = float(a), float(b)
+        jobs.append(SourcePair(depth_1=depth[a].to(dev), rgb_1=rgb[a].to(dev), mask_1=mask[a].to(dev),
+                               flow_12=flow[a].to(dev), depth_2=depth[b].to(dev), rgb_2=rgb[b].to(dev),
+                               K_1=Kc, c2w_1=c2w[a], K_2=Kc, c2w_2=c2w[b], time_1=t1, time_2=t2,
+                               time_tgt=tt, view=v))
+        exp.append(ref.compute_dyn_pcl(dyn_mask_1=mask[a], rgb_1=rgb[a], depth_1=depth[a], flow_12=flow[a],
+                                       flow_12_occ_mask=torch.zeros(H, W, 1), rgb_2=rgb[b], depth_2=depth[b],
+                                       K_1=Kc, c2w_1=c2w[a], K_2=Kc, c2w_2=c2w[b], time_1=torch.tensor(t1),
+                                       time_2=torch.tensor(t2), time_tgt=torch.tensor(tt)))
+    cams = [opencv_to_p3d_camera(Kc, c2w[F], H, W)] * 3
+    cloud = unproject_warp_project(jobs, cams, H, W, dev, want_world=True, want_src_pix=True)
+    torch.cuda.synchronize()
+    n = [e["pcl"].shape[0] for e in exp]
+    assert cloud["num_points"].tolist() == [n[0] + n[1], n[2], n[3]]
+    assert cloud["first_idx"].tolist() == [0, n[0] + n[1], n[0] + n[1] + n[2]]
+    P = sum(n)
+    assert int(cloud["total"]) == P
+    pcl = torch.cat([e["pcl"] for e in exp]).numpy()
+    col = torch.cat([e["rgb"] for e in exp]).numpy()
+    sp = torch.cat([e["src_pix"] for e in exp]).numpy()
+    assert np.array_equal(cloud["src_pix"][:P].cpu().numpy(), sp)
+    np.testing.assert_allclose(cloud["xyz_world"][:P].cpu().numpy(), pcl, rtol=PTS_RTOL, atol=PTS_ATOL)
+    np.testing.assert_allclose(cloud["rgb"][:P].cpu().numpy(), col, atol=RGB_ATOL, rtol=0)
+
+
+def test_uwp_large_matches_oracle_counts():
+    """Config-1-shaped image with the float4 path and >1 scan tile per job: survivor count and
+    order vs the oracle, geometry within tolerance."""
+    from pgdvs_b200 import synthetic
+    from pgdvs_b200.dyn_renderer import opencv_to_p3d_camera, unproject_warp_project
+    dev = _dev()
+    wl = synthetic.make_workload("c1_nvidia_1view", dev, mask_mode="ellipse")
+    pairs, cams = wl.jobs([0])
+    p3d = [opencv_to_p3d_camera(K, c, wl.H, wl.W) for (K, c) in cams]
+    cloud = unproject_warp_project(pairs, p3d, wl.H, wl.W, dev, want_world=True, want_src_pix=True)
+    torch.cuda.synchronize()
+    sc = wl.scene
+    tot = 0
+    for j, (a, b) in enumerate([(0, 1), (1, 0)]):
+        fl = sc.flow_next[a] if b == a + 1 else sc.flow_prev[a]
+        e = ref.compute_dyn_pcl(dyn_mask_1=sc.mask[a].cpu(), rgb_1=sc.rgb[a].cpu(), depth_1=sc.depth[a].cpu(),
+                                flow_12=fl.cpu(), flow_12_occ_mask=torch.zeros(wl.H, wl.W, 1),
+                                rgb_2=sc.rgb[b].cpu(), depth_2=sc.depth[b].cpu(), K_1=T(sc.K), c2w_1=T(sc.c2w[a]),
+                                K_2=T(sc.K), c2w_2=T(sc.c2w[b]), time_1=torch.tensor(sc.times[a]),
+                                time_2=torch.tensor(sc.times[b]), time_tgt=torch.tensor(0.5))
+        n = e["pcl"].shape[0]
+        assert n > 1000
+        assert np.array_equal(cloud["src_pix"][tot:tot + n].cpu().numpy(), e["src_pix"].numpy())
+        np.testing.assert_allclose(cloud["xyz_world"][tot:tot + n].cpu().numpy(), e["pcl"].numpy(),
+                                   rtol=PTS_RTOL, atol=PTS_ATOL)
+        np.testing.assert_allclose(cloud["rgb"][tot:tot + n].cpu().numpy(), e["rgb"].numpy(), atol=RGB_ATOL, rtol=0)
+        tot += n
+    assert int(cloud["total"]) == tot
+
+
+@pytest.mark.parametrize("mode,fn", [("alpha", "alpha_composite"), ("norm", "norm_weighted_sum"), ("wsum", "weighted_sum")])
+def test_standalone_compositors(mode, fn):
+    import pgdvs_b200
+    rng = np.random.default_rng(2)
+    N, K, H, W, C, P = 2, 5, 9, 11, 6, 300
+    idx = rng.integers(-1, P, (N, K, H, W)).astype(np.int64)
+    al = rng.uniform(0, 1, (N, K, H, W)).astype(np.float32)
+    ft = rng.uniform(-1, 1, (C, P)).astype(np.float32)
+    d = _dev()
+    out = getattr(pgdvs_b200, fn)(T(idx).to(d), T(al).to(d), T(ft).to(d)).cpu().numpy()
+    exp = oracle.composite(idx, al, ft, mode)
+    assert np.array_equal(out, exp)  # same op order, explicitly rounded -> bit-exact
+
+
+def test_merge_blend():
+    import pgdvs_b200
+    g = torch.Generator().manual_seed(0)
+    B, H, W = 2, 7, 9
+    dr, tr, st = (torch.rand(B, 3, H, W, generator=g) for _ in range(3))
+    dm = (torch.rand(B, 1, H, W, generator=g) < 0.5).float()
+    tm = (torch.rand(B, 1, H, W, generator=g) < 0.5).float()
+    d = _dev()
+    rgb, m, comb = pgdvs_b200.ops.merge_blend(dr.to(d), dm.to(d), tr.to(d), tm.to(d), st.to(d))
+    e_rgb, e_m = ref.merge_dyn_track(dr, dm, tr, tm)
+    e_c = ref.blend_static_dynamic(st, e_rgb, e_m)
+    assert torch.equal(rgb.cpu(), e_rgb) and torch.equal(m.cpu(), e_m) and torch.equal(comb.cpu(), e_c)
+
+
+def test_knn_mean_dist():
+    import pgdvs_b200
+    g = torch.Generator().manual_seed(1)
+    pcl = torch.randn(3000, 3, generator=g)
+    flags, thres, avg = ref.knn_outlier_flags(pcl, knn=50, std_thres=0.1)
+    out = pgdvs_b200.ops.knn_mean_dist(pcl.to(_dev()), pcl.to(_dev()), 51, skip_first=1).cpu()
+    np.testing.assert_allclose(out.numpy(), avg.numpy(), rtol=2e-5, atol=1e-7)
+    q = torch.randn(500, 3, generator=g)
+    d2 = ((q[:, None] - pcl[None]) ** 2).sum(-1)
+    exp = torch.topk(d2, 7, dim=1, largest=False).values.mean(1)
+    out = pgdvs_b200.ops.knn_mean_dist(q.to(_dev()), pcl.to(_dev()), 7).cpu()
+    np.testing.assert_allclose(out.numpy(), exp.numpy(), rtol=2e-5, atol=1e-7)
+
+
+def test_render_dyn_pcl_l2_matches_oracle(golden_dir):
+    """PGDVSDynamicRenderer.render_dyn_pcl on the cloud the REAL reference handed to pytorch3d."""
+    import pgdvs_b200
+    from types import SimpleNamespace
+    g = np.load(golden_dir / "dyn_pcl_case0.npz")
+    H, W = int(g["H"]), int(g["W"])
+    d = _dev()
+    cfg = SimpleNamespace(dyn_render_pcl_pt_radius=float(g["b_radius"]), dyn_render_pcl_pts_per_pixel=int(g["b_ppp"]))
+    r = pgdvs_b200.PGDVSDynamicRenderer()
+    img, mask, frags = r.render_dyn_pcl(dyn_mask=torch.zeros(H, W, 1, device=d), dyn_pcl=T(g["b_points"][0]).to(d),
+                                        rgbs=T(g["b_features"][0]).to(d), flat_cam=T(g["flat_cam_tgt"]).to(d),
+                                        render_cfg=cfg, return_fragments=True)
+    e_img, e_mask, (ndc, e_idx, e_z, e_d) = ref.render_dyn_pcl(
+        H=H, W=W, dyn_pcl=T(g["b_points"][0]), rgbs=T(g["b_features"][0]), flat_cam=T(g["flat_cam_tgt"]),
+        radius=cfg.dyn_render_pcl_pt_radius, points_per_pixel=cfg.dyn_render_pcl_pts_per_pixel,
+        return_fragments=True)
+    # NDC inputs differ by fp32 rounding of the camera transform, so compare idx as a fraction
+    agree = (frags["idx"].cpu().numpy() == e_idx).mean()
+    assert agree > 0.995, agree
+    same = np.all(frags["idx"].cpu().numpy() == e_idx, axis=-1)[0]
+    np.testing.assert_allclose(img.cpu().numpy()[same], e_img.numpy()[same], atol=1e-4, rtol=0)
+    assert (mask.cpu().numpy() == e_mask.numpy()).mean() > 0.995
+    # empty cloud -> zeros (pgdvs_renderer_dyn.py:680-682)
+    img0, mask0 = r.render_dyn_pcl(dyn_mask=torch.zeros(H, W, 1, device=d), dyn_pcl=torch.zeros(0, 3, device=d),
+                                   rgbs=torch.zeros(0, 3, device=d), flat_cam=T(g["flat_cam_tgt"]).to(d), render_cfg=cfg)
+    assert img0.shape == (H, W, 3) and float(img0.abs().sum()) == 0 and float(mask0.sum()) == 0
+
+
+def test_forward_end_to_end_vs_oracle():
+    """PGDVSDynamicRenderer.forward on a reference-shaped data dict: the fused GPU path vs the
+    oracle pipeline run on the GPU's own NDC cloud (bit-exact raster) and vs the oracle's own
+    cloud (tolerance + idx-agreement fraction)."""
+    import pgdvs_b200
+    from types import SimpleNamespace
+    d = _dev()
+    B, H, W = 2, 24, 40
+    g = torch.Generator().manual_seed(3)
+    data = {
+        "rgb_src_temporal": torch.rand(B, 2, H, W, 3, generator=g),
+        "depth_src_temporal": 2 + 3 * torch.rand(B, 2, H, W, 1, generator=g),
+        "dyn_mask_src_temporal": (torch.rand(B, 2, H, W, 1, generator=g) < 0.8).float(),
+        "flow_fwd": 1.5 * torch.randn(B, H, W, 2, generator=g),
+        "flow_fwd_occ_mask": (torch.rand(B, H, W, 1, generator=g) < 0.1).float(),
+        "time_src_temporal": torch.tensor([[0.0, 1.0], [4.0, 5.0]]),
+        "time_tgt": torch.tensor([[0.25], [4.5]]),
+    }
+    Kc = torch.eye(4)
+    Kc[0, 0] = Kc[1, 1] = 0.9 * W
+    Kc[0, 2], Kc[1, 2] = W / 2, H / 2
+
+    def flat(tx):
+        c2w = torch.eye(4)
+        c2w[:3, 3] = torch.tensor([tx, 0.01, 0.0])
+        return torch.cat([torch.tensor([float(H), float(W)]), Kc.reshape(-1), c2w.reshape(-1)])
+
+    data["flat_cam_src_temporal"] = torch.stack([torch.stack([flat(0.0), flat(0.05)]), torch.stack([flat(0.1), flat(0.15)])])
+    data["flat_cam_tgt"] = torch.stack([flat(0.02), flat(0.13)])
+    data["dyn_mask_src_temporal"][1, 0] = 0  # second batch item: empty mask branch (:104, :133-152)
+    cfg = SimpleNamespace(dyn_render_type="pcl", dyn_render_pcl_pt_radius=0.05, dyn_render_pcl_pts_per_pixel=4,
+                          dyn_render_use_flow_consistency=True, dyn_pcl_remove_outlier=False)
+    static = torch.rand(B, 3, H, W, generator=g)
+    r = pgdvs_b200.PGDVSDynamicRenderer()
+    rgb, mask, info = r(({k: v.to(d) for k, v in data.items()}), None, cfg, static_rgb=static.to(d))
+    assert rgb.shape == (B, 3, H, W) and mask.shape == (B, 1, H, W)
+    assert float(mask[1].sum()) == 0 and float(rgb[1].abs().sum()) == 0
+    fs = data["flat_cam_src_temporal"]
+    o = ref.compute_dyn_pcl(
+        dyn_mask_1=data["dyn_mask_src_temporal"][0, 0], rgb_1=data["rgb_src_temporal"][0, 0],
+        depth_1=data["depth_src_temporal"][0, 0], flow_12=data["flow_fwd"][0],
+        flow_12_occ_mask=data["flow_fwd_occ_mask"][0], rgb_2=data["rgb_src_temporal"][0, 1],
+        depth_2=data["depth_src_temporal"][0, 1], K_1=fs[0, 0, 2:18].reshape(4, 4), c2w_1=fs[0, 0, 18:34].reshape(4, 4),
+        K_2=fs[0, 1, 2:18].reshape(4, 4), c2w_2=fs[0, 1, 18:34].reshape(4, 4), time_1=torch.tensor(0.0),
+        time_2=torch.tensor(1.0), time_tgt=torch.tensor(0.25), use_flow_consistency=True)
+    e_img, e_mask = ref.render_dyn_pcl(H=H, W=W, dyn_pcl=o["pcl"], rgbs=o["rgb"], flat_cam=data["flat_cam_tgt"][0],
+                                       radius=0.05, points_per_pixel=4)
+    m_agree = (mask[0, 0].cpu() == e_mask[..., 0]).float().mean()
+    assert m_agree > 0.995
+    diff = (rgb[0].cpu().permute(1, 2, 0) - e_img).abs().max(dim=-1).values
+    assert (diff < 1e-4).float().mean() > 0.99  # boundary flips allowed on <1% of pixels
+    comb = info["combined_rgb"].cpu()
+    e_comb = ref.blend_static_dynamic(static, rgb.cpu(), mask.cpu())
+    assert torch.equal(comb, e_comb)
+
+
+def test_pytorch3d_facade_generic_equals_fused():
+    """The pytorch3d-shaped classes: the generic two-step path (rasterize -> torch weights ->
+    stand-alone compositor, any C) and the fused path give the same image."""
+    import pgdvs_b200 as p3
+    d = _dev()
+    g = torch.Generator().manual_seed(9)
+    H, W, P = 20, 30, 1500
+    pts = torch.randn(1, P, 3, generator=g) * torch.tensor([1.0, 0.6, 0.5]) + torch.tensor([0.0, 0.0, 4.0])
+    feats = torch.rand(1, P, 3, generator=g)
+    Kc = torch.eye(3)[None].clone()
+    Kc[0, 0, 0] = Kc[0, 1, 1] = 0.9 * W
+    Kc[0, 0, 2], Kc[0, 1, 2] = W / 2, H / 2
+    cams = p3.cameras_from_opencv_projection(torch.eye(3)[None].to(d), torch.zeros(1, 3).to(d), Kc.to(d),
+                                             torch.LongTensor([[H, W]]))
+    s = p3.PointsRasterizationSettings(image_size=(H, W), radius=0.08, points_per_pixel=5, bin_size=0)
+    rast = p3.PointsRasterizer(cameras=cams, raster_settings=s)
+    for comp in (p3.NormWeightedCompositor(background_color=(0, 0, 0)), p3.AlphaCompositor(background_color=(0.1, 0.2, 0.3))):
+        rend = p3.PointsRenderer(rasterizer=rast, compositor=comp)
+        cloud = p3.Pointclouds(points=pts.to(d), features=feats.to(d))
+        fused = rend(cloud)
+        generic = rend(cloud, dummy_kwarg=True) if False else None
+        frags = rast(cloud)
+        w = 1 - frags.dists.permute(0, 3, 1, 2) / (0.08 * 0.08)
+        two_step = comp(frags.idx.long().permute(0, 3, 1, 2), w, feats[0].to(d).permute(1, 0)).permute(0, 2, 3, 1)
+        assert fused.shape == (1, H, W, 3)
+        np.testing.assert_allclose(fused.cpu().numpy(), two_step.cpu().numpy(), atol=IMG_ATOL, rtol=0)
+        assert float((frags.idx >= 0).float().mean()) > 0.05

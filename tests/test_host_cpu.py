@@ -1,0 +1,131 @@
+"""CPU-side checks (no GPU, no compute calls): the C-ABI library loads and exports every symbol
+the header declares, argument validation, host camera algebra vs the reference fixtures,
+synthetic workload shapes, view sharding."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    from pgdvs_b200 import _cabi
+    if not _cabi.LIB_PATH.exists():
+        g.build()
+    return _cabi.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from pgdvs_b200 import _cabi
+    header = (ROOT / "include" / "pgdvs_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pgdvs_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_cabi.EXPORTED_SYMBOLS)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pgdvs_b200.h but not exported"
+    assert lib.pgdvs_abi_version() == 1
+
+
+def test_error_strings_and_host_side_validation(lib):
+    assert lib.pgdvs_error_string(0) == b"ok"
+    assert b"150" in lib.pgdvs_error_string(-2)
+    n = ctypes.c_size_t(0)
+    assert lib.pgdvs_bin_workspace_bytes(1, 288, 544, 313344, 0.01, ctypes.byref(n)) == 0
+    # counters for (288+2)*(544+2) cells + rank (8 B) + two float4 records per point
+    assert n.value >= 290 * 546 * 4 + 313344 * (8 + 16 + 16)
+    assert lib.pgdvs_bin_workspace_bytes(1, 0, 544, 10, 0.01, ctypes.byref(n)) == -1
+    assert lib.pgdvs_bin_workspace_bytes(1, 8, 8, 10, -1.0, ctypes.byref(n)) == -1
+    assert lib.pgdvs_uwp_workspace_bytes(4, 288, 544, ctypes.byref(n)) == 0 and n.value > 0
+    # argument errors are detected before any CUDA call (safe without a GPU)
+    assert lib.pgdvs_rasterize_composite(None, 0, 1, 0, 8, 8, 4, 0.1, 0, 0, 0, 1.0, None, None, None,
+                                         None, None, None, None, None) == -1
+    dummy = ctypes.c_void_p(256)
+    assert lib.pgdvs_rasterize_composite(dummy, 1 << 40, 1, 0, 8, 8, 151, 0.1, 0, 0, 0, 1.0, None, None,
+                                         None, None, None, None, None, None) == -2
+    assert lib.pgdvs_rasterize_composite(dummy, 16, 1, 0, 8, 8, 4, 0.1, 0, 0, 0, 1.0, None, None, None,
+                                         None, None, None, None, None) == -3
+    assert lib.pgdvs_knn_mean_dist(None, 5, None, 5, 65, 0, None, None, 0, None) == -2
+
+
+def test_struct_layout_matches_library(lib):
+    from pgdvs_b200 import _cabi
+    lay = (ctypes.c_int32 * 4)()
+    assert lib.pgdvs_struct_layout(lay) == 0
+    assert list(lay) == [ctypes.sizeof(_cabi.PgdvsCamera), ctypes.sizeof(_cabi.PgdvsUwpJob),
+                         _cabi.PgdvsUwpJob.M1.offset, _cabi.PgdvsUwpJob.view.offset]
+    assert lay[0] == 64 and lay[2] == 64
+
+
+def test_host_camera_matches_reference_fixture(golden_dir):
+    from pgdvs_b200.dyn_renderer import opencv_to_p3d_camera
+    g = np.load(golden_dir / "camera.npz")
+    fc = g["flat_cam"]
+    R, T, f, p0 = opencv_to_p3d_camera(fc[2:18], fc[18:34], int(fc[0]), int(fc[1]))
+    np.testing.assert_allclose(R.reshape(3, 3), g["R"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(T, g["T"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(f, g["focal"], rtol=1e-6)
+    np.testing.assert_allclose(p0, g["p0"], rtol=1e-6, atol=1e-7)
+
+
+def test_facade_camera_conversion_matches_fixture(golden_dir):
+    import pgdvs_b200 as p3
+    g = np.load(golden_dir / "camera.npz")
+    fc = torch.from_numpy(g["flat_cam"])
+    w2c = torch.inverse(fc[18:34].reshape(4, 4))
+    cams = p3.cameras_from_opencv_projection(w2c[None, :3, :3], w2c[None, :3, 3], fc[2:18].reshape(4, 4)[None, :3, :3],
+                                             torch.LongTensor([[int(fc[0]), int(fc[1])]]))
+    np.testing.assert_allclose(cams.R[0].numpy(), g["R"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cams.T[0].numpy(), g["T"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(cams.focal_length[0].numpy(), g["focal"], rtol=1e-6)
+    np.testing.assert_allclose(cams.principal_point[0].numpy(), g["p0"], rtol=1e-6, atol=1e-7)
+
+
+def test_no_cpu_fallback():
+    import pgdvs_b200
+    pts = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pgdvs_b200.rasterize_points_packed(pts, torch.zeros(1, dtype=torch.int64), torch.full((1,), 4), (8, 8), 0.1, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pgdvs_b200.norm_weighted_sum(torch.zeros(1, 1, 2, 2, dtype=torch.int64), torch.zeros(1, 1, 2, 2), torch.zeros(3, 4))
+
+
+def test_product_package_never_imports_oracle():
+    for p in (ROOT / "ml-pgdvs_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "oracle" not in re.sub(r"#.*", "", src).replace("oracle/", ""), f"{p} references the oracle"
+
+
+def test_parse_image_size_and_settings():
+    from pgdvs_b200.ops import parse_image_size
+    assert parse_image_size(64) == (64, 64) and parse_image_size((3, 5)) == (3, 5)
+    for bad in [(0, 5), (3, 5, 7), (3.5, 4)]:
+        with pytest.raises(ValueError):
+            parse_image_size(bad)
+
+
+def test_pointclouds_structure():
+    import pgdvs_b200 as p3
+    a, b = torch.rand(5, 3), torch.rand(7, 3)
+    pc = p3.Pointclouds([a, b], [torch.rand(5, 3), torch.rand(7, 3)])
+    assert pc.points_packed().shape == (12, 3)
+    assert pc.num_points_per_cloud().tolist() == [5, 7] and pc.cloud_to_packed_first_idx().tolist() == [0, 5]
+    pc.features = torch.ones(2, 5, 3)[:, :5]
+    assert pc.features_packed().shape[1] == 3
+
+
+@pytest.mark.parametrize("name,P", [("c1_nvidia_1view", 313344), ("c3_iphone", 1036800), ("c4_davis", 819840)])
+def test_synthetic_workload_shapes(name, P):
+    from pgdvs_b200 import synthetic
+    cfg = synthetic.CONFIGS[name]
+    assert cfg["S"] * cfg["H"] * cfg["W"] == P  # BASELINE.md point counts
+    wl = synthetic.make_workload("tiny", torch.device("cpu"), n_views=5)
+    assert wl.n_views == 5 and len(wl.view_pairs[0]) == 2 and wl.static_rgb.shape == (5, 24, 40, 3)
+    pairs, cams = wl.jobs([4, 1])
+    assert [p.view for p in pairs] == [0, 0, 1, 1] and len(cams) == 2
