@@ -128,64 +128,94 @@ def _upload_structs(structs, ctype, device) -> torch.Tensor:
     return torch.from_numpy(raw.copy()).to(device, non_blocking=False)
 
 
-def unproject_warp_project(pairs: Sequence[SourcePair], cams_p3d: Sequence, H: int, W: int, device,
+class PreparedViews:
+    """Device-resident job / camera descriptor arrays for a batch of target views.  Building
+    them is host work (tiny 4x4 algebra + one small H2D copy); once prepared, the whole hot path
+    can be re-run with zero host<->device traffic."""
+
+    def __init__(self, pairs: Sequence[SourcePair], cams_p3d: Sequence, H: int, W: int, device):
+        self.n_jobs, self.n_views, self.H, self.W = len(pairs), len(cams_p3d), H, W
+        self.device = torch.device(device)
+        assert all(pairs[i].view <= pairs[i + 1].view for i in range(self.n_jobs - 1)), \
+            "jobs must be sorted by view"
+        cam_structs = []
+        for (R, T, f, p0) in cams_p3d:
+            c = _cabi.PgdvsCamera()
+            _fill(c.R, R)
+            _fill(c.T, T)
+            _fill(c.focal, f)
+            _fill(c.p0, p0)
+            cam_structs.append(c)
+        self.jobs_dev = _upload_structs([p.to_struct() for p in pairs], _cabi.PgdvsUwpJob, device)
+        self.cams_dev = _upload_structs(cam_structs, _cabi.PgdvsCamera, device)
+        self._keepalive = list(pairs)
+        self.h2d_bytes = self.jobs_dev.numel() + self.cams_dev.numel()
+
+
+def prepare_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, device) -> PreparedViews:
+    """tgt_cams: per view (K44, c2w44) in OpenCV convention (flat_cam[2:18], flat_cam[18:34])."""
+    cams = [opencv_to_p3d_camera(K, c2w, H, W) for (K, c2w) in tgt_cams]
+    return PreparedViews(pairs, cams, H, W, device)
+
+
+def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=None,
                            want_world: bool = False, want_src_pix: bool = False):
     """Fused unproject -> warp -> lerp -> project for a batch of source pairs (sorted by view).
-    cams_p3d: per view (R_p3d[9], T[3], focal[2], p0[2]).  Returns a dict of packed outputs
-    (capacity-sized buffers + device-side counts; nothing is synchronised)."""
-    n_jobs, n_views = len(pairs), len(cams_p3d)
-    assert all(pairs[i].view <= pairs[i + 1].view for i in range(n_jobs - 1)), "jobs must be sorted by view"
-    cam_structs = []
-    for (R, T, f, p0) in cams_p3d:
-        c = _cabi.PgdvsCamera()
-        _fill(c.R, R)
-        _fill(c.T, T)
-        _fill(c.focal, f)
-        _fill(c.p0, p0)
-        cam_structs.append(c)
-    jobs_dev = _upload_structs([p.to_struct() for p in pairs], _cabi.PgdvsUwpJob, device)
-    cams_dev = _upload_structs(cam_structs, _cabi.PgdvsCamera, device)
+    `pairs` is a list of SourcePair (+ cams_p3d: per view (R_p3d[9], T[3], focal[2], p0[2])) or a
+    PreparedViews.  Returns a dict of packed outputs (capacity-sized buffers + device-side
+    counts; nothing is synchronised)."""
+    prep = pairs if isinstance(pairs, PreparedViews) else PreparedViews(pairs, cams_p3d, H, W, device)
+    n_jobs, n_views, H, W, device = prep.n_jobs, prep.n_views, prep.H, prep.W, prep.device
     cap = max(n_jobs * H * W, 1)
     xyz_ndc = torch.empty((cap, 3), dtype=torch.float32, device=device)
     rgb = torch.empty((cap, 3), dtype=torch.float32, device=device)
     xyz_world = torch.empty((cap, 3), dtype=torch.float32, device=device) if want_world else None
     src_pix = torch.empty((cap,), dtype=torch.int32, device=device) if want_src_pix else None
-    first_idx = torch.zeros((n_views,), dtype=torch.int64, device=device)
-    num_points = torch.zeros((n_views,), dtype=torch.int64, device=device)
-    total = torch.zeros((1,), dtype=torch.int64, device=device)
+    first_idx = torch.empty((n_views,), dtype=torch.int64, device=device)
+    num_points = torch.empty((n_views,), dtype=torch.int64, device=device)
+    total = torch.empty((1,), dtype=torch.int64, device=device)
     L = _cabi.lib()
     nbytes = ctypes.c_size_t(0)
     _cabi.check(L.pgdvs_uwp_workspace_bytes(n_jobs, H, W, ctypes.byref(nbytes)), "pgdvs_uwp_workspace_bytes")
-    ws = ops._WS.get(torch.device(device), nbytes.value, tag="uwp")
+    ws = ops._WS.get(device, nbytes.value, tag="uwp")
     with torch.cuda.device(device):
         _cabi.check(L.pgdvs_unproject_warp_project(
-            jobs_dev.data_ptr(), n_jobs, cams_dev.data_ptr(), n_views, H, W, xyz_ndc.data_ptr(),
+            prep.jobs_dev.data_ptr(), n_jobs, prep.cams_dev.data_ptr(), n_views, H, W, xyz_ndc.data_ptr(),
             rgb.data_ptr(), xyz_world.data_ptr() if want_world else None,
             src_pix.data_ptr() if want_src_pix else None, first_idx.data_ptr(), num_points.data_ptr(),
             total.data_ptr(), ops._aligned_ptr(ws), nbytes.value, ops._stream_ptr(device)),
             "pgdvs_unproject_warp_project")
+    ops.LAUNCHES["count"] += 2  # k_uwp + k_uwp_finalize
     return {"xyz_ndc": xyz_ndc, "rgb": rgb, "xyz_world": xyz_world, "src_pix": src_pix,
-            "first_idx": first_idx, "num_points": num_points, "total": total,
-            "_keepalive": (jobs_dev, cams_dev, list(pairs))}
+            "first_idx": first_idx, "num_points": num_points, "total": total, "_keepalive": prep}
+
+
+def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int, compositor: str = "norm",
+                    static_rgb: Optional[torch.Tensor] = None, return_fragments: bool = False,
+                    raster_events=None):
+    """uwp kernel -> binning -> rasterize+composite(+mask, +static blend) for prepared views:
+    3 stream-ordered stages, zero host syncs."""
+    cloud = unproject_warp_project(prep)
+    out = ops.render_packed(cloud["xyz_ndc"], cloud["rgb"], cloud["first_idx"], cloud["num_points"],
+                            (prep.H, prep.W), radius, points_per_pixel, compositor=compositor,
+                            background=(0.0, 0.0, 0.0), static_rgb=static_rgb,
+                            return_fragments=return_fragments, return_mask=True,
+                            raster_events=raster_events)
+    out["first_idx"], out["num_points"], out["cloud"] = cloud["first_idx"], cloud["num_points"], cloud
+    return out
 
 
 def render_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, *, radius: float,
                  points_per_pixel: int, compositor: str = "norm", static_rgb: Optional[torch.Tensor] = None,
                  return_fragments: bool = False, device=None):
-    """The whole hot path for a batch of target views in 3 stream-ordered stages and zero host
-    syncs: uwp kernel -> binning -> rasterize+composite(+mask, +static blend).
+    """The whole hot path for a batch of target views.
 
     tgt_cams: per view (K44, c2w44) OpenCV; static_rgb optional [N,H,W,3] (GNT render).
     Returns dict(image [N,H,W,3], mask [N,H,W,1], [idx,zbuf,dists], first_idx, num_points)."""
     device = device if device is not None else pairs[0].depth_1.device
-    cams = [opencv_to_p3d_camera(K, c2w, H, W) for (K, c2w) in tgt_cams]
-    cloud = unproject_warp_project(pairs, cams, H, W, device)
-    out = ops.render_packed(cloud["xyz_ndc"], cloud["rgb"], cloud["first_idx"], cloud["num_points"],
-                            (H, W), radius, points_per_pixel, compositor=compositor,
-                            background=(0.0, 0.0, 0.0), static_rgb=static_rgb,
-                            return_fragments=return_fragments, return_mask=True)
-    out["first_idx"], out["num_points"], out["cloud"] = cloud["first_idx"], cloud["num_points"], cloud
-    return out
+    prep = prepare_views(pairs, tgt_cams, H, W, device)
+    return render_prepared(prep, radius=radius, points_per_pixel=points_per_pixel, compositor=compositor,
+                           static_rgb=static_rgb, return_fragments=return_fragments)
 
 
 # ----------------------------------------------------------------------------- L2 class

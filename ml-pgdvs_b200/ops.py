@@ -27,6 +27,9 @@ _COMPOSITORS = {
 
 kMaxPointsPerPixel = _cabi.MAX_POINTS_PER_PIXEL
 
+# number of kernels of libpgdvs_b200.so launched so far (bench.py reports the per-step delta)
+LAUNCHES = {"count": 0}
+
 
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
@@ -86,7 +89,7 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
                   radius: Union[float, torch.Tensor], points_per_pixel: int,
                   compositor: Optional[str] = "norm", background: Optional[Sequence[float]] = None,
                   static_rgb: Optional[torch.Tensor] = None, return_fragments: bool = True,
-                  return_mask: bool = True, rr_weight: Optional[float] = None):
+                  return_mask: bool = True, rr_weight: Optional[float] = None, raster_events=None):
     """Fused bin -> rasterize -> composite of a packed batch of NDC clouds.
 
     points_ndc [P,3] (NDC x, NDC y, view z), features [P,C] (C<=4) or None, first_idx /
@@ -145,6 +148,7 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
             first_idx.data_ptr(), num_points.data_ptr(), N, P,
             radius_t.data_ptr() if radius_t is not None else None, radius_max, H, W, ws_ptr,
             nbytes.value, stream), "pgdvs_bin_points")
+        LAUNCHES["count"] += 3 if P > 0 else 1  # k_count, k_scan, k_fill
         out = {}
         idx = zbuf = dists = image = mask = None
         if return_fragments:
@@ -167,6 +171,8 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
             st = _f32c(static_rgb)
             if tuple(st.shape) != (N, H, W, C):
                 raise ValueError("static_rgb must be [N,H,W,C]")
+        if raster_events is not None:
+            raster_events[0].record(torch.cuda.current_stream(dev))
         _cabi.check(L.pgdvs_rasterize_composite(
             ws_ptr, nbytes.value, N, P, H, W, K, radius_max, 1 if radius_t is not None else 0, C, mode,
             float(rr_weight) if rr_weight is not None else 1.0, bg,
@@ -176,6 +182,9 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
             dists.data_ptr() if dists is not None else None,
             image.data_ptr() if image is not None else None,
             mask.data_ptr() if mask is not None else None, stream), "pgdvs_rasterize_composite")
+        if raster_events is not None:
+            raster_events[1].record(torch.cuda.current_stream(dev))
+        LAUNCHES["count"] += 1
     out.update(idx=idx, zbuf=zbuf, dists=dists, image=image, mask=mask)
     return out
 

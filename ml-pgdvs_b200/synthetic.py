@@ -140,10 +140,12 @@ def _target_cam(scene: Scene, t: float, k: int, n_cams: int):
 
 def _pair(scene: Scene, a: int, b: int, t_tgt: float) -> SourcePair:
     flow = scene.flow_next[a] if b == a + 1 else scene.flow_prev[a]
-    return SourcePair(depth_1=scene.depth[a], rgb_1=scene.rgb[a], mask_1=scene.mask[a], flow_12=flow,
-                      depth_2=scene.depth[b], rgb_2=scene.rgb[b], K_1=scene.K, c2w_1=scene.c2w[a],
-                      K_2=scene.K, c2w_2=scene.c2w[b], time_1=scene.times[a], time_2=scene.times[b],
-                      time_tgt=t_tgt, view=0)
+    sp = SourcePair(depth_1=scene.depth[a], rgb_1=scene.rgb[a], mask_1=scene.mask[a], flow_12=flow,
+                    depth_2=scene.depth[b], rgb_2=scene.rgb[b], K_1=scene.K, c2w_1=scene.c2w[a],
+                    K_2=scene.K, c2w_2=scene.c2w[b], time_1=scene.times[a], time_2=scene.times[b],
+                    time_tgt=t_tgt, view=0)
+    sp._src_frames, sp._t_tgt = (a, b), float(t_tgt)  # provenance, used by the CPU reference arm
+    return sp
 
 
 def make_workload(name: str, device, n_views: Optional[int] = None, seed: int = 1234,

@@ -44,6 +44,10 @@ def _load():
             fn.restype = ctypes.c_int
             fn.argtypes = [fp, lp, lp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int,
                            ip, fp, fp, ctypes.c_int]
+        lib.oracle_rasterize_points_naive_rows.restype = ctypes.c_int
+        lib.oracle_rasterize_points_naive_rows.argtypes = [
+            fp, lp, lp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int,
+            ctypes.c_int, ip, fp, fp, ctypes.c_int]
         lib.oracle_composite.restype = ctypes.c_int
         lib.oracle_composite.argtypes = [lp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, fp]
@@ -90,6 +94,31 @@ def rasterize_points(points, first_idx, num_pts, image_size, radius, points_per_
             int(n_threads))
     if rc != 0:
         raise RuntimeError(f"oracle rasterize failed rc={rc}")
+    return idx, zbuf, dists
+
+
+def rasterize_points_rows(points, first_idx, num_pts, image_size, radius, points_per_pixel, y0, y1,
+                          n_threads: int = 1):
+    """Naive rasterizer restricted to image rows [y0, y1): outputs [N, y1-y0, W, K].
+    bench.py times this as a bounded sample of the reference's CPU rasterization path."""
+    lib = _load()
+    points = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    first_idx = np.ascontiguousarray(first_idx, dtype=np.int64).reshape(-1)
+    num_pts = np.ascontiguousarray(num_pts, dtype=np.int64).reshape(-1)
+    P, N = points.shape[0], first_idx.shape[0]
+    H, W = int(image_size[0]), int(image_size[1])
+    K = int(points_per_pixel)
+    rad = np.full((P,), radius, dtype=np.float32)
+    R = int(y1) - int(y0)
+    idx = np.empty((N, R, W, K), dtype=np.int32)
+    zbuf = np.empty((N, R, W, K), dtype=np.float32)
+    dists = np.empty((N, R, W, K), dtype=np.float32)
+    rc = lib.oracle_rasterize_points_naive_rows(
+        _ptr(points, ctypes.c_float), _ptr(first_idx, ctypes.c_int64), _ptr(num_pts, ctypes.c_int64),
+        N, H, W, _ptr(rad, ctypes.c_float), K, int(y0), int(y1), _ptr(idx, ctypes.c_int32),
+        _ptr(zbuf, ctypes.c_float), _ptr(dists, ctypes.c_float), int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle rasterize rows failed rc={rc}")
     return idx, zbuf, dists
 
 

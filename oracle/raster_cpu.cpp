@@ -171,6 +171,51 @@ int oracle_rasterize_points_naive(const float* points, const int64_t* first_idx,
   return 0;
 }
 
+// Same loop nest restricted to image rows [y0, y1) (outputs are [N, y1-y0, W, K]).  Used by
+// bench.py to time a BOUNDED sample of the naive CPU rasterizer: its cost is exactly
+// proportional to the number of rows because every pixel visits every point.
+int oracle_rasterize_points_naive_rows(const float* points, const int64_t* first_idx,
+                                       const int64_t* num_pts, int N, int H, int W,
+                                       const float* radius, int K, int y0, int y1,
+                                       int32_t* idx_out, float* zbuf_out, float* dists_out,
+                                       int n_threads) {
+  if (K <= 0 || H <= 0 || W <= 0 || N < 0 || y0 < 0 || y1 > H || y0 >= y1) return 1;
+  const int R = y1 - y0;
+  const int64_t total = (int64_t)N * R * W * K;
+  for (int64_t i = 0; i < total; ++i) {
+    idx_out[i] = -1;
+    zbuf_out[i] = -1.0f;
+    dists_out[i] = -1.0f;
+  }
+  parallel_rows((int64_t)N * R, n_threads, [&](int64_t row) {
+    const int n = (int)(row / R);
+    const int yi = y0 + (int)(row % R);
+    const int64_t p0 = first_idx[n];
+    const int64_t p1 = p0 + num_pts[n];
+    const float yf = PixToNonSquareNdc(H - 1 - yi, H, W);
+    KHeap q(K);
+    for (int xi = 0; xi < W; ++xi) {
+      const float xf = PixToNonSquareNdc(W - 1 - xi, W, H);
+      q.clear();
+      for (int64_t p = p0; p < p1; ++p) {
+        const float px = points[p * 3 + 0];
+        const float py = points[p * 3 + 1];
+        const float pz = points[p * 3 + 2];
+        const float pr = radius[p];
+        const float radius2 = pr * pr;
+        if (pz < 0) continue;
+        const float dx = px - xf;
+        const float dy = py - yf;
+        const float dist2 = dx * dx + dy * dy;
+        if (dist2 < radius2) q.push(Hit{pz, (int)p, dist2});
+      }
+      const int64_t o = (((int64_t)n * R + (yi - y0)) * W + xi) * K;
+      q.drain(idx_out + o, zbuf_out + o, dists_out + o);
+    }
+  });
+  return 0;
+}
+
 // Accelerated checker: identical per-(pixel,point) arithmetic and identical
 // (z, idx, d2) ordering as oracle_rasterize_points_naive, but each pixel row only
 // visits points whose y lies within a conservative band of the row (points are
