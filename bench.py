@@ -231,7 +231,7 @@ def run_ours(args):
 
     def step(ev=None):
         out = render_prepared(prep, radius=radius, points_per_pixel=K, compositor="norm",
-                              static_rgb=wl.static_rgb, raster_events=ev)
+                              static_rgb=wl.static_rgb, raster_events=ev, return_fragments=args.fragments)
         if world > 1:
             # frames are gathered on rank 0 over NCCL/NVLink, overlapped with the next step
             done = torch.cuda.Event()
@@ -314,7 +314,9 @@ def run_ours(args):
 
     # -------------------------------------------------- roofline of the dominant kernel
     peak, peak_src = measured_peak_hbm()
-    b_rc = algorithmic_bytes_raster(V, total_points, H, W, K)
+    # B_rc of SURVEY.md 8(d) (+ the static frame read by the fused blend); without fragments the
+    # 12*K*H*W bytes of idx/zbuf/dists are neither written nor counted
+    b_rc = algorithmic_bytes_raster(V, total_points, H, W, K if args.fragments else 0) + 12 * V * H * W
     achieved = b_rc / (raster_ms / 1e3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "raster_traffic.json"
@@ -356,6 +358,7 @@ def run_ours(args):
             "config": {"workload": args.workload, "views_per_gpu": V, "image": [H, W],
                        "source_frames_per_view": wl.meta["S"], "points_per_view": total_points // V,
                        "points_per_pixel": K, "radius": radius, "compositor": "norm_weighted+mask+static_blend",
+                       "fragments_written": bool(args.fragments),
                        "parallelism": f"views sharded over {world} GPU(s); NCCL gather of frames to rank 0" if world > 1 else "1 GPU",
                        "cache": f"L2 flushed with a {L2_FLUSH_BYTES >> 20} MiB memset before every step (inside the timed bracket); "
                                 f"per-step working set ~{(b_rc + 72 * total_points) / 1e9:.1f} GB >> 126 MB L2"},
@@ -385,6 +388,8 @@ def main():
     ap.add_argument("--workload", default="c2_nvidia_seq")
     ap.add_argument("--views", type=int, default=None, help="views per GPU (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fragments", dest="fragments", action="store_false",
+                    help="do not materialise idx/zbuf/dists (fused-only mode; B_rc drops the 12*K*H*W term)")
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -8,9 +8,11 @@
 //     (z, record slot) pairs in registers;
 //   * candidates are only the records filed under cells within `halo` of the pixel — for
 //     every window row that is one contiguous run of the cell-sorted arrays;
-//   * the hit test reproduces the reference arithmetic bit for bit (dist2_rn, strict <),
-//     ties in z are broken by the smaller packed index exactly like the CPU rasterizer's
-//     (z, idx, dist2) priority queue, so idx/zbuf/dists are deterministic and bit-exact.
+//   * the hit test reproduces the reference arithmetic bit for bit (dist2_rn, strict <);
+//   * the common-case insertion is a branch-free compare-exchange chain on z alone; exact
+//     fp32 z ties (which the CPU rasterizer's (z, idx, dist2) priority queue orders by the
+//     smaller packed index) are DETECTED in the fast path and the few affected pixels are
+//     redone by a tie-aware slow path, so idx/zbuf/dists stay deterministic and bit-exact.
 #include "common.cuh"
 
 namespace pgdvs {
@@ -33,11 +35,13 @@ struct RasterParams {
   float* mask;
 };
 
+constexpr float kInf = __builtin_huge_valf();
+
 // candidate (z, idx) strictly before list element (ze, slot se)?  Total order (z, idx).
 __device__ __forceinline__ bool cand_less(float z, int idx, float ze, int se,
                                           const float4* __restrict__ recA) {
   bool lt = z < ze;
-  if (z == ze) {  // rare: exact fp32 z tie -> smaller packed index first
+  if (z == ze) {  // exact fp32 z tie -> smaller packed index first
     lt = (se < 0) ? true : (idx < __float_as_int(recA[se].w));
   }
   return lt;
@@ -50,18 +54,46 @@ struct KList {
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int i = 0; i < KP; ++i) {
-      z[i] = __int_as_float(0x7f800000);  // +inf
+      z[i] = kInf;
       s[i] = -1;
     }
   }
-  __device__ __forceinline__ void insert(float cz, int cidx, int cslot,
-                                         const float4* __restrict__ recA) {
+  // Fast path: strict-< compare-exchange chain (5 ALU ops per slot, no branches, no loads).
+  // Returns true if an exact z tie was involved in a way that could change the result:
+  //   - the candidate ties with the current last element (it may have to displace it), or
+  //   - the evicted element ties with the new last element (the wrong twin may have left).
+  // Ties that stay inside the list are caught by has_adjacent_tie() at the end.
+  __device__ __forceinline__ bool insert_fast(float cz, int cs) {
+    bool tie = (cz == z[KP - 1]);
+    if (cz < z[KP - 1]) {
+#pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        const bool p = cz < z[i];
+        const float tz = z[i];
+        const int ts = s[i];
+        z[i] = p ? cz : tz;
+        s[i] = p ? cs : ts;
+        cz = p ? tz : cz;
+        cs = p ? ts : cs;
+      }
+      tie = tie || (cs >= 0 && cz == z[KP - 1]);
+    }
+    return tie;
+  }
+  __device__ __forceinline__ bool has_adjacent_tie() const {
+    bool t = false;
+#pragma unroll
+    for (int i = 1; i < KP; ++i) t = t || (s[i] >= 0 && z[i] == z[i - 1]);
+    return t;
+  }
+  // Exact path: full (z, idx) order.
+  __device__ __forceinline__ void insert_exact(float cz, int cidx, int cslot,
+                                               const float4* __restrict__ recA) {
     if (!cand_less(cz, cidx, z[KP - 1], s[KP - 1], recA)) return;
-    bool p_hi = true;  // cand < element i (known true for i = KP-1)
+    bool p_hi = true;
 #pragma unroll
     for (int i = KP - 1; i > 0; --i) {
       const bool p_lo = cand_less(cz, cidx, z[i - 1], s[i - 1], recA);
-      // new[i] = p_lo ? old[i-1] : (p_hi ? cand : old[i])
       z[i] = p_lo ? z[i - 1] : (p_hi ? cz : z[i]);
       s[i] = p_lo ? s[i - 1] : (p_hi ? cslot : s[i]);
       p_hi = p_lo;
@@ -73,91 +105,122 @@ struct KList {
   }
 };
 
+struct PixelCtx {
+  float xf, yf, r2;
+  bool per_point_r;
+};
+
+__device__ __forceinline__ bool hit_test(const PixelCtx& c, const float4 a,
+                                         const float4* __restrict__ recB, int j) {
+  const float d2 = dist2_rn(a.x, a.y, c.xf, c.yf);
+  float r2 = c.r2;
+  if (c.per_point_r) {
+    const float r = __ldg(&recB[j].w);
+    r2 = __fmul_rn(r, r);
+  }
+  return d2 < r2;
+}
+
+// Tie-aware rescan of one pixel (rare).  Kept out of line so the fast path stays small.
+template <int KP>
+__device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx& c, int n, int x,
+                                          int y, float* zout, int* sout) {
+  KList<KP> q;
+  q.init();
+  const int span = 2 * p.halo + 1;
+  for (int ry = 0; ry < span; ++ry) {
+    const int64_t cell0 = ((int64_t)n * p.GH + (y + ry)) * p.GW + x;
+    const int s = __ldg(p.cell_start + cell0);
+    const int e = __ldg(p.cell_start + cell0 + span);
+    for (int j = s; j < e; ++j) {
+      const float4 a = __ldg(p.recA + j);
+      if (hit_test(c, a, p.recB, j)) q.insert_exact(a.z, __float_as_int(a.w), j, p.recA);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < KP; ++i) {
+    zout[i] = q.z[i];
+    sout[i] = q.s[i];
+  }
+}
+
 template <int KP>
 __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ RasterParams p) {
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
   const int n = blockIdx.z;
   if (x >= p.W || y >= p.H) return;
-  const float xf = pixel_center_ndc(p.ax, x);
-  const float yf = pixel_center_ndc(p.ay, y);
+  PixelCtx c;
+  c.xf = pixel_center_ndc(p.ax, x);
+  c.yf = pixel_center_ndc(p.ay, y);
+  c.r2 = p.r2;
+  c.per_point_r = p.r2 < 0.0f;
   const float4* __restrict__ recA = p.recA;
   const float4* __restrict__ recB = p.recB;
-  const bool per_point_r = p.r2 < 0.0f;
 
   KList<KP> q;
   q.init();
+  bool tie = false;
 
   const int span = 2 * p.halo + 1;
-  for (int ry = 0; ry < span; ++ry) {
-    // extended-grid row (y + ry), cells [x, x + 2*halo] <-> image cells [x-halo, x+halo]
-    const int64_t cell0 = ((int64_t)n * p.GH + (y + ry)) * p.GW + x;
-    const int s = __ldg(p.cell_start + cell0);
-    const int e = __ldg(p.cell_start + cell0 + span);
-    for (int j = s; j < e; ++j) {
+  const int* __restrict__ cs = p.cell_start + ((int64_t)n * p.GH + y) * p.GW + x;
+  if (p.halo == 1) {
+    // 3x3 cell window (every PGDVS configuration with r_px < 1.5): the three row runs are
+    // walked by ONE flattened loop so that lanes with uneven rows do not wait for each other
+    // three times.
+    const int s0 = __ldg(cs), e0 = __ldg(cs + 3);
+    const int s1 = __ldg(cs + p.GW), e1 = __ldg(cs + p.GW + 3);
+    const int s2 = __ldg(cs + 2 * p.GW), e2 = __ldg(cs + 2 * p.GW + 3);
+    const int c0 = e0 - s0, c01 = c0 + (e1 - s1), total = c01 + (e2 - s2);
+    const int o1 = s1 - c0, o2 = s2 - c01;
+    for (int t = 0; t < total; ++t) {
+      const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
       const float4 a = __ldg(recA + j);
-      const float d2 = dist2_rn(a.x, a.y, xf, yf);
-      float r2 = p.r2;
-      if (per_point_r) {
-        const float r = __ldg(&recB[j].w);
-        r2 = __fmul_rn(r, r);
+      if (hit_test(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
+    }
+  } else {
+    for (int ry = 0; ry < span; ++ry) {
+      const int s = __ldg(cs + (int64_t)ry * p.GW);
+      const int e = __ldg(cs + (int64_t)ry * p.GW + span);
+      for (int j = s; j < e; ++j) {
+        const float4 a = __ldg(recA + j);
+        if (hit_test(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
       }
-      if (d2 < r2) q.insert(a.z, __float_as_int(a.w), j, recA);
+    }
+  }
+  if (tie || q.has_adjacent_tie()) {
+    float zt[KP];
+    int st[KP];
+    rescan_exact<KP>(p, c, n, x, y, zt, st);
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      q.z[i] = zt[i];
+      q.s[i] = st[i];
     }
   }
 
   // ---------------------------------------------------------------- epilogue
   const int K = p.K;
   const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float ones_acc = 0.f;  // the same compositor applied to all-ones features (mask render)
   const int mode = p.compositor;
+  // pass 1: fragments (idx / zbuf / dists) and the PointsRenderer weights
+  float w[KP];
   float t_alpha = 0.f;
-  if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      if (k < K && q.s[k] >= 0) {
-        const float4 a = __ldg(recA + q.s[k]);
-        const float d2 = dist2_rn(a.x, a.y, xf, yf);
-        const float w = __fsub_rn(1.0f, __fdiv_rn(d2, p.rr_weight));
-        t_alpha = __fadd_rn(t_alpha, w);
-      }
-    }
-    t_alpha = fmaxf(t_alpha, 1e-4f);  // kEps of norm_weighted_sum
-  }
-  float cum_alpha = 1.0f;
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
+    w[k] = 0.f;
     if (k < K) {
       const int sl = q.s[k];
       int o_idx = -1;
       float o_z = -1.0f, o_d = -1.0f;
       if (sl >= 0) {
         const float4 a = __ldg(recA + sl);
-        const float d2 = dist2_rn(a.x, a.y, xf, yf);
+        o_d = dist2_rn(a.x, a.y, c.xf, c.yf);
         o_idx = __float_as_int(a.w);
         o_z = a.z;
-        o_d = d2;
         if (mode != PGDVS_COMPOSITE_NONE) {
-          const float w = __fsub_rn(1.0f, __fdiv_rn(d2, p.rr_weight));
-          const float4 f4 = __ldg(recB + sl);
-          const float f[4] = {f4.x, f4.y, f4.z, f4.w};
-          if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              acc[c] = __fadd_rn(acc[c], __fdiv_rn(__fmul_rn(w, f[c]), t_alpha));
-            ones_acc = __fadd_rn(ones_acc, __fdiv_rn(w, t_alpha));
-          } else if (mode == PGDVS_COMPOSITE_ALPHA) {
-            const float cw = __fmul_rn(cum_alpha, w);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(cw, f[c]));
-            ones_acc = __fadd_rn(ones_acc, cw);
-            cum_alpha = __fmul_rn(cum_alpha, __fsub_rn(1.0f, w));
-          } else {  // weighted sum
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w, f[c]));
-            ones_acc = __fadd_rn(ones_acc, w);
-          }
+          w[k] = __fsub_rn(1.0f, __fdiv_rn(o_d, p.rr_weight));  // 1 - dists/(r*r)
+          t_alpha = __fadd_rn(t_alpha, w[k]);
         }
       }
       if (p.idx) p.idx[pix * K + k] = o_idx;
@@ -165,20 +228,46 @@ __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ Ra
       if (p.dists) p.dists[pix * K + k] = o_d;
     }
   }
-  if (mode != PGDVS_COMPOSITE_NONE) {
-    const bool is_bg = q.s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
-    const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
-    if (p.mask) p.mask[pix] = m;
-    if (p.image) {
-      for (int c = 0; c < p.C; ++c) {
-        float v = is_bg ? p.bg[c] : acc[c];
-        if (p.static_rgb) {
-          // combined = (1 - mask) * static + mask * dyn   (pgdvs_renderer.py:169-172)
-          const float st = __ldg(p.static_rgb + pix * p.C + c);
-          v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st), __fmul_rn(m, v));
-        }
-        p.image[pix * p.C + c] = v;
+  if (mode == PGDVS_COMPOSITE_NONE) return;
+
+  // pass 2: compositor.  The K-ordered accumulation follows the pytorch3d CPU loops; the
+  // norm-weighted division by max(sum w, 1e-4) is applied as one reciprocal multiply
+  // (images are tolerance-matched, |delta| <= 1e-5; fragments above are bit-exact).
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float ones_acc = 0.f;  // the same compositor applied to all-ones features (mask render)
+  float cum_alpha = 1.0f;
+  const float inv_t = __frcp_rn(fmaxf(t_alpha, 1e-4f));
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    if (k < K && q.s[k] >= 0) {
+      const float4 f4 = __ldg(recB + q.s[k]);
+      float wk = w[k];
+      if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
+        wk = __fmul_rn(wk, inv_t);
+      } else if (mode == PGDVS_COMPOSITE_ALPHA) {
+        const float a = wk;
+        wk = __fmul_rn(cum_alpha, a);
+        cum_alpha = __fmul_rn(cum_alpha, __fsub_rn(1.0f, a));
       }
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(wk, f4.x));
+      acc[1] = __fadd_rn(acc[1], __fmul_rn(wk, f4.y));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(wk, f4.z));
+      acc[3] = __fadd_rn(acc[3], __fmul_rn(wk, f4.w));
+      ones_acc = __fadd_rn(ones_acc, wk);
+    }
+  }
+  const bool is_bg = q.s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
+  const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
+  if (p.mask) p.mask[pix] = m;
+  if (p.image) {
+    for (int ch = 0; ch < p.C; ++ch) {
+      float v = is_bg ? p.bg[ch] : acc[ch];
+      if (p.static_rgb) {
+        // combined = (1 - mask) * static + mask * dyn   (pgdvs_renderer.py:169-172)
+        const float st = __ldg(p.static_rgb + pix * p.C + ch);
+        v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st), __fmul_rn(m, v));
+      }
+      p.image[pix * p.C + ch] = v;
     }
   }
 }
