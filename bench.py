@@ -330,9 +330,10 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import raster as oracle
-        fi = out["first_idx"].cpu().numpy()
-        npc = out["num_points"].cpu().numpy()
-        ndc = out["cloud"]["xyz_ndc"][fi[0]:fi[0] + npc[0]].cpu().numpy()
+        oc = render_prepared(prep, radius=radius, points_per_pixel=K, compositor="norm", return_cloud=True)
+        fi = oc["first_idx"].cpu().numpy()
+        npc = oc["num_points"].cpu().numpy()
+        ndc = oc["cloud"]["xyz_ndc"][fi[0]:fi[0] + npc[0]].cpu().numpy()
         n_threads = os.cpu_count() or 1
         z, n1 = np.zeros(1, np.int64), np.full(1, ndc.shape[0], np.int64)
         tc = time.perf_counter()

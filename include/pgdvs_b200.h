@@ -136,6 +136,8 @@ typedef struct PgdvsUwpJob {
   const float* rgb2;    /* [H,W,3] frame 2 (bilinear)              */
   const uint8_t* keep;  /* [H*W] or NULL: per-SOURCE-PIXEL outlier verdict (0 = drop), applied
                            after the validity test (pgdvs_renderer_dyn.py:438-440) */
+  const float* rgbd2;   /* [H,W,4] or NULL: frame 2 packed as (r,g,b,depth) by pgdvs_pack_rgbd,
+                           16-byte aligned; when given, rgb2/depth2 are not read */
   float M1[9];          /* c2w_1[:3,:3] @ inv(K_1[:3,:3])  (base.py:40-45) */
   float o1[3];          /* c2w_1[:3,3]                              */
   float K2inv[9];       /* inv(K_2[:3,:3])                         (dyn.py:362-365) */
@@ -161,6 +163,28 @@ int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs, const Pgdv
                                  float* xyz_world, int32_t* src_pix, int64_t* first_idx,
                                  int64_t* num_points, int64_t* total_points, void* workspace,
                                  size_t workspace_bytes, void* stream);
+
+/* Fused variant used by the batched renderer: the same kernel additionally files every point
+ * under its raster cell, then the cell counters are scanned and the records scattered, i.e.
+ * on return `workspace` is in exactly the state pgdvs_bin_points would leave it in for
+ *   N = n_views, P = n_jobs*H*W (capacity), radius_max = radius, features = rgb (C = 3)
+ * and can be handed to pgdvs_rasterize_composite with those arguments.
+ * xyz_ndc / rgb / first_idx / num_points may be NULL (not materialised). */
+int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int W, float radius, size_t* bytes);
+int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras, int n_views, int H,
+                  int W, float radius, float* xyz_ndc, float* rgb, int64_t* first_idx,
+                  int64_t* num_points, int64_t* total_points, void* workspace, size_t workspace_bytes,
+                  void* stream);
+
+/* Pack source frames as (r,g,b,depth) float4 planes so that the warp stage fetches frame-2
+ * colour (bilinear, pgdvs_renderer_dyn.py:350-356) and depth (nearest, :342-348) with four
+ * 128-bit loads.  frames_dev: device array [n_frames]. */
+typedef struct PgdvsFramePack {
+  const float* rgb;   /* [H,W,3] */
+  const float* depth; /* [H,W]   */
+  float* rgbd;        /* [H,W,4] out, 16-byte aligned */
+} PgdvsFramePack;
+int pgdvs_pack_rgbd(const PgdvsFramePack* frames_dev, int n_frames, int H, int W, void* stream);
 
 /* World -> NDC only (PointsRasterizer.transform) for an already-built cloud, e.g. the one
  * handed to render_dyn_pcl (pgdvs_renderer_dyn.py:671-724) or StaticGeoPointRenderer. */

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = (
     "pgdvs_abi_version", "pgdvs_error_string", "pgdvs_struct_layout", "pgdvs_bin_workspace_bytes", "pgdvs_bin_points",
     "pgdvs_rasterize_composite", "pgdvs_composite", "pgdvs_uwp_workspace_bytes",
     "pgdvs_unproject_warp_project", "pgdvs_project_points", "pgdvs_merge_blend",
+    "pgdvs_uwp_bin_workspace_bytes", "pgdvs_uwp_bin", "pgdvs_pack_rgbd",
     "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist",
 )
 
@@ -32,10 +33,15 @@ class PgdvsUwpJob(ctypes.Structure):
     _fields_ = [
         ("depth1", c_void_p), ("rgb1", c_void_p), ("mask1", c_void_p), ("flow12", c_void_p),
         ("occ12", c_void_p), ("depth2", c_void_p), ("rgb2", c_void_p), ("keep", c_void_p),
+        ("rgbd2", c_void_p),
         ("M1", c_float * 9), ("o1", c_float * 3), ("K2inv", c_float * 9), ("R2", c_float * 9),
         ("o2", c_float * 3), ("w1", c_float), ("w2", c_float), ("same_time", c_int32),
         ("view", c_int32),
     ]
+
+
+class PgdvsFramePack(ctypes.Structure):
+    _fields_ = [("rgb", c_void_p), ("depth", c_void_p), ("rgbd", c_void_p)]
 
 
 class PgdvsError(RuntimeError):
@@ -79,6 +85,13 @@ def lib():
     L.pgdvs_unproject_warp_project.argtypes = [
         c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
         c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.pgdvs_uwp_bin_workspace_bytes.restype = c_int
+    L.pgdvs_uwp_bin_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_float, POINTER(c_size_t)]
+    L.pgdvs_uwp_bin.restype = c_int
+    L.pgdvs_uwp_bin.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.pgdvs_pack_rgbd.restype = c_int
+    L.pgdvs_pack_rgbd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p]
     L.pgdvs_project_points.restype = c_int
     L.pgdvs_project_points.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     L.pgdvs_merge_blend.restype = c_int

@@ -20,31 +20,16 @@ struct BinParams {
   const int64_t* first_idx;
   const int64_t* num_points;
   int C;
-  int H, W, halo, GW, GH;
-  float xf0, yf0;  // NDC centre of output column 0 / row 0
-  float inv_pix;   // pixels per NDC unit = min(H,W)/2
+  CellGrid g;
   int* cell_start;
   int2* rank;
   float4* recA;
   float4* recB;
+  // fused path only: records in packed order written by the uwp kernel, and their count
+  const float4* preA;
+  const float4* preB;
+  const int64_t* total;
 };
-
-// cell of the nearest pixel centre, in extended-grid coordinates; -1 if the point can
-// never be rasterized (behind the camera, or further than `halo` cells outside the image)
-__device__ __forceinline__ int point_cell(const BinParams& p, int n, float x, float y, float z) {
-  if (z < 0.0f) return -1;  // pytorch3d: `if (pz < 0) continue;`
-  // pixel centres: xf(col) = xf0 - col / inv_pix  ->  col = (xf0 - x) * inv_pix
-  const float colf = (p.xf0 - x) * p.inv_pix;
-  const float rowf = (p.yf0 - y) * p.inv_pix;
-  // NaN / huge coordinates fail these comparisons and are dropped (they can never satisfy
-  // dist2 < r2 either)
-  if (!(colf > -(float)p.halo - 1.0f && colf < (float)(p.W + p.halo))) return -1;
-  if (!(rowf > -(float)p.halo - 1.0f && rowf < (float)(p.H + p.halo))) return -1;
-  const int gx = __float2int_rn(colf) + p.halo;
-  const int gy = __float2int_rn(rowf) + p.halo;
-  if (gx < 0 || gx >= p.GW || gy < 0 || gy >= p.GH) return -1;
-  return (n * p.GH + gy) * p.GW + gx;
-}
 
 __global__ void __launch_bounds__(256) k_count(BinParams p) {
   const int n = blockIdx.y;
@@ -56,7 +41,7 @@ __global__ void __launch_bounds__(256) k_count(BinParams p) {
     const float x = __ldg(p.points + q * 3 + 0);
     const float y = __ldg(p.points + q * 3 + 1);
     const float z = __ldg(p.points + q * 3 + 2);
-    const int cell = point_cell(p, n, x, y, z);
+    const int cell = point_cell(p.g, n, x, y, z);
     int rank = 0;
     if (cell >= 0) rank = atomicAdd(p.cell_start + cell, 1);
     p.rank[q] = make_int2(cell, rank);
@@ -87,6 +72,19 @@ __global__ void __launch_bounds__(256) k_fill(BinParams p) {
       if (p.radius != nullptr) f[3] = __ldg(p.radius + q);
       p.recB[pos] = make_float4(f[0], f[1], f[2], f[3]);
     }
+  }
+}
+
+// Fused path: the uwp kernel already produced (cell, rank) and the packed-order records.
+__global__ void __launch_bounds__(256) k_fill_pre(BinParams p) {
+  const int64_t total = *p.total;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int2 cr = p.rank[q];
+    if (cr.x < 0) continue;
+    const int pos = __ldg(p.cell_start + cr.x) + cr.y;
+    p.recA[pos] = __ldg(p.preA + q);
+    p.recB[pos] = __ldg(p.preB + q);
   }
 }
 
@@ -213,16 +211,10 @@ extern "C" int pgdvs_bin_points(const float* points, const float* features, int 
   p.first_idx = first_idx;
   p.num_points = num_points;
   p.C = features ? C : 0;
-  p.H = H;
-  p.W = W;
-  p.halo = L.halo;
-  p.GW = L.GW;
-  p.GH = L.GH;
-  const NdcAxis ax = make_ndc_axis(W, H), ay = make_ndc_axis(H, W);
-  // centre of output column 0 is PixToNonSquareNdc(W-1, W, H) (host evaluation, fp32)
-  p.xf0 = -ax.offset + (ax.range * (float)(W - 1) + ax.offset) / (float)W;
-  p.yf0 = -ay.offset + (ay.range * (float)(H - 1) + ay.offset) / (float)H;
-  p.inv_pix = 0.5f * (float)(H < W ? H : W);
+  p.g = make_cell_grid(H, W, L.halo);
+  p.preA = nullptr;
+  p.preB = nullptr;
+  p.total = nullptr;
   p.cell_start = reinterpret_cast<int*>(ws + L.off_start);
   p.rank = reinterpret_cast<int2*>(ws + L.off_rank);
   p.recA = reinterpret_cast<float4*>(ws + L.off_recA);
@@ -256,3 +248,30 @@ extern "C" int pgdvs_bin_points(const float* points, const float* features, int 
   }
   return PGDVS_OK;
 }
+
+// Second half of the fused path (called by pgdvs_uwp_bin in uwp.cu): scan the cell counters
+// the uwp kernel accumulated, then scatter its packed-order records into cell order.
+namespace pgdvs {
+int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,
+                        const int64_t* total_dev, cudaStream_t stream) {
+  BinParams p = {};
+  p.cell_start = reinterpret_cast<int*>(ws + L.off_start);
+  p.rank = reinterpret_cast<int2*>(ws + L.off_rank);
+  p.recA = reinterpret_cast<float4*>(ws + L.off_recA);
+  p.recB = reinterpret_cast<float4*>(ws + L.off_recB);
+  p.preA = reinterpret_cast<const float4*>(ws + T.off_preA);
+  p.preB = reinterpret_cast<const float4*>(ws + T.off_preB);
+  p.total = total_dev;
+  k_scan<<<(unsigned)L.n_tiles, 1024, 0, stream>>>(
+      p.cell_start, reinterpret_cast<unsigned long long*>(ws + L.off_state),
+      reinterpret_cast<int*>(ws + L.off_ticket));
+  if (int rc = check_launch()) return rc;
+  if (capacity > 0) {
+    int64_t g = (capacity + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    k_fill_pre<<<(unsigned)g, 256, 0, stream>>>(p);
+    if (int rc = check_launch()) return rc;
+  }
+  return 0;
+}
+}  // namespace pgdvs

@@ -107,6 +107,64 @@ inline BinLayout make_bin_layout(int N, int H, int W, int64_t P, float radius_ma
   return L;
 }
 
+// The fused path (uwp kernel counts cells itself) parks its not-yet-sorted records behind
+// the regular layout, so the rasterizer sees the same front part in both modes.
+struct FusedTail {
+  size_t off_preA;  // float4 [P]  (x_ndc, y_ndc, z, packed idx) in packed (reference) order
+  size_t off_preB;  // float4 [P]  (r, g, b, 0)
+  size_t total;
+};
+
+inline FusedTail make_fused_tail(const BinLayout& L, int64_t P) {
+  FusedTail T;
+  size_t o = L.total;
+  T.off_preA = o;
+  o = align256(o + sizeof(float4) * (size_t)(P > 0 ? P : 1));
+  T.off_preB = o;
+  o = align256(o + sizeof(float4) * (size_t)(P > 0 ? P : 1));
+  T.total = o;
+  return T;
+}
+
+// Geometry of the extended 1-pixel cell grid (see BinLayout).
+struct CellGrid {
+  int H, W, halo, GW, GH;
+  float xf0, yf0;  // NDC centre of output column 0 / row 0
+  float inv_pix;   // pixels per NDC unit = min(H,W)/2
+};
+
+inline CellGrid make_cell_grid(int H, int W, int halo) {
+  CellGrid g;
+  g.H = H;
+  g.W = W;
+  g.halo = halo;
+  g.GW = W + 2 * halo;
+  g.GH = H + 2 * halo;
+  const NdcAxis ax = make_ndc_axis(W, H), ay = make_ndc_axis(H, W);
+  // centre of output column 0 is PixToNonSquareNdc(W-1, W, H) (host evaluation, fp32)
+  g.xf0 = -ax.offset + (ax.range * (float)(W - 1) + ax.offset) / (float)W;
+  g.yf0 = -ay.offset + (ay.range * (float)(H - 1) + ay.offset) / (float)H;
+  g.inv_pix = 0.5f * (float)(H < W ? H : W);
+  return g;
+}
+
+// cell of the nearest pixel centre, in extended-grid coordinates of view n; -1 if the point
+// can never be rasterized (behind the camera, or further than `halo` cells outside the image)
+__device__ __forceinline__ int point_cell(const CellGrid& g, int n, float x, float y, float z) {
+  if (z < 0.0f) return -1;  // pytorch3d: `if (pz < 0) continue;`
+  // pixel centres: xf(col) = xf0 - col / inv_pix  ->  col = (xf0 - x) * inv_pix
+  const float colf = (g.xf0 - x) * g.inv_pix;
+  const float rowf = (g.yf0 - y) * g.inv_pix;
+  // NaN / huge coordinates fail these comparisons and are dropped (they can never satisfy
+  // dist2 < r2 either)
+  if (!(colf > -(float)g.halo - 1.0f && colf < (float)(g.W + g.halo))) return -1;
+  if (!(rowf > -(float)g.halo - 1.0f && rowf < (float)(g.H + g.halo))) return -1;
+  const int gx = __float2int_rn(colf) + g.halo;
+  const int gy = __float2int_rn(rowf) + g.halo;
+  if (gx < 0 || gx >= g.GW || gy < 0 || gy >= g.GH) return -1;
+  return (n * g.GH + gy) * g.GW + gx;
+}
+
 // PointsRasterizer.transform for PerspectiveCameras(in_ndc=True):
 //   view = p @ R + T ; x = (fx*X + px*Z)/Z ; y = (fy*Y + py*Z)/Z ; z = Z (view depth)
 __device__ __forceinline__ float3 world_to_ndc(const PgdvsCamera& c, float wx, float wy, float wz) {

@@ -107,14 +107,15 @@ struct KList {
 
 struct PixelCtx {
   float xf, yf, r2;
-  bool per_point_r;
 };
 
+// PPR = per-point radius (recB.w); the scalar-radius instantiation carries no extra load/branch
+template <bool PPR>
 __device__ __forceinline__ bool hit_test(const PixelCtx& c, const float4 a,
                                          const float4* __restrict__ recB, int j) {
   const float d2 = dist2_rn(a.x, a.y, c.xf, c.yf);
   float r2 = c.r2;
-  if (c.per_point_r) {
+  if (PPR) {
     const float r = __ldg(&recB[j].w);
     r2 = __fmul_rn(r, r);
   }
@@ -122,7 +123,7 @@ __device__ __forceinline__ bool hit_test(const PixelCtx& c, const float4 a,
 }
 
 // Tie-aware rescan of one pixel (rare).  Kept out of line so the fast path stays small.
-template <int KP>
+template <int KP, bool PPR>
 __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx& c, int n, int x,
                                           int y, float* zout, int* sout) {
   KList<KP> q;
@@ -134,7 +135,7 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
     const int e = __ldg(p.cell_start + cell0 + span);
     for (int j = s; j < e; ++j) {
       const float4 a = __ldg(p.recA + j);
-      if (hit_test(c, a, p.recB, j)) q.insert_exact(a.z, __float_as_int(a.w), j, p.recA);
+      if (hit_test<PPR>(c, a, p.recB, j)) q.insert_exact(a.z, __float_as_int(a.w), j, p.recA);
     }
   }
 #pragma unroll
@@ -144,7 +145,7 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
   }
 }
 
-template <int KP>
+template <int KP, bool PPR>
 __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ RasterParams p) {
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
@@ -154,7 +155,6 @@ __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ Ra
   c.xf = pixel_center_ndc(p.ax, x);
   c.yf = pixel_center_ndc(p.ay, y);
   c.r2 = p.r2;
-  c.per_point_r = p.r2 < 0.0f;
   const float4* __restrict__ recA = p.recA;
   const float4* __restrict__ recB = p.recB;
 
@@ -173,10 +173,17 @@ __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ Ra
     const int s2 = __ldg(cs + 2 * p.GW), e2 = __ldg(cs + 2 * p.GW + 3);
     const int c0 = e0 - s0, c01 = c0 + (e1 - s1), total = c01 + (e2 - s2);
     const int o1 = s1 - c0, o2 = s2 - c01;
+    // software-pipelined: the record of iteration t+1 is in flight while t is processed
+    int j = (0 < c0 ? s0 : (0 < c01 ? o1 : o2));
+    float4 a = (total > 0) ? __ldg(recA + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = 0; t < total; ++t) {
-      const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-      const float4 a = __ldg(recA + j);
-      if (hit_test(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
+      const int tn = t + 1;
+      const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
+      float4 an = a;
+      if (tn < total) an = __ldg(recA + jn);
+      if (hit_test<PPR>(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
+      a = an;
+      j = jn;
     }
   } else {
     for (int ry = 0; ry < span; ++ry) {
@@ -184,14 +191,14 @@ __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ Ra
       const int e = __ldg(cs + (int64_t)ry * p.GW + span);
       for (int j = s; j < e; ++j) {
         const float4 a = __ldg(recA + j);
-        if (hit_test(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
+        if (hit_test<PPR>(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
       }
     }
   }
   if (tie || q.has_adjacent_tie()) {
     float zt[KP];
     int st[KP];
-    rescan_exact<KP>(p, c, n, x, y, zt, st);
+    rescan_exact<KP, PPR>(p, c, n, x, y, zt, st);
 #pragma unroll
     for (int i = 0; i < KP; ++i) {
       q.z[i] = zt[i];
@@ -206,26 +213,47 @@ __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ Ra
   // pass 1: fragments (idx / zbuf / dists) and the PointsRenderer weights
   float w[KP];
   float t_alpha = 0.f;
+  const bool vec4 = (KP % 4 == 0) && (K == KP);  // K*4 B per pixel is a multiple of 16 B
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    w[k] = 0.f;
-    if (k < K) {
-      const int sl = q.s[k];
-      int o_idx = -1;
-      float o_z = -1.0f, o_d = -1.0f;
-      if (sl >= 0) {
-        const float4 a = __ldg(recA + sl);
-        o_d = dist2_rn(a.x, a.y, c.xf, c.yf);
-        o_idx = __float_as_int(a.w);
-        o_z = a.z;
-        if (mode != PGDVS_COMPOSITE_NONE) {
-          w[k] = __fsub_rn(1.0f, __fdiv_rn(o_d, p.rr_weight));  // 1 - dists/(r*r)
-          t_alpha = __fadd_rn(t_alpha, w[k]);
+  for (int k0 = 0; k0 < KP; k0 += 4) {
+    int o_idx[4];
+    float o_z[4], o_d[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = k0 + kk;
+      o_idx[kk] = -1;
+      o_z[kk] = -1.0f;
+      o_d[kk] = -1.0f;
+      if (k < KP) {
+        w[k] = 0.f;
+        const int sl = (k < K) ? q.s[k] : -1;
+        if (sl >= 0) {
+          const float4 a = __ldg(recA + sl);
+          o_d[kk] = dist2_rn(a.x, a.y, c.xf, c.yf);
+          o_idx[kk] = __float_as_int(a.w);
+          o_z[kk] = a.z;
+          if (mode != PGDVS_COMPOSITE_NONE) {
+            w[k] = __fsub_rn(1.0f, __fdiv_rn(o_d[kk], p.rr_weight));  // 1 - dists/(r*r)
+            t_alpha = __fadd_rn(t_alpha, w[k]);
+          }
         }
       }
-      if (p.idx) p.idx[pix * K + k] = o_idx;
-      if (p.zbuf) p.zbuf[pix * K + k] = o_z;
-      if (p.dists) p.dists[pix * K + k] = o_d;
+    }
+    if (vec4) {
+      const int64_t o = pix * K + k0;
+      if (p.idx) *reinterpret_cast<int4*>(p.idx + o) = make_int4(o_idx[0], o_idx[1], o_idx[2], o_idx[3]);
+      if (p.zbuf) *reinterpret_cast<float4*>(p.zbuf + o) = make_float4(o_z[0], o_z[1], o_z[2], o_z[3]);
+      if (p.dists) *reinterpret_cast<float4*>(p.dists + o) = make_float4(o_d[0], o_d[1], o_d[2], o_d[3]);
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk;
+        if (k < K) {
+          if (p.idx) p.idx[pix * K + k] = o_idx[kk];
+          if (p.zbuf) p.zbuf[pix * K + k] = o_z[kk];
+          if (p.dists) p.dists[pix * K + k] = o_d[kk];
+        }
+      }
     }
   }
   if (mode == PGDVS_COMPOSITE_NONE) return;
@@ -276,7 +304,10 @@ template <int KP>
 static int launch_raster(const RasterParams& p, cudaStream_t stream) {
   dim3 block(32, 8);
   dim3 grid((p.W + 31) / 32, (p.H + 7) / 8, p.N);
-  k_raster_cells<KP><<<grid, block, 0, stream>>>(p);
+  if (p.r2 < 0.0f)
+    k_raster_cells<KP, true><<<grid, block, 0, stream>>>(p);
+  else
+    k_raster_cells<KP, false><<<grid, block, 0, stream>>>(p);
   return check_launch();
 }
 

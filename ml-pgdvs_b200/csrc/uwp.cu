@@ -1,21 +1,28 @@
 // Fused unproject -> flow-warp -> time-lerp -> project kernel.
 //
 // One launch turns a batch of (target view, source-frame pair) jobs into a packed NDC point
-// cloud ready for binning.  It replaces ~25 separate torch kernels and six boolean-index
-// compactions (each a host sync) of the reference:
+// cloud ready for the rasterizer.  It replaces ~25 separate torch kernels and six
+// boolean-index compactions (each a host sync) of the reference:
 //   get_batched_rays                 pgdvs_renderer_base.py:17-57
 //   compute_dyn_pcl (geometry part)  pgdvs_renderer_dyn.py:304-388
 //   w2c / camera / transform         pgdvs_renderer_dyn.py:676-687 + PointsRasterizer.transform
 //
 // Each thread owns 4 consecutive source pixels (float4-vectorised, fully coalesced reads of
-// depth / mask / occlusion / flow / rgb).  Surviving points are written in the reference's
-// order (job-major, row-major pixels): a block-level prefix sum orders points inside a
-// 1024-pixel tile and a single-pass chained scan (decoupled look-back, ticketed tiles)
-// orders the tiles, so the packed indices — and therefore the rasterizer's idx output —
-// are identical to the reference's boolean-mask compaction.
+// depth / mask / occlusion / flow / rgb).  Frame-2 colour (bilinear) and depth (nearest) are
+// gathered from a packed (r,g,b,depth) float4 plane when the caller provides one: the nearest
+// pixel is always one of the four bilinear taps, so 4 x 128-bit loads replace 13 scalar ones.
+// Surviving points are written in the reference's order (job-major, row-major pixels): a
+// block-level prefix sum orders points inside a 1024-pixel tile and a single-pass chained
+// scan (decoupled look-back, ticketed tiles) orders the tiles, so the packed indices — and
+// therefore the rasterizer's idx output — are identical to the reference's boolean-mask
+// compaction.  In the fused mode (pgdvs_uwp_bin) the kernel also files every point under its
+// raster cell (one atomicAdd), which removes the separate counting pass over the cloud.
 #include "common.cuh"
 
 namespace pgdvs {
+
+int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,
+                        const int64_t* total_dev, cudaStream_t stream);
 
 constexpr int kUwpThreads = 256;
 constexpr int kUwpPix = 4;                               // pixels per thread
@@ -29,13 +36,19 @@ struct UwpParams {
   int n_jobs, H, W;
   int tiles_per_job;
   int64_t n_tiles;
-  float* xyz_ndc;
-  float* rgb;
-  float* xyz_world;
-  int32_t* src_pix;
+  float* xyz_ndc;    // [cap,3] or null
+  float* rgb;        // [cap,3] or null
+  float* xyz_world;  // [cap,3] or null
+  int32_t* src_pix;  // [cap] or null
   unsigned long long* state;  // [n_tiles]
   int* ticket;
   int64_t* job_start;         // [n_jobs + 1]
+  // fused binning (all null/0 in the plain mode)
+  CellGrid g;
+  int* cell_count;
+  int2* rank;
+  float4* preA;
+  float4* preB;
 };
 
 // torch grid_sample(align_corners=False) source index of pixel coordinate c on an axis of
@@ -57,6 +70,7 @@ __device__ __forceinline__ void load4(const float* p, int64_t i, bool vec, int64
   }
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ UwpParams p) {
   __shared__ int s_tile;
   __shared__ int s_warp[kUwpThreads / 32];
@@ -71,6 +85,8 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
   const int64_t pix0 = (int64_t)jt * kUwpTile + (int64_t)threadIdx.x * kUwpPix;
   const bool in_range = pix0 < HW;
   const bool vec = ((HW & 3) == 0) && in_range;  // host guarantees 16-byte aligned planes
+  // (u, v) of the first pixel; the other three follow by incrementing (one div per thread)
+  const int v0 = (int)(pix0 / p.W), u0 = (int)(pix0 - (int64_t)v0 * p.W);
 
   // ------------------------------------------------------------ validity (cheap loads only)
   float m[4] = {0, 0, 0, 0}, fl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -81,17 +97,19 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
     load4(J.flow12, pix0 * 2 + 4, vec, HW * 2, fl + 4);
     float oc[4] = {0, 0, 0, 0};
     if (J.occ12 != nullptr) load4(J.occ12, pix0, vec, HW, oc);
+    int uu = u0, vv = v0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int64_t pix = pix0 + k;
-      if (pix >= HW) break;
-      bool ok = (m[k] != 0.0f);                       // dyn_mask.bool()
-      if (J.occ12 != nullptr) ok = ok && !(oc[k] > 0.0f);  // ~(occ > 0) & mask
-      const float u = (float)(int)(pix % p.W), v = (float)(int)(pix / p.W);
-      const float u2 = __fadd_rn(u, fl[2 * k]), v2 = __fadd_rn(v, fl[2 * k + 1]);
-      ok = ok && (u2 >= 0.0f) && (u2 <= (float)(p.W - 1)) && (v2 >= 0.0f) && (v2 <= (float)(p.H - 1));
-      if (ok && J.keep != nullptr) ok = (J.keep[pix] != 0);
-      if (ok) valid |= 1u << k;
+      if (pix < HW) {
+        bool ok = (m[k] != 0.0f);                            // dyn_mask.bool()
+        if (J.occ12 != nullptr) ok = ok && !(oc[k] > 0.0f);  // ~(occ > 0) & mask
+        const float u2 = __fadd_rn((float)uu, fl[2 * k]), v2 = __fadd_rn((float)vv, fl[2 * k + 1]);
+        ok = ok && (u2 >= 0.0f) && (u2 <= (float)(p.W - 1)) && (v2 >= 0.0f) && (v2 <= (float)(p.H - 1));
+        if (ok && J.keep != nullptr) ok = (J.keep[pix] != 0);
+        if (ok) valid |= 1u << k;
+      }
+      if (++uu == p.W) { uu = 0; ++vv; }
     }
   }
   const int cnt = __popc(valid);
@@ -166,11 +184,14 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
     load4(J.rgb1, pix0 * 3 + 4, vec, HW * 3, c1 + 4);
     load4(J.rgb1, pix0 * 3 + 8, vec, HW * 3, c1 + 8);
   }
+  const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
+  int uu = u0, vv = v0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (!(valid & (1u << k))) continue;
+    const float u = (float)uu, v = (float)vv;
     const int64_t pix = pix0 + k;
-    const float u = (float)(int)(pix % p.W), v = (float)(int)(pix / p.W);
+    if (++uu == p.W) { uu = 0; ++vv; }
+    if (!(valid & (1u << k))) continue;
     // rays_d = (c2w[:3,:3] @ K^-1) @ [u, v, 1]
     float wx = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
     float wy = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
@@ -184,25 +205,40 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
       const float iy = grid_unnormalize(v2, (float)p.H);
       // depth_2: grid_sample(mode="nearest"): nearbyint (half to even), zeros padding
       const float nx = nearbyintf(ix), ny = nearbyintf(iy);
-      float dep2 = 0.0f;
-      if (nx >= 0.0f && nx <= (float)(p.W - 1) && ny >= 0.0f && ny <= (float)(p.H - 1))
-        dep2 = __ldg(J.depth2 + (int64_t)ny * p.W + (int64_t)nx);
       // rgb: grid_sample(rgb_2, mode="bilinear"), zeros padding  (colour comes from frame 2)
       const float x0f = floorf(ix), y0f = floorf(iy);
       const float tw = __fsub_rn(ix, x0f), te = __fsub_rn(1.0f, tw);
       const float tn = __fsub_rn(iy, y0f), ts = __fsub_rn(1.0f, tn);
       const int x0 = (int)x0f, y0 = (int)y0f;
       const float wgt[4] = {__fmul_rn(ts, te), __fmul_rn(ts, tw), __fmul_rn(tn, te), __fmul_rn(tn, tw)};
-      const int xs[4] = {x0, x0 + 1, x0, x0 + 1};
-      const int ys[4] = {y0, y0, y0 + 1, y0 + 1};
+      float dep2 = 0.0f;
       cr = cg = cb = 0.0f;
+      if (rgbd2 != nullptr) {
+        // the nearest pixel is one of the 4 bilinear taps: tap (ny==y0 ? 0 : 1, nx==x0 ? 0 : 1)
+        const int near_tap = ((ny != y0f) ? 2 : 0) + ((nx != x0f) ? 1 : 0);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (xs[t] >= 0 && xs[t] < p.W && ys[t] >= 0 && ys[t] < p.H) {
-          const float* q = J.rgb2 + ((int64_t)ys[t] * p.W + xs[t]) * 3;
-          cr = __fadd_rn(cr, __fmul_rn(__ldg(q + 0), wgt[t]));
-          cg = __fadd_rn(cg, __fmul_rn(__ldg(q + 1), wgt[t]));
-          cb = __fadd_rn(cb, __fmul_rn(__ldg(q + 2), wgt[t]));
+        for (int t = 0; t < 4; ++t) {
+          const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
+          if (xs >= 0 && xs < p.W && ys >= 0 && ys < p.H) {
+            const float4 q = __ldg(rgbd2 + (int64_t)ys * p.W + xs);
+            cr = __fadd_rn(cr, __fmul_rn(q.x, wgt[t]));
+            cg = __fadd_rn(cg, __fmul_rn(q.y, wgt[t]));
+            cb = __fadd_rn(cb, __fmul_rn(q.z, wgt[t]));
+            if (t == near_tap) dep2 = q.w;
+          }
+        }
+      } else {
+        if (nx >= 0.0f && nx <= (float)(p.W - 1) && ny >= 0.0f && ny <= (float)(p.H - 1))
+          dep2 = __ldg(J.depth2 + (int64_t)ny * p.W + (int64_t)nx);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
+          if (xs >= 0 && xs < p.W && ys >= 0 && ys < p.H) {
+            const float* q = J.rgb2 + ((int64_t)ys * p.W + xs) * 3;
+            cr = __fadd_rn(cr, __fmul_rn(__ldg(q + 0), wgt[t]));
+            cg = __fadd_rn(cg, __fmul_rn(__ldg(q + 1), wgt[t]));
+            cb = __fadd_rn(cb, __fmul_rn(__ldg(q + 2), wgt[t]));
+          }
         }
       }
       // pcl_2 = o_2 + (R_2 @ (K_2^-1 @ [u2, v2, 1])) * depth_2
@@ -217,12 +253,24 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
       wz = J.w1 * wz + J.w2 * qz;
     }
     const float3 ndc = world_to_ndc(cam, wx, wy, wz);
-    p.xyz_ndc[out * 3 + 0] = ndc.x;
-    p.xyz_ndc[out * 3 + 1] = ndc.y;
-    p.xyz_ndc[out * 3 + 2] = ndc.z;
-    p.rgb[out * 3 + 0] = cr;
-    p.rgb[out * 3 + 1] = cg;
-    p.rgb[out * 3 + 2] = cb;
+    if (FUSED) {
+      const int cell = point_cell(p.g, J.view, ndc.x, ndc.y, ndc.z);
+      int rank = 0;
+      if (cell >= 0) rank = atomicAdd(p.cell_count + cell, 1);
+      p.rank[out] = make_int2(cell, rank);
+      p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
+      p.preB[out] = make_float4(cr, cg, cb, 0.0f);
+    }
+    if (p.xyz_ndc) {
+      p.xyz_ndc[out * 3 + 0] = ndc.x;
+      p.xyz_ndc[out * 3 + 1] = ndc.y;
+      p.xyz_ndc[out * 3 + 2] = ndc.z;
+    }
+    if (p.rgb) {
+      p.rgb[out * 3 + 0] = cr;
+      p.rgb[out * 3 + 1] = cg;
+      p.rgb[out * 3 + 2] = cb;
+    }
     if (p.xyz_world) {
       p.xyz_world[out * 3 + 0] = wx;
       p.xyz_world[out * 3 + 1] = wy;
@@ -246,8 +294,19 @@ __global__ void k_uwp_finalize(const PgdvsUwpJob* jobs, int n_jobs, int n_views,
     if (jv >= v) a = j;
     if (jv >= v + 1) b = j;
   }
-  first_idx[v] = job_start[a];
-  num_points[v] = job_start[b] - job_start[a];
+  if (first_idx) first_idx[v] = job_start[a];
+  if (num_points) num_points[v] = job_start[b] - job_start[a];
+}
+
+// (r,g,b) [HW,3] + depth [HW] -> (r,g,b,depth) float4 [HW] for a batch of frames
+__global__ void __launch_bounds__(256) k_pack_rgbd(const PgdvsFramePack* frames, int64_t HW) {
+  const PgdvsFramePack f = frames[blockIdx.y];
+  float4* __restrict__ out = reinterpret_cast<float4*>(f.rgbd);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    out[i] = make_float4(__ldg(f.rgb + i * 3), __ldg(f.rgb + i * 3 + 1), __ldg(f.rgb + i * 3 + 2),
+                         __ldg(f.depth + i));
+  }
 }
 
 struct UwpLayout {
@@ -272,6 +331,48 @@ static inline UwpLayout make_uwp_layout(int n_jobs, int H, int W) {
   return L;
 }
 
+static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras, int n_views, int H,
+                   int W, float* xyz_ndc, float* rgb, float* xyz_world, int32_t* src_pix,
+                   int64_t* first_idx, int64_t* num_points, int64_t* total_points, char* ws,
+                   const UwpLayout& L, const CellGrid* grid, int* cell_count, int2* rank, float4* preA,
+                   float4* preB, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.total, stream);
+  if (e != cudaSuccess) return (int)e;
+  if (n_jobs > 0) {
+    UwpParams p = {};
+    p.jobs = jobs;
+    p.cams = cameras;
+    p.n_jobs = n_jobs;
+    p.H = H;
+    p.W = W;
+    p.tiles_per_job = L.tiles_per_job;
+    p.n_tiles = L.n_tiles;
+    p.xyz_ndc = xyz_ndc;
+    p.rgb = rgb;
+    p.xyz_world = xyz_world;
+    p.src_pix = src_pix;
+    p.state = reinterpret_cast<unsigned long long*>(ws + L.off_state);
+    p.ticket = reinterpret_cast<int*>(ws + L.off_ticket);
+    p.job_start = reinterpret_cast<int64_t*>(ws + L.off_job_start);
+    if (grid != nullptr) {
+      p.g = *grid;
+      p.cell_count = cell_count;
+      p.rank = rank;
+      p.preA = preA;
+      p.preB = preB;
+      k_uwp<true><<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
+    } else {
+      k_uwp<false><<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
+    }
+    if (int rc = check_launch()) return rc;
+  }
+  // always run: also publishes total_points (0 when there are no jobs: job_start is zeroed)
+  k_uwp_finalize<<<(n_views + 128) / 128, 128, 0, stream>>>(
+      jobs, n_jobs, n_views, reinterpret_cast<const int64_t*>(ws + L.off_job_start), first_idx,
+      num_points, total_points);
+  return check_launch();
+}
+
 }  // namespace pgdvs
 
 using namespace pgdvs;
@@ -288,41 +389,71 @@ extern "C" int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs,
                                             int32_t* src_pix, int64_t* first_idx,
                                             int64_t* num_points, int64_t* total_points,
                                             void* workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
   if (n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !workspace) return PGDVS_E_BADARG;
   if (n_views > 0 && (!first_idx || !num_points)) return PGDVS_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;
   UwpLayout L = make_uwp_layout(n_jobs, H, W);
   if (workspace_bytes < L.total) return PGDVS_E_WORKSPACE;
   if ((int64_t)n_jobs * H * W >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
-  char* ws = static_cast<char*>(workspace);
-  cudaError_t e = cudaMemsetAsync(ws, 0, L.total, stream);
-  if (e != cudaSuccess) return (int)e;
-  if (n_jobs > 0) {
-    if (!jobs || !cameras || !xyz_ndc || !rgb) return PGDVS_E_BADARG;
-    UwpParams p;
-    p.jobs = jobs;
-    p.cams = cameras;
-    p.n_jobs = n_jobs;
-    p.H = H;
-    p.W = W;
-    p.tiles_per_job = L.tiles_per_job;
-    p.n_tiles = L.n_tiles;
-    p.xyz_ndc = xyz_ndc;
-    p.rgb = rgb;
-    p.xyz_world = xyz_world;
-    p.src_pix = src_pix;
-    p.state = reinterpret_cast<unsigned long long*>(ws + L.off_state);
-    p.ticket = reinterpret_cast<int*>(ws + L.off_ticket);
-    p.job_start = reinterpret_cast<int64_t*>(ws + L.off_job_start);
-    k_uwp<<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
-    if (int rc = check_launch()) return rc;
-  }
-  if (n_views > 0) {
-    k_uwp_finalize<<<(n_views + 127) / 128, 128, 0, stream>>>(
-        jobs, n_jobs, n_views, reinterpret_cast<const int64_t*>(ws + L.off_job_start), first_idx,
-        num_points, total_points);
-    if (int rc = check_launch()) return rc;
-  }
+  if (n_jobs > 0 && (!jobs || !cameras || !xyz_ndc || !rgb)) return PGDVS_E_BADARG;
+  return run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, xyz_world, src_pix, first_idx,
+                 num_points, total_points, static_cast<char*>(workspace), L, nullptr, nullptr, nullptr,
+                 nullptr, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int W, float radius,
+                                             size_t* bytes) {
+  if (!bytes || n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !(radius >= 0.0f))
+    return PGDVS_E_BADARG;
+  const int64_t cap = (int64_t)n_jobs * H * W;
+  if (cap >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  BinLayout B = make_bin_layout(n_views, H, W, cap, radius);
+  if (B.cells + kScanTile >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  FusedTail T = make_fused_tail(B, cap);
+  *bytes = T.total + align256(make_uwp_layout(n_jobs, H, W).total);
   return PGDVS_OK;
+}
+
+extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras,
+                             int n_views, int H, int W, float radius, float* xyz_ndc, float* rgb,
+                             int64_t* first_idx, int64_t* num_points, int64_t* total_points,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !workspace || !(radius >= 0.0f) || !total_points)
+    return PGDVS_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;
+  const int64_t cap = (int64_t)n_jobs * H * W;
+  if (cap >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  BinLayout B = make_bin_layout(n_views, H, W, cap, radius);
+  if (B.cells + kScanTile >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  FusedTail T = make_fused_tail(B, cap);
+  UwpLayout U = make_uwp_layout(n_jobs, H, W);
+  if (workspace_bytes < T.total + align256(U.total)) return PGDVS_E_WORKSPACE;
+  if (n_jobs > 0 && (!jobs || !cameras)) return PGDVS_E_BADARG;
+  if (n_views == 0) return PGDVS_OK;
+  char* ws = static_cast<char*>(workspace);
+  // cell counters, scan state and ticket sit contiguously at the front of the bin layout
+  cudaError_t e = cudaMemsetAsync(ws + B.off_start, 0, B.off_rank - B.off_start, stream);
+  if (e != cudaSuccess) return (int)e;
+  const CellGrid g = make_cell_grid(H, W, B.halo);
+  int rc = run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, nullptr, nullptr, first_idx,
+                   num_points, total_points, ws + T.total, U, &g,
+                   reinterpret_cast<int*>(ws + B.off_start), reinterpret_cast<int2*>(ws + B.off_rank),
+                   reinterpret_cast<float4*>(ws + T.off_preA), reinterpret_cast<float4*>(ws + T.off_preB),
+                   stream);
+  if (rc) return rc;
+  return bin_scan_fill_fused(ws, B, T, cap, total_points, stream);
+}
+
+extern "C" int pgdvs_pack_rgbd(const PgdvsFramePack* frames_dev, int n_frames, int H, int W,
+                               void* stream) {
+  if (n_frames < 0 || H <= 0 || W <= 0) return PGDVS_E_BADARG;
+  if (n_frames == 0) return PGDVS_OK;
+  if (!frames_dev) return PGDVS_E_BADARG;
+  const int64_t HW = (int64_t)H * W;
+  int gx = (int)((HW + 255) / 256);
+  if (gx > 148 * 4) gx = 148 * 4;
+  dim3 grid(gx, n_frames);
+  k_pack_rgbd<<<grid, 256, 0, (cudaStream_t)stream>>>(frames_dev, HW);
+  return check_launch();
 }

@@ -85,6 +85,7 @@ class SourcePair:
         self.flow_12, self.depth_2, self.rgb_2 = _plane(flow_12), _plane(depth_2), _plane(rgb_2)
         self.occ_12 = _plane(occ_12) if occ_12 is not None else None
         self.keep = keep
+        self.rgbd_2 = None  # packed (r,g,b,depth) plane of frame 2, attached by PreparedViews
         self.view = int(view)
         c2w_1, c2w_2 = _np44(c2w_1), _np44(c2w_2)
         if M1 is None:
@@ -110,6 +111,7 @@ class SourcePair:
         j.occ12 = self.occ_12.data_ptr() if self.occ_12 is not None else None
         j.depth2, j.rgb2 = self.depth_2.data_ptr(), self.rgb_2.data_ptr()
         j.keep = self.keep.data_ptr() if self.keep is not None else None
+        j.rgbd2 = self.rgbd_2.data_ptr() if self.rgbd_2 is not None else None
         _fill(j.M1, self.M1)
         _fill(j.o1, self.o1)
         _fill(j.K2inv, self.K2inv)
@@ -133,7 +135,8 @@ class PreparedViews:
     them is host work (tiny 4x4 algebra + one small H2D copy); once prepared, the whole hot path
     can be re-run with zero host<->device traffic."""
 
-    def __init__(self, pairs: Sequence[SourcePair], cams_p3d: Sequence, H: int, W: int, device):
+    def __init__(self, pairs: Sequence[SourcePair], cams_p3d: Sequence, H: int, W: int, device,
+                 pack_frames: bool = True):
         self.n_jobs, self.n_views, self.H, self.W = len(pairs), len(cams_p3d), H, W
         self.device = torch.device(device)
         assert all(pairs[i].view <= pairs[i + 1].view for i in range(self.n_jobs - 1)), \
@@ -146,10 +149,43 @@ class PreparedViews:
             _fill(c.focal, f)
             _fill(c.p0, p0)
             cam_structs.append(c)
+        # frame-2 planes are shared by many jobs (every source frame feeds several target views):
+        # pack each distinct (rgb, depth) pair once per render as an (r,g,b,depth) float4 plane
+        self.n_frames = 0
+        self.frames_dev = None
+        if pack_frames:
+            uniq = {}
+            for p in pairs:
+                if p.same_time:
+                    continue
+                key = (p.rgb_2.data_ptr(), p.depth_2.data_ptr())
+                if key not in uniq:
+                    uniq[key] = (len(uniq), p.rgb_2, p.depth_2)
+            if uniq:
+                self.rgbd = torch.empty((len(uniq), H, W, 4), dtype=torch.float32, device=device)
+                packs = [None] * len(uniq)
+                for key, (i, rgb, depth) in uniq.items():
+                    fp = _cabi.PgdvsFramePack()
+                    fp.rgb, fp.depth, fp.rgbd = rgb.data_ptr(), depth.data_ptr(), self.rgbd[i].data_ptr()
+                    packs[i] = fp
+                for p in pairs:
+                    if not p.same_time:
+                        p.rgbd_2 = self.rgbd[uniq[(p.rgb_2.data_ptr(), p.depth_2.data_ptr())][0]]
+                self.frames_dev = _upload_structs(packs, _cabi.PgdvsFramePack, device)
+                self.n_frames = len(uniq)
         self.jobs_dev = _upload_structs([p.to_struct() for p in pairs], _cabi.PgdvsUwpJob, device)
         self.cams_dev = _upload_structs(cam_structs, _cabi.PgdvsCamera, device)
         self._keepalive = list(pairs)
-        self.h2d_bytes = self.jobs_dev.numel() + self.cams_dev.numel()
+        self.h2d_bytes = self.jobs_dev.numel() + self.cams_dev.numel() + \
+            (self.frames_dev.numel() if self.frames_dev is not None else 0)
+
+    def pack_frames(self):
+        """(r,g,b) + depth -> (r,g,b,depth) planes for the distinct frame-2 images (1 launch)."""
+        if self.n_frames:
+            with torch.cuda.device(self.device):
+                _cabi.check(_cabi.lib().pgdvs_pack_rgbd(self.frames_dev.data_ptr(), self.n_frames, self.H,
+                                                        self.W, ops._stream_ptr(self.device)), "pgdvs_pack_rgbd")
+            ops.LAUNCHES["count"] += 1
 
 
 def prepare_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, device) -> PreparedViews:
@@ -178,6 +214,7 @@ def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=
     nbytes = ctypes.c_size_t(0)
     _cabi.check(L.pgdvs_uwp_workspace_bytes(n_jobs, H, W, ctypes.byref(nbytes)), "pgdvs_uwp_workspace_bytes")
     ws = ops._WS.get(device, nbytes.value, tag="uwp")
+    prep.pack_frames()
     with torch.cuda.device(device):
         _cabi.check(L.pgdvs_unproject_warp_project(
             prep.jobs_dev.data_ptr(), n_jobs, prep.cams_dev.data_ptr(), n_views, H, W, xyz_ndc.data_ptr(),
@@ -192,30 +229,69 @@ def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=
 
 def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int, compositor: str = "norm",
                     static_rgb: Optional[torch.Tensor] = None, return_fragments: bool = False,
-                    raster_events=None):
+                    raster_events=None, fused: bool = True, return_cloud: bool = False):
     """uwp kernel -> binning -> rasterize+composite(+mask, +static blend) for prepared views:
-    3 stream-ordered stages, zero host syncs."""
-    cloud = unproject_warp_project(prep)
-    out = ops.render_packed(cloud["xyz_ndc"], cloud["rgb"], cloud["first_idx"], cloud["num_points"],
-                            (prep.H, prep.W), radius, points_per_pixel, compositor=compositor,
-                            background=(0.0, 0.0, 0.0), static_rgb=static_rgb,
-                            return_fragments=return_fragments, return_mask=True,
-                            raster_events=raster_events)
-    out["first_idx"], out["num_points"], out["cloud"] = cloud["first_idx"], cloud["num_points"], cloud
+    stream-ordered stages, zero host syncs.  `fused=False` runs the stage-by-stage variant
+    (uwp -> packed [P,3] cloud -> pgdvs_bin_points -> rasterize), which gives identical results."""
+    if not fused:
+        cloud = unproject_warp_project(prep)
+        out = ops.render_packed(cloud["xyz_ndc"], cloud["rgb"], cloud["first_idx"], cloud["num_points"],
+                                (prep.H, prep.W), radius, points_per_pixel, compositor=compositor,
+                                background=(0.0, 0.0, 0.0), static_rgb=static_rgb,
+                                return_fragments=return_fragments, return_mask=True,
+                                raster_events=raster_events)
+        out["first_idx"], out["num_points"], out["cloud"] = cloud["first_idx"], cloud["num_points"], cloud
+        return out
+    # fused: [pack frames] -> uwp kernel (also files points under raster cells) -> scan -> fill
+    # -> rasterize+composite.  The packed [P,3] cloud is only materialised on request.
+    dev, H, W, n_jobs, n_views = prep.device, prep.H, prep.W, prep.n_jobs, prep.n_views
+    K = int(points_per_pixel)
+    if K < 1 or K > ops.kMaxPointsPerPixel:
+        raise ValueError("Must have 1 <= points_per_pixel <= %d" % ops.kMaxPointsPerPixel)
+    cap = n_jobs * H * W
+    L = _cabi.lib()
+    nbytes = ctypes.c_size_t(0)
+    _cabi.check(L.pgdvs_uwp_bin_workspace_bytes(n_jobs, n_views, H, W, float(radius), ctypes.byref(nbytes)),
+                "pgdvs_uwp_bin_workspace_bytes")
+    ws = ops._WS.get(dev, nbytes.value, tag="fused")
+    ws_ptr = ops._aligned_ptr(ws)
+    xyz_ndc = rgb = None
+    if return_cloud:
+        xyz_ndc = torch.empty((max(cap, 1), 3), dtype=torch.float32, device=dev)
+        rgb = torch.empty((max(cap, 1), 3), dtype=torch.float32, device=dev)
+    first_idx = torch.empty((n_views,), dtype=torch.int64, device=dev)
+    num_points = torch.empty((n_views,), dtype=torch.int64, device=dev)
+    total = torch.empty((1,), dtype=torch.int64, device=dev)
+    prep.pack_frames()
+    with torch.cuda.device(dev):
+        _cabi.check(L.pgdvs_uwp_bin(
+            prep.jobs_dev.data_ptr(), n_jobs, prep.cams_dev.data_ptr(), n_views, H, W, float(radius),
+            xyz_ndc.data_ptr() if xyz_ndc is not None else None, rgb.data_ptr() if rgb is not None else None,
+            first_idx.data_ptr(), num_points.data_ptr(), total.data_ptr(), ws_ptr, nbytes.value,
+            ops._stream_ptr(dev)), "pgdvs_uwp_bin")
+    ops.LAUNCHES["count"] += 4  # k_uwp, k_uwp_finalize, k_scan, k_fill_pre
+    out = ops.rasterize_workspace(ws_ptr, nbytes.value, dev, n_views, cap, H, W, K, float(radius), False, 3,
+                                  ops._COMPOSITORS[compositor], float(radius) * float(radius),
+                                  (0.0, 0.0, 0.0), static_rgb, return_fragments, True, raster_events)
+    out["first_idx"], out["num_points"] = first_idx, num_points
+    out["cloud"] = {"xyz_ndc": xyz_ndc, "rgb": rgb, "first_idx": first_idx, "num_points": num_points,
+                    "total": total, "_keepalive": prep}
     return out
 
 
 def render_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, *, radius: float,
                  points_per_pixel: int, compositor: str = "norm", static_rgb: Optional[torch.Tensor] = None,
-                 return_fragments: bool = False, device=None):
+                 return_fragments: bool = False, device=None, fused: bool = True,
+                 return_cloud: bool = False):
     """The whole hot path for a batch of target views.
 
     tgt_cams: per view (K44, c2w44) OpenCV; static_rgb optional [N,H,W,3] (GNT render).
-    Returns dict(image [N,H,W,3], mask [N,H,W,1], [idx,zbuf,dists], first_idx, num_points)."""
+    Returns dict(image [N,H,W,3], mask [N,H,W,1], [idx,zbuf,dists], first_idx, num_points, cloud)."""
     device = device if device is not None else pairs[0].depth_1.device
     prep = prepare_views(pairs, tgt_cams, H, W, device)
     return render_prepared(prep, radius=radius, points_per_pixel=points_per_pixel, compositor=compositor,
-                           static_rgb=static_rgb, return_fragments=return_fragments)
+                           static_rgb=static_rgb, return_fragments=return_fragments, fused=fused,
+                           return_cloud=return_cloud)
 
 
 # ----------------------------------------------------------------------------- L2 class

@@ -149,6 +149,20 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
             radius_t.data_ptr() if radius_t is not None else None, radius_max, H, W, ws_ptr,
             nbytes.value, stream), "pgdvs_bin_points")
         LAUNCHES["count"] += 3 if P > 0 else 1  # k_count, k_scan, k_fill
+    return rasterize_workspace(ws_ptr, nbytes.value, dev, N, P, H, W, K, radius_max, radius_t is not None,
+                               C, mode, rr_weight, background, static_rgb, return_fragments, return_mask,
+                               raster_events)
+
+
+def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int, W: int, K: int,
+                        radius_max: float, per_point_radius: bool, C: int, mode: int, rr_weight,
+                        background, static_rgb, return_fragments: bool, return_mask: bool,
+                        raster_events=None):
+    """Rasterize-and-composite over a workspace that pgdvs_bin_points / pgdvs_uwp_bin left in
+    the binned state (N, P, radius_max must repeat what the binning call was given)."""
+    L = _cabi.lib()
+    stream = _stream_ptr(dev)
+    with torch.cuda.device(dev):
         out = {}
         idx = zbuf = dists = image = mask = None
         if return_fragments:
@@ -174,7 +188,7 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
         if raster_events is not None:
             raster_events[0].record(torch.cuda.current_stream(dev))
         _cabi.check(L.pgdvs_rasterize_composite(
-            ws_ptr, nbytes.value, N, P, H, W, K, radius_max, 1 if radius_t is not None else 0, C, mode,
+            ws_ptr, ws_bytes, N, P, H, W, K, radius_max, 1 if per_point_radius else 0, C, mode,
             float(rr_weight) if rr_weight is not None else 1.0, bg,
             st.data_ptr() if st is not None else None,
             idx.data_ptr() if idx is not None else None,

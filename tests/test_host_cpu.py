@@ -60,7 +60,7 @@ def test_struct_layout_matches_library(lib):
     assert lib.pgdvs_struct_layout(lay) == 0
     assert list(lay) == [ctypes.sizeof(_cabi.PgdvsCamera), ctypes.sizeof(_cabi.PgdvsUwpJob),
                          _cabi.PgdvsUwpJob.M1.offset, _cabi.PgdvsUwpJob.view.offset]
-    assert lay[0] == 64 and lay[2] == 64
+    assert lay[0] == 64 and lay[2] == 72  # 9 pointers precede M1
 
 
 def test_host_camera_matches_reference_fixture(golden_dir):
