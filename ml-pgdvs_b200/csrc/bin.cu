@@ -4,11 +4,14 @@
 // coarse binning has a fixed max_points_per_bin that overflows on real clouds; here the
 // per-cell lists are sized exactly by a counting sort, so nothing can overflow.
 //
-//   k_count : one atomicAdd per point on its cell counter; the returned rank is kept so the
-//             fill pass needs no second atomic.
+//   k_count : one fire-and-forget atomic (RED) per point on its cell counter; the cell id is
+//             kept so the fill pass does not redo the projection-to-cell arithmetic.
 //   k_scan  : single-pass chained scan (decoupled look-back) over the cell counters,
 //             warp-shuffle prefix sums inside a tile, int4-vectorised loads/stores.
-//   k_fill  : scatter (x,y,z,idx) and the feature record to start[cell] + rank.
+//   k_fill  : pos = atomicAdd(cursor[cell], 1) on the scanned array itself, then scatter
+//             (x,y,z,idx) and the feature record.  The cursor array ends up holding per-cell
+//             END offsets; the rasterizer reads start(c) = end(c-1).  Four points per thread
+//             are kept in flight because the cell -> cursor -> scatter chain is latency-bound.
 #include "common.cuh"
 
 namespace pgdvs {
@@ -21,8 +24,8 @@ struct BinParams {
   const int64_t* num_points;
   int C;
   CellGrid g;
-  int* cell_start;
-  int2* rank;
+  int* cells;     // counts -> starts -> ends
+  int* cell_of;   // [P]
   float4* recA;
   float4* recB;
   // fused path only: records in packed order written by the uwp kernel, and their count
@@ -42,9 +45,8 @@ __global__ void __launch_bounds__(256) k_count(BinParams p) {
     const float y = __ldg(p.points + q * 3 + 1);
     const float z = __ldg(p.points + q * 3 + 2);
     const int cell = point_cell(p.g, n, x, y, z);
-    int rank = 0;
-    if (cell >= 0) rank = atomicAdd(p.cell_start + cell, 1);
-    p.rank[q] = make_int2(cell, rank);
+    if (cell >= 0) atomicAdd(p.cells + cell, 1);  // result unused -> RED
+    p.cell_of[q] = cell;
   }
 }
 
@@ -55,9 +57,9 @@ __global__ void __launch_bounds__(256) k_fill(BinParams p) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t q = first + i;
-    const int2 cr = p.rank[q];
-    if (cr.x < 0) continue;
-    const int pos = __ldg(p.cell_start + cr.x) + cr.y;
+    const int cell = p.cell_of[q];
+    if (cell < 0) continue;
+    const int pos = atomicAdd(p.cells + cell, 1);
     float4 a;
     a.x = __ldg(p.points + q * 3 + 0);
     a.y = __ldg(p.points + q * 3 + 1);
@@ -75,16 +77,34 @@ __global__ void __launch_bounds__(256) k_fill(BinParams p) {
   }
 }
 
-// Fused path: the uwp kernel already produced (cell, rank) and the packed-order records.
+// Fused path: the uwp kernel already produced the cell of every point and the packed-order
+// records.  Each thread moves kFillUnroll points with all loads, then all atomics, then all
+// stores issued back to back.
+constexpr int kFillUnroll = 4;
 __global__ void __launch_bounds__(256) k_fill_pre(BinParams p) {
   const int64_t total = *p.total;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int2 cr = p.rank[q];
-    if (cr.x < 0) continue;
-    const int pos = __ldg(p.cell_start + cr.x) + cr.y;
-    p.recA[pos] = __ldg(p.preA + q);
-    p.recB[pos] = __ldg(p.preB + q);
+  const int64_t base = ((int64_t)blockIdx.x * blockDim.x) * kFillUnroll + threadIdx.x;
+  int cell[kFillUnroll];
+  float4 a[kFillUnroll], b[kFillUnroll];
+#pragma unroll
+  for (int u = 0; u < kFillUnroll; ++u) {
+    const int64_t q = base + (int64_t)u * blockDim.x;
+    cell[u] = -1;
+    if (q < total) {
+      cell[u] = __ldg(p.cell_of + q);
+      a[u] = __ldg(p.preA + q);
+      b[u] = __ldg(p.preB + q);
+    }
+  }
+  int pos[kFillUnroll];
+#pragma unroll
+  for (int u = 0; u < kFillUnroll; ++u) pos[u] = (cell[u] >= 0) ? atomicAdd(p.cells + cell[u], 1) : -1;
+#pragma unroll
+  for (int u = 0; u < kFillUnroll; ++u) {
+    if (pos[u] >= 0) {
+      p.recA[pos[u]] = a[u];
+      p.recB[pos[u]] = b[u];
+    }
   }
 }
 
@@ -154,10 +174,7 @@ __global__ void __launch_bounds__(1024) k_scan(int* data, unsigned long long* st
         if (has_prefix) break;
         look -= 32;
       }
-      if (lane == 0) {
-        __threadfence();
-        atomicExch(state + tile, kFlagPrefix | (unsigned int)(prefix + aggregate));
-      }
+      if (lane == 0) atomicExch(state + tile, kFlagPrefix | (unsigned int)(prefix + aggregate));
     }
     if (lane == 0) s_prefix = prefix;
   }
@@ -169,6 +186,30 @@ __global__ void __launch_bounds__(1024) k_scan(int* data, unsigned long long* st
   o.z = o.y + v.y;
   o.w = o.z + v.z;
   base[threadIdx.x] = o;
+}
+
+// Second half of the fused path (called by pgdvs_uwp_bin in uwp.cu): scan the cell counters
+// the uwp kernel accumulated, then scatter its packed-order records into cell order.
+int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,
+                        const int64_t* total_dev, cudaStream_t stream) {
+  BinParams p = {};
+  p.cells = reinterpret_cast<int*>(ws + L.off_cells);
+  p.cell_of = reinterpret_cast<int*>(ws + L.off_cell_of);
+  p.recA = reinterpret_cast<float4*>(ws + L.off_recA);
+  p.recB = reinterpret_cast<float4*>(ws + L.off_recB);
+  p.preA = reinterpret_cast<const float4*>(ws + T.off_preA);
+  p.preB = reinterpret_cast<const float4*>(ws + T.off_preB);
+  p.total = total_dev;
+  k_scan<<<(unsigned)L.n_tiles, 1024, 0, stream>>>(
+      p.cells, reinterpret_cast<unsigned long long*>(ws + L.off_state),
+      reinterpret_cast<int*>(ws + L.off_ticket));
+  if (int rc = check_launch()) return rc;
+  if (capacity > 0) {
+    const int64_t g = (capacity + 256 * kFillUnroll - 1) / (256 * kFillUnroll);
+    k_fill_pre<<<(unsigned)g, 256, 0, stream>>>(p);
+    if (int rc = check_launch()) return rc;
+  }
+  return 0;
 }
 
 }  // namespace pgdvs
@@ -204,7 +245,7 @@ extern "C" int pgdvs_bin_points(const float* points, const float* features, int 
     return PGDVS_E_BADARG;
 
   char* ws = static_cast<char*>(workspace);
-  BinParams p;
+  BinParams p = {};
   p.points = points;
   p.features = features;
   p.radius = radius;
@@ -212,66 +253,31 @@ extern "C" int pgdvs_bin_points(const float* points, const float* features, int 
   p.num_points = num_points;
   p.C = features ? C : 0;
   p.g = make_cell_grid(H, W, L.halo);
-  p.preA = nullptr;
-  p.preB = nullptr;
-  p.total = nullptr;
-  p.cell_start = reinterpret_cast<int*>(ws + L.off_start);
-  p.rank = reinterpret_cast<int2*>(ws + L.off_rank);
+  p.cells = reinterpret_cast<int*>(ws + L.off_cells);
+  p.cell_of = reinterpret_cast<int*>(ws + L.off_cell_of);
   p.recA = reinterpret_cast<float4*>(ws + L.off_recA);
   p.recB = reinterpret_cast<float4*>(ws + L.off_recB);
 
-  // counters, scan state and ticket are contiguous at the front of the workspace
-  cudaError_t e = cudaMemsetAsync(ws + L.off_start, 0, L.off_rank - L.off_start, stream);
+  // front pad, counters, scan state and ticket are contiguous at the front of the workspace
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.off_zero_end, stream);
   if (e != cudaSuccess) return (int)e;
+  int gx = 1;
   if (P > 0) {
     // enough blocks to fill the machine even for one cloud; grid-stride inside
-    int64_t per_cloud = (P + (N > 0 ? N : 1) - 1) / (N > 0 ? N : 1);
-    int gx = (int)((per_cloud + 255) / 256);
+    const int64_t per_cloud = (P + N - 1) / N;
+    gx = (int)((per_cloud + 255) / 256);
     if (gx < 1) gx = 1;
     if (gx > 148 * 16) gx = 148 * 16;
-    dim3 grid(gx, N);
-    k_count<<<grid, 256, 0, stream>>>(p);
+    k_count<<<dim3(gx, N), 256, 0, stream>>>(p);
     if (int rc = check_launch()) return rc;
   }
   k_scan<<<(unsigned)L.n_tiles, 1024, 0, stream>>>(
-      p.cell_start, reinterpret_cast<unsigned long long*>(ws + L.off_state),
+      p.cells, reinterpret_cast<unsigned long long*>(ws + L.off_state),
       reinterpret_cast<int*>(ws + L.off_ticket));
   if (int rc = check_launch()) return rc;
   if (P > 0) {
-    int64_t per_cloud = (P + N - 1) / N;
-    int gx = (int)((per_cloud + 255) / 256);
-    if (gx < 1) gx = 1;
-    if (gx > 148 * 16) gx = 148 * 16;
-    dim3 grid(gx, N);
-    k_fill<<<grid, 256, 0, stream>>>(p);
+    k_fill<<<dim3(gx, N), 256, 0, stream>>>(p);
     if (int rc = check_launch()) return rc;
   }
   return PGDVS_OK;
 }
-
-// Second half of the fused path (called by pgdvs_uwp_bin in uwp.cu): scan the cell counters
-// the uwp kernel accumulated, then scatter its packed-order records into cell order.
-namespace pgdvs {
-int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,
-                        const int64_t* total_dev, cudaStream_t stream) {
-  BinParams p = {};
-  p.cell_start = reinterpret_cast<int*>(ws + L.off_start);
-  p.rank = reinterpret_cast<int2*>(ws + L.off_rank);
-  p.recA = reinterpret_cast<float4*>(ws + L.off_recA);
-  p.recB = reinterpret_cast<float4*>(ws + L.off_recB);
-  p.preA = reinterpret_cast<const float4*>(ws + T.off_preA);
-  p.preB = reinterpret_cast<const float4*>(ws + T.off_preB);
-  p.total = total_dev;
-  k_scan<<<(unsigned)L.n_tiles, 1024, 0, stream>>>(
-      p.cell_start, reinterpret_cast<unsigned long long*>(ws + L.off_state),
-      reinterpret_cast<int*>(ws + L.off_ticket));
-  if (int rc = check_launch()) return rc;
-  if (capacity > 0) {
-    int64_t g = (capacity + 255) / 256;
-    if (g > 148 * 32) g = 148 * 32;
-    k_fill_pre<<<(unsigned)g, 256, 0, stream>>>(p);
-    if (int rc = check_launch()) return rc;
-  }
-  return 0;
-}
-}  // namespace pgdvs

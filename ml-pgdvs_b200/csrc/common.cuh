@@ -64,10 +64,14 @@ struct BinLayout {
   int halo, GW, GH;
   int64_t cells;      // N * GH * GW
   int64_t n_tiles;    // scan tiles
-  size_t off_start;   // int32 [cells + 1]   counts, then exclusive starts (in place)
+  // int32 [cells + 1], preceded by a zeroed 256-byte pad so that element [-1] reads 0.
+  // Life cycle: per-cell counts -> (k_scan) exclusive starts -> (fill: atomicAdd cursor)
+  // per-cell ENDS.  The rasterizer therefore reads start(c) = cell_end[c - 1].
+  size_t off_cells;
   size_t off_state;   // uint64 [n_tiles]    decoupled look-back state
   size_t off_ticket;  // int32 [4]           scan ticket counter (+pad)
-  size_t off_rank;    // int2  [P]           (cell, rank within cell) per packed point
+  size_t off_zero_end;  // everything in [0, off_zero_end) is zeroed before each binning
+  size_t off_cell_of; // int32  [P]          cell of every packed point (-1 = never rasterized)
   size_t off_recA;    // float4 [P]          (x_ndc, y_ndc, z, packed idx as int bits)
   size_t off_recB;    // float4 [P]          features (C<=4) or (f0,f1,f2,radius)
   size_t total;
@@ -90,15 +94,16 @@ inline BinLayout make_bin_layout(int N, int H, int W, int64_t P, float radius_ma
   L.GH = H + 2 * L.halo;
   L.cells = (int64_t)N * L.GH * L.GW;
   L.n_tiles = (L.cells + 1 + kScanTile - 1) / kScanTile;
-  size_t o = 0;
-  L.off_start = o;
+  size_t o = 256;  // zero pad in front of the cell array (cell_end[-1] == 0)
+  L.off_cells = o;
   o = align256(o + sizeof(int32_t) * (size_t)(L.n_tiles * kScanTile));
   L.off_state = o;
   o = align256(o + sizeof(uint64_t) * (size_t)L.n_tiles);
   L.off_ticket = o;
   o = align256(o + 256);
-  L.off_rank = o;
-  o = align256(o + sizeof(int2) * (size_t)(P > 0 ? P : 1));
+  L.off_zero_end = o;
+  L.off_cell_of = o;
+  o = align256(o + sizeof(int32_t) * (size_t)(P > 0 ? P : 1));
   L.off_recA = o;
   o = align256(o + sizeof(float4) * (size_t)(P > 0 ? P : 1));
   L.off_recB = o;

@@ -18,7 +18,7 @@
 namespace pgdvs {
 
 struct RasterParams {
-  const int* cell_start;
+  const int* cell_end;  // per-cell END offsets; start(c) = cell_end[c - 1] (cell_end[-1] == 0)
   const float4* recA;
   const float4* recB;
   int N, H, W, K, C, halo, GW, GH;
@@ -131,8 +131,8 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
   const int span = 2 * p.halo + 1;
   for (int ry = 0; ry < span; ++ry) {
     const int64_t cell0 = ((int64_t)n * p.GH + (y + ry)) * p.GW + x;
-    const int s = __ldg(p.cell_start + cell0);
-    const int e = __ldg(p.cell_start + cell0 + span);
+    const int s = __ldg(p.cell_end + cell0 - 1);
+    const int e = __ldg(p.cell_end + cell0 + span - 1);
     for (int j = s; j < e; ++j) {
       const float4 a = __ldg(p.recA + j);
       if (hit_test<PPR>(c, a, p.recB, j)) q.insert_exact(a.z, __float_as_int(a.w), j, p.recA);
@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(256) k_raster_cells(const __grid_constant__ Ra
   bool tie = false;
 
   const int span = 2 * p.halo + 1;
-  const int* __restrict__ cs = p.cell_start + ((int64_t)n * p.GH + y) * p.GW + x;
+  // cs[c] = start of cell (x + c) of the first window row = cell_end[... - 1]
+  const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
   if (p.halo == 1) {
     // 3x3 cell window (every PGDVS configuration with r_px < 1.5): the three row runs are
     // walked by ONE flattened loop so that lanes with uneven rows do not wait for each other
@@ -339,7 +340,7 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
 
   const char* ws = static_cast<const char*>(workspace);
   RasterParams p;
-  p.cell_start = reinterpret_cast<const int*>(ws + L.off_start);
+  p.cell_end = reinterpret_cast<const int*>(ws + L.off_cells);
   p.recA = reinterpret_cast<const float4*>(ws + L.off_recA);
   p.recB = reinterpret_cast<const float4*>(ws + L.off_recB);
   p.N = N;

@@ -46,7 +46,7 @@ struct UwpParams {
   // fused binning (all null/0 in the plain mode)
   CellGrid g;
   int* cell_count;
-  int2* rank;
+  int* cell_of;
   float4* preA;
   float4* preB;
 };
@@ -71,7 +71,7 @@ __device__ __forceinline__ void load4(const float* p, int64_t i, bool vec, int64
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ UwpParams p) {
+__global__ void __launch_bounds__(kUwpThreads, 2) k_uwp(const __grid_constant__ UwpParams p) {
   __shared__ int s_tile;
   __shared__ int s_warp[kUwpThreads / 32];
   __shared__ long long s_prefix;
@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
+  int aggregate = 0;
   if (warp == 0) {
     const int w = (lane < kUwpThreads / 32) ? s_warp[lane] : 0;
     int winc = w;
@@ -132,18 +133,128 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
       const int o = __shfl_up_sync(0xffffffffu, winc, d);
       if (lane >= d) winc += o;
     }
-    if (lane < kUwpThreads / 32) s_warp[lane] = winc - w;
-    const int aggregate = __shfl_sync(0xffffffffu, winc, 31);
-    // ---------------------------------------------------------- order between tiles
+    if (lane < kUwpThreads / 32) s_warp[lane] = winc - w;  // read after the next barrier
+    aggregate = __shfl_sync(0xffffffffu, winc, 31);
+    // publish this tile's count NOW, so that successors never wait on our geometry
+    if (lane == 0)
+      atomicExch(p.state + tile, (tile == 0 ? kUFlagPrefix : kUFlagAgg) | (unsigned int)aggregate);
+  }
+
+  // ------------------------------------------------------------ geometry (branch-free over the
+  // 4 pixels so that all 16 frame-2 taps are in flight together; stores are predicated later)
+  float d1[4], c1[12];
+  float ox[4], oy[4], oz[4], cr[4], cg[4], cb[4], wx[4], wy[4], wz[4];
+  const bool any_valid = valid != 0;
+  const PgdvsCamera cam = p.cams[J.view];
+  const bool lerp = (J.same_time == 0);
+  if (any_valid) {
+    load4(J.depth1, pix0, vec, HW, d1);
+    if (!lerp) {
+      load4(J.rgb1, pix0 * 3, vec, HW * 3, c1);
+      load4(J.rgb1, pix0 * 3 + 4, vec, HW * 3, c1 + 4);
+      load4(J.rgb1, pix0 * 3 + 8, vec, HW * 3, c1 + 8);
+    }
+    const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
+    float u2a[4], v2a[4], wgt[4][4], dep2[4];
+    float4 tap[4][4];
+    int near_tap[4];
+    {
+      int uu = u0, vv = v0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float u = (float)uu, v = (float)vv;
+        if (++uu == p.W) { uu = 0; ++vv; }
+        // rays_d = (c2w[:3,:3] @ K^-1) @ [u, v, 1]
+        wx[k] = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
+        wy[k] = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
+        wz[k] = J.o1[2] + (J.M1[6] * u + J.M1[7] * v + J.M1[8]) * d1[k];
+        cr[k] = cg[k] = cb[k] = 0.0f;
+        dep2[k] = 0.0f;
+        if (lerp) {
+          const bool ok = (valid >> k) & 1u;
+          const float u2 = __fadd_rn(u, fl[2 * k]), v2 = __fadd_rn(v, fl[2 * k + 1]);
+          u2a[k] = u2;
+          v2a[k] = v2;
+          const float ix = grid_unnormalize(u2, (float)p.W);
+          const float iy = grid_unnormalize(v2, (float)p.H);
+          // depth_2: grid_sample(mode="nearest"): nearbyint (half to even), zeros padding
+          const float nx = nearbyintf(ix), ny = nearbyintf(iy);
+          // rgb: grid_sample(rgb_2, mode="bilinear"), zeros padding (colour comes from frame 2)
+          const float x0f = floorf(ix), y0f = floorf(iy);
+          const float tw = __fsub_rn(ix, x0f), te = __fsub_rn(1.0f, tw);
+          const float tn = __fsub_rn(iy, y0f), ts = __fsub_rn(1.0f, tn);
+          const int x0 = (int)x0f, y0 = (int)y0f;
+          wgt[k][0] = __fmul_rn(ts, te);
+          wgt[k][1] = __fmul_rn(ts, tw);
+          wgt[k][2] = __fmul_rn(tn, te);
+          wgt[k][3] = __fmul_rn(tn, tw);
+          // the nearest pixel is one of the 4 bilinear taps
+          near_tap[k] = ((ny != y0f) ? 2 : 0) + ((nx != x0f) ? 1 : 0);
+          if (rgbd2 != nullptr) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
+              const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
+              tap[k][t] = make_float4(0.f, 0.f, 0.f, 0.f);  // zeros padding
+              if (inb) tap[k][t] = __ldg(rgbd2 + (int64_t)ys * p.W + xs);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
+              const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
+              tap[k][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (inb) {
+                const int64_t o = (int64_t)ys * p.W + xs;
+                tap[k][t] = make_float4(__ldg(J.rgb2 + o * 3), __ldg(J.rgb2 + o * 3 + 1),
+                                        __ldg(J.rgb2 + o * 3 + 2), __ldg(J.depth2 + o));
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!lerp) {
+        cr[k] = c1[3 * k];
+        cg[k] = c1[3 * k + 1];
+        cb[k] = c1[3 * k + 2];
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          cr[k] = __fadd_rn(cr[k], __fmul_rn(tap[k][t].x, wgt[k][t]));
+          cg[k] = __fadd_rn(cg[k], __fmul_rn(tap[k][t].y, wgt[k][t]));
+          cb[k] = __fadd_rn(cb[k], __fmul_rn(tap[k][t].z, wgt[k][t]));
+          if (t == near_tap[k]) dep2[k] = tap[k][t].w;
+        }
+        // pcl_2 = o_2 + (R_2 @ (K_2^-1 @ [u2, v2, 1])) * depth_2
+        const float u2 = u2a[k], v2 = v2a[k];
+        const float kx = J.K2inv[0] * u2 + J.K2inv[1] * v2 + J.K2inv[2];
+        const float ky = J.K2inv[3] * u2 + J.K2inv[4] * v2 + J.K2inv[5];
+        const float kz = J.K2inv[6] * u2 + J.K2inv[7] * v2 + J.K2inv[8];
+        const float qx = J.o2[0] + (J.R2[0] * kx + J.R2[1] * ky + J.R2[2] * kz) * dep2[k];
+        const float qy = J.o2[1] + (J.R2[3] * kx + J.R2[4] * ky + J.R2[5] * kz) * dep2[k];
+        const float qz = J.o2[2] + (J.R2[6] * kx + J.R2[7] * ky + J.R2[8] * kz) * dep2[k];
+        wx[k] = J.w1 * wx[k] + J.w2 * qx;
+        wy[k] = J.w1 * wy[k] + J.w2 * qy;
+        wz[k] = J.w1 * wz[k] + J.w2 * qz;
+      }
+      const float3 ndc = world_to_ndc(cam, wx[k], wy[k], wz[k]);
+      ox[k] = ndc.x;
+      oy[k] = ndc.y;
+      oz[k] = ndc.z;
+    }
+  }
+
+  // ------------------------------------------------------------ order between tiles
+  if (warp == 0) {
     long long prefix = 0;
-    if (tile == 0) {
-      if (lane == 0) atomicExch(p.state + tile, kUFlagPrefix | (unsigned int)aggregate);
-    } else {
-      if (lane == 0) atomicExch(p.state + tile, kUFlagAgg | (unsigned int)aggregate);
+    if (tile != 0) {
       int look = tile - 1;
       while (true) {
         const int idx = look - lane;
-        unsigned long long st = kUFlagPrefix;
+        unsigned long long st = kUFlagPrefix;  // lanes past the start act as a zero prefix
         if (idx >= 0) {
           do {
             st = *reinterpret_cast<volatile unsigned long long*>(p.state + idx);
@@ -171,112 +282,36 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp(const __grid_constant__ Uwp
     }
   }
   __syncthreads();
-  if (valid == 0) return;
+  if (!any_valid) return;
   int64_t out = s_prefix + s_warp[warp] + (inc - cnt);
 
-  // ------------------------------------------------------------ geometry for survivors
-  float d1[4], c1[12];
-  load4(J.depth1, pix0, vec, HW, d1);
-  const PgdvsCamera cam = p.cams[J.view];
-  const bool lerp = (J.same_time == 0);
-  if (!lerp) {
-    load4(J.rgb1, pix0 * 3, vec, HW * 3, c1);
-    load4(J.rgb1, pix0 * 3 + 4, vec, HW * 3, c1 + 4);
-    load4(J.rgb1, pix0 * 3 + 8, vec, HW * 3, c1 + 8);
-  }
-  const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
-  int uu = u0, vv = v0;
+  // ------------------------------------------------------------ stores, in packed order
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float u = (float)uu, v = (float)vv;
-    const int64_t pix = pix0 + k;
-    if (++uu == p.W) { uu = 0; ++vv; }
-    if (!(valid & (1u << k))) continue;
-    // rays_d = (c2w[:3,:3] @ K^-1) @ [u, v, 1]
-    float wx = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
-    float wy = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
-    float wz = J.o1[2] + (J.M1[6] * u + J.M1[7] * v + J.M1[8]) * d1[k];
-    float cr, cg, cb;
-    if (!lerp) {
-      cr = c1[3 * k]; cg = c1[3 * k + 1]; cb = c1[3 * k + 2];
-    } else {
-      const float u2 = __fadd_rn(u, fl[2 * k]), v2 = __fadd_rn(v, fl[2 * k + 1]);
-      const float ix = grid_unnormalize(u2, (float)p.W);
-      const float iy = grid_unnormalize(v2, (float)p.H);
-      // depth_2: grid_sample(mode="nearest"): nearbyint (half to even), zeros padding
-      const float nx = nearbyintf(ix), ny = nearbyintf(iy);
-      // rgb: grid_sample(rgb_2, mode="bilinear"), zeros padding  (colour comes from frame 2)
-      const float x0f = floorf(ix), y0f = floorf(iy);
-      const float tw = __fsub_rn(ix, x0f), te = __fsub_rn(1.0f, tw);
-      const float tn = __fsub_rn(iy, y0f), ts = __fsub_rn(1.0f, tn);
-      const int x0 = (int)x0f, y0 = (int)y0f;
-      const float wgt[4] = {__fmul_rn(ts, te), __fmul_rn(ts, tw), __fmul_rn(tn, te), __fmul_rn(tn, tw)};
-      float dep2 = 0.0f;
-      cr = cg = cb = 0.0f;
-      if (rgbd2 != nullptr) {
-        // the nearest pixel is one of the 4 bilinear taps: tap (ny==y0 ? 0 : 1, nx==x0 ? 0 : 1)
-        const int near_tap = ((ny != y0f) ? 2 : 0) + ((nx != x0f) ? 1 : 0);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
-          if (xs >= 0 && xs < p.W && ys >= 0 && ys < p.H) {
-            const float4 q = __ldg(rgbd2 + (int64_t)ys * p.W + xs);
-            cr = __fadd_rn(cr, __fmul_rn(q.x, wgt[t]));
-            cg = __fadd_rn(cg, __fmul_rn(q.y, wgt[t]));
-            cb = __fadd_rn(cb, __fmul_rn(q.z, wgt[t]));
-            if (t == near_tap) dep2 = q.w;
-          }
-        }
-      } else {
-        if (nx >= 0.0f && nx <= (float)(p.W - 1) && ny >= 0.0f && ny <= (float)(p.H - 1))
-          dep2 = __ldg(J.depth2 + (int64_t)ny * p.W + (int64_t)nx);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
-          if (xs >= 0 && xs < p.W && ys >= 0 && ys < p.H) {
-            const float* q = J.rgb2 + ((int64_t)ys * p.W + xs) * 3;
-            cr = __fadd_rn(cr, __fmul_rn(__ldg(q + 0), wgt[t]));
-            cg = __fadd_rn(cg, __fmul_rn(__ldg(q + 1), wgt[t]));
-            cb = __fadd_rn(cb, __fmul_rn(__ldg(q + 2), wgt[t]));
-          }
-        }
-      }
-      // pcl_2 = o_2 + (R_2 @ (K_2^-1 @ [u2, v2, 1])) * depth_2
-      const float kx = J.K2inv[0] * u2 + J.K2inv[1] * v2 + J.K2inv[2];
-      const float ky = J.K2inv[3] * u2 + J.K2inv[4] * v2 + J.K2inv[5];
-      const float kz = J.K2inv[6] * u2 + J.K2inv[7] * v2 + J.K2inv[8];
-      const float qx = J.o2[0] + (J.R2[0] * kx + J.R2[1] * ky + J.R2[2] * kz) * dep2;
-      const float qy = J.o2[1] + (J.R2[3] * kx + J.R2[4] * ky + J.R2[5] * kz) * dep2;
-      const float qz = J.o2[2] + (J.R2[6] * kx + J.R2[7] * ky + J.R2[8] * kz) * dep2;
-      wx = J.w1 * wx + J.w2 * qx;
-      wy = J.w1 * wy + J.w2 * qy;
-      wz = J.w1 * wz + J.w2 * qz;
-    }
-    const float3 ndc = world_to_ndc(cam, wx, wy, wz);
+    if (!((valid >> k) & 1u)) continue;
     if (FUSED) {
-      const int cell = point_cell(p.g, J.view, ndc.x, ndc.y, ndc.z);
-      int rank = 0;
-      if (cell >= 0) rank = atomicAdd(p.cell_count + cell, 1);
-      p.rank[out] = make_int2(cell, rank);
-      p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
-      p.preB[out] = make_float4(cr, cg, cb, 0.0f);
+      const int cell = point_cell(p.g, J.view, ox[k], oy[k], oz[k]);
+      if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
+      p.cell_of[out] = cell;
+      p.preA[out] = make_float4(ox[k], oy[k], oz[k], __int_as_float((int)out));
+      p.preB[out] = make_float4(cr[k], cg[k], cb[k], 0.0f);
     }
     if (p.xyz_ndc) {
-      p.xyz_ndc[out * 3 + 0] = ndc.x;
-      p.xyz_ndc[out * 3 + 1] = ndc.y;
-      p.xyz_ndc[out * 3 + 2] = ndc.z;
+      p.xyz_ndc[out * 3 + 0] = ox[k];
+      p.xyz_ndc[out * 3 + 1] = oy[k];
+      p.xyz_ndc[out * 3 + 2] = oz[k];
     }
     if (p.rgb) {
-      p.rgb[out * 3 + 0] = cr;
-      p.rgb[out * 3 + 1] = cg;
-      p.rgb[out * 3 + 2] = cb;
+      p.rgb[out * 3 + 0] = cr[k];
+      p.rgb[out * 3 + 1] = cg[k];
+      p.rgb[out * 3 + 2] = cb[k];
     }
     if (p.xyz_world) {
-      p.xyz_world[out * 3 + 0] = wx;
-      p.xyz_world[out * 3 + 1] = wy;
-      p.xyz_world[out * 3 + 2] = wz;
+      p.xyz_world[out * 3 + 0] = wx[k];
+      p.xyz_world[out * 3 + 1] = wy[k];
+      p.xyz_world[out * 3 + 2] = wz[k];
     }
-    if (p.src_pix) p.src_pix[out] = (int32_t)pix;
+    if (p.src_pix) p.src_pix[out] = (int32_t)(pix0 + k);
     ++out;
   }
 }
@@ -334,7 +369,7 @@ static inline UwpLayout make_uwp_layout(int n_jobs, int H, int W) {
 static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras, int n_views, int H,
                    int W, float* xyz_ndc, float* rgb, float* xyz_world, int32_t* src_pix,
                    int64_t* first_idx, int64_t* num_points, int64_t* total_points, char* ws,
-                   const UwpLayout& L, const CellGrid* grid, int* cell_count, int2* rank, float4* preA,
+                   const UwpLayout& L, const CellGrid* grid, int* cell_count, int* cell_of, float4* preA,
                    float4* preB, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(ws, 0, L.total, stream);
   if (e != cudaSuccess) return (int)e;
@@ -357,7 +392,7 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
     if (grid != nullptr) {
       p.g = *grid;
       p.cell_count = cell_count;
-      p.rank = rank;
+      p.cell_of = cell_of;
       p.preA = preA;
       p.preB = preB;
       k_uwp<true><<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
@@ -433,12 +468,12 @@ extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCam
   if (n_views == 0) return PGDVS_OK;
   char* ws = static_cast<char*>(workspace);
   // cell counters, scan state and ticket sit contiguously at the front of the bin layout
-  cudaError_t e = cudaMemsetAsync(ws + B.off_start, 0, B.off_rank - B.off_start, stream);
+  cudaError_t e = cudaMemsetAsync(ws, 0, B.off_zero_end, stream);
   if (e != cudaSuccess) return (int)e;
   const CellGrid g = make_cell_grid(H, W, B.halo);
   int rc = run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, nullptr, nullptr, first_idx,
                    num_points, total_points, ws + T.total, U, &g,
-                   reinterpret_cast<int*>(ws + B.off_start), reinterpret_cast<int2*>(ws + B.off_rank),
+                   reinterpret_cast<int*>(ws + B.off_cells), reinterpret_cast<int*>(ws + B.off_cell_of),
                    reinterpret_cast<float4*>(ws + T.off_preA), reinterpret_cast<float4*>(ws + T.off_preB),
                    stream);
   if (rc) return rc;
