@@ -188,6 +188,13 @@ __global__ void __launch_bounds__(1024) k_scan(int* data, unsigned long long* st
   base[threadIdx.x] = o;
 }
 
+// In-place exclusive scan of n_tiles * kScanTile ints (state / ticket must be zeroed).
+int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state, int* ticket,
+                           cudaStream_t stream) {
+  k_scan<<<(unsigned)n_tiles, 1024, 0, stream>>>(data, state, ticket);
+  return check_launch();
+}
+
 // Second half of the fused path (called by pgdvs_uwp_bin in uwp.cu): scan the cell counters
 // the uwp kernel accumulated, then scatter its packed-order records into cell order.
 int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,

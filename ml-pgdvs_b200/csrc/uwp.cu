@@ -1,34 +1,37 @@
-// Fused unproject -> flow-warp -> time-lerp -> project kernel.
+// Fused unproject -> flow-warp -> time-lerp -> project stage.
 //
-// One launch turns a batch of (target view, source-frame pair) jobs into a packed NDC point
-// cloud ready for the rasterizer.  It replaces ~25 separate torch kernels and six
-// boolean-index compactions (each a host sync) of the reference:
+// Turns a batch of (target view, source-frame pair) jobs into a packed NDC point cloud ready
+// for the rasterizer.  It replaces ~25 separate torch kernels and six boolean-index
+// compactions (each a host sync) of the reference:
 //   get_batched_rays                 pgdvs_renderer_base.py:17-57
 //   compute_dyn_pcl (geometry part)  pgdvs_renderer_dyn.py:304-388
 //   w2c / camera / transform         pgdvs_renderer_dyn.py:676-687 + PointsRasterizer.transform
 //
-// Each thread owns 4 consecutive source pixels (float4-vectorised, fully coalesced reads of
-// depth / mask / occlusion / flow / rgb).  Frame-2 colour (bilinear) and depth (nearest) are
-// gathered from a packed (r,g,b,depth) float4 plane when the caller provides one: the nearest
-// pixel is always one of the four bilinear taps, so 4 x 128-bit loads replace 13 scalar ones.
-// Surviving points are written in the reference's order (job-major, row-major pixels): a
-// block-level prefix sum orders points inside a 1024-pixel tile and a single-pass chained
-// scan (decoupled look-back, ticketed tiles) orders the tiles, so the packed indices — and
-// therefore the rasterizer's idx output — are identical to the reference's boolean-mask
-// compaction.  In the fused mode (pgdvs_uwp_bin) the kernel also files every point under its
-// raster cell (one atomicAdd), which removes the separate counting pass over the cloud.
+// Survivors must come out in the reference's order (job-major, row-major source pixels) so
+// that packed indices — and therefore the rasterizer's idx output — equal the reference's
+// boolean-mask compaction.  That ordered compaction is done without any spin-waiting:
+//   k_uwp_count : per 1024-pixel tile, how many pixels survive (mask / occlusion / in-bounds /
+//                 keep tests; float4-vectorised coalesced loads, warp-shuffle reduction)
+//   k_scan      : exclusive scan of the tile counts (bin.cu)
+//   k_uwp       : each thread owns 4 consecutive pixels; a warp-shuffle + shared-memory prefix
+//                 sum orders survivors inside the tile, the scanned tile offset orders tiles.
+// Frame-2 colour (bilinear) and depth (nearest) are gathered from a packed (r,g,b,depth)
+// float4 plane when the caller provides one: the nearest pixel is always one of the four
+// bilinear taps, so 4 x 128-bit loads replace 13 scalar ones.  In the fused mode
+// (pgdvs_uwp_bin) the kernel also files every point under its raster cell (one RED atomic),
+// which removes the separate counting pass over the cloud.
 #include "common.cuh"
 
 namespace pgdvs {
 
 int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,
                         const int64_t* total_dev, cudaStream_t stream);
+int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state, int* ticket,
+                           cudaStream_t stream);
 
 constexpr int kUwpThreads = 256;
 constexpr int kUwpPix = 4;                               // pixels per thread
 constexpr int kUwpTile = kUwpThreads * kUwpPix;          // pixels per tile
-constexpr unsigned long long kUFlagAgg = 1ull << 32;
-constexpr unsigned long long kUFlagPrefix = 2ull << 32;
 
 struct UwpParams {
   const PgdvsUwpJob* jobs;
@@ -36,13 +39,11 @@ struct UwpParams {
   int n_jobs, H, W;
   int tiles_per_job;
   int64_t n_tiles;
+  int* tile_off;     // [n_tiles + 1]: counts, then exclusive offsets; [n_tiles] = total
   float* xyz_ndc;    // [cap,3] or null
   float* rgb;        // [cap,3] or null
   float* xyz_world;  // [cap,3] or null
   int32_t* src_pix;  // [cap] or null
-  unsigned long long* state;  // [n_tiles]
-  int* ticket;
-  int64_t* job_start;         // [n_jobs + 1]
   // fused binning (all null/0 in the plain mode)
   CellGrid g;
   int* cell_count;
@@ -70,32 +71,17 @@ __device__ __forceinline__ void load4(const float* p, int64_t i, bool vec, int64
   }
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(kUwpThreads, 2) k_uwp(const __grid_constant__ UwpParams p) {
-  __shared__ int s_tile;
-  __shared__ int s_warp[kUwpThreads / 32];
-  __shared__ long long s_prefix;
-  if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1);
-  __syncthreads();
-  const int tile = s_tile;
-  const int job_i = tile / p.tiles_per_job;
-  const int jt = tile - job_i * p.tiles_per_job;
-  const PgdvsUwpJob& J = p.jobs[job_i];
+// Which of this thread's 4 pixels survive (pgdvs_renderer_dyn.py:304-316, 438-440); also
+// returns the flow of the 4 pixels, which the geometry needs again.
+__device__ __forceinline__ unsigned pixel_validity(const UwpParams& p, const PgdvsUwpJob& J, int64_t pix0,
+                                                   int u0, int v0, bool in_range, bool vec, float fl[8]) {
   const int64_t HW = (int64_t)p.H * p.W;
-  const int64_t pix0 = (int64_t)jt * kUwpTile + (int64_t)threadIdx.x * kUwpPix;
-  const bool in_range = pix0 < HW;
-  const bool vec = ((HW & 3) == 0) && in_range;  // host guarantees 16-byte aligned planes
-  // (u, v) of the first pixel; the other three follow by incrementing (one div per thread)
-  const int v0 = (int)(pix0 / p.W), u0 = (int)(pix0 - (int64_t)v0 * p.W);
-
-  // ------------------------------------------------------------ validity (cheap loads only)
-  float m[4] = {0, 0, 0, 0}, fl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned valid = 0;
   if (in_range) {
+    float m[4], oc[4] = {0, 0, 0, 0};
     load4(J.mask1, pix0, vec, HW, m);
     load4(J.flow12, pix0 * 2, vec, HW * 2, fl);
     load4(J.flow12, pix0 * 2 + 4, vec, HW * 2, fl + 4);
-    float oc[4] = {0, 0, 0, 0};
     if (J.occ12 != nullptr) load4(J.occ12, pix0, vec, HW, oc);
     int uu = u0, vv = v0;
 #pragma unroll
@@ -112,6 +98,51 @@ __global__ void __launch_bounds__(kUwpThreads, 2) k_uwp(const __grid_constant__ 
       if (++uu == p.W) { uu = 0; ++vv; }
     }
   }
+  return valid;
+}
+
+__global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant__ UwpParams p) {
+  __shared__ int s_warp[kUwpThreads / 32];
+  const int tile = blockIdx.x;
+  const int job_i = tile / p.tiles_per_job;
+  const int jt = tile - job_i * p.tiles_per_job;
+  const PgdvsUwpJob& J = p.jobs[job_i];
+  const int64_t HW = (int64_t)p.H * p.W;
+  const int64_t pix0 = (int64_t)jt * kUwpTile + (int64_t)threadIdx.x * kUwpPix;
+  const bool in_range = pix0 < HW;
+  const bool vec = ((HW & 3) == 0) && in_range;
+  const int v0 = (int)(pix0 / p.W), u0 = (int)(pix0 - (int64_t)v0 * p.W);
+  float fl[8];
+  int cnt = __popc(pixel_validity(p, J, pix0, u0, v0, in_range, vec, fl));
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kUwpThreads / 32; ++w) t += s_warp[w];
+    p.tile_off[tile] = t;
+  }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ UwpParams p) {
+  __shared__ int s_warp[kUwpThreads / 32];
+  const int tile = blockIdx.x;
+  const int job_i = tile / p.tiles_per_job;
+  const int jt = tile - job_i * p.tiles_per_job;
+  const PgdvsUwpJob& J = p.jobs[job_i];
+  const int64_t HW = (int64_t)p.H * p.W;
+  const int64_t pix0 = (int64_t)jt * kUwpTile + (int64_t)threadIdx.x * kUwpPix;
+  const bool in_range = pix0 < HW;
+  const bool vec = ((HW & 3) == 0) && in_range;  // host guarantees 16-byte aligned planes
+  // (u, v) of the first pixel; the other three follow by incrementing (one div per thread)
+  const int v0 = (int)(pix0 / p.W), u0 = (int)(pix0 - (int64_t)v0 * p.W);
+  const int tile_base = __ldg(p.tile_off + tile);
+
+  float fl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const unsigned valid = pixel_validity(p, J, pix0, u0, v0, in_range, vec, fl);
   const int cnt = __popc(valid);
 
   // ------------------------------------------------------------ order inside the tile
@@ -124,204 +155,145 @@ __global__ void __launch_bounds__(kUwpThreads, 2) k_uwp(const __grid_constant__ 
   }
   if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  int aggregate = 0;
-  if (warp == 0) {
-    const int w = (lane < kUwpThreads / 32) ? s_warp[lane] : 0;
-    int winc = w;
+  int warp_off = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, winc, d);
-      if (lane >= d) winc += o;
-    }
-    if (lane < kUwpThreads / 32) s_warp[lane] = winc - w;  // read after the next barrier
-    aggregate = __shfl_sync(0xffffffffu, winc, 31);
-    // publish this tile's count NOW, so that successors never wait on our geometry
-    if (lane == 0)
-      atomicExch(p.state + tile, (tile == 0 ? kUFlagPrefix : kUFlagAgg) | (unsigned int)aggregate);
-  }
+  for (int w = 0; w < kUwpThreads / 32; ++w)
+    if (w < warp) warp_off += s_warp[w];
+  if (valid == 0) return;
+  int64_t out = (int64_t)tile_base + warp_off + (inc - cnt);
 
-  // ------------------------------------------------------------ geometry (branch-free over the
-  // 4 pixels so that all 16 frame-2 taps are in flight together; stores are predicated later)
+  // ------------------------------------------------------------ geometry for survivors
   float d1[4], c1[12];
-  float ox[4], oy[4], oz[4], cr[4], cg[4], cb[4], wx[4], wy[4], wz[4];
-  const bool any_valid = valid != 0;
+  load4(J.depth1, pix0, vec, HW, d1);
   const PgdvsCamera cam = p.cams[J.view];
   const bool lerp = (J.same_time == 0);
-  if (any_valid) {
-    load4(J.depth1, pix0, vec, HW, d1);
-    if (!lerp) {
-      load4(J.rgb1, pix0 * 3, vec, HW * 3, c1);
-      load4(J.rgb1, pix0 * 3 + 4, vec, HW * 3, c1 + 4);
-      load4(J.rgb1, pix0 * 3 + 8, vec, HW * 3, c1 + 8);
-    }
-    const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
-    float u2a[4], v2a[4], wgt[4][4], dep2[4];
-    float4 tap[4][4];
-    int near_tap[4];
-    {
-      int uu = u0, vv = v0;
+  if (!lerp) {
+    load4(J.rgb1, pix0 * 3, vec, HW * 3, c1);
+    load4(J.rgb1, pix0 * 3 + 4, vec, HW * 3, c1 + 4);
+    load4(J.rgb1, pix0 * 3 + 8, vec, HW * 3, c1 + 8);
+  }
+  const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
+  int uu = u0, vv = v0;
+  // two pixels at a time: their 8 frame-2 taps are issued back to back before any is consumed
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float u = (float)uu, v = (float)vv;
-        if (++uu == p.W) { uu = 0; ++vv; }
-        // rays_d = (c2w[:3,:3] @ K^-1) @ [u, v, 1]
-        wx[k] = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
-        wy[k] = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
-        wz[k] = J.o1[2] + (J.M1[6] * u + J.M1[7] * v + J.M1[8]) * d1[k];
-        cr[k] = cg[k] = cb[k] = 0.0f;
-        dep2[k] = 0.0f;
-        if (lerp) {
-          const bool ok = (valid >> k) & 1u;
-          const float u2 = __fadd_rn(u, fl[2 * k]), v2 = __fadd_rn(v, fl[2 * k + 1]);
-          u2a[k] = u2;
-          v2a[k] = v2;
-          const float ix = grid_unnormalize(u2, (float)p.W);
-          const float iy = grid_unnormalize(v2, (float)p.H);
-          // depth_2: grid_sample(mode="nearest"): nearbyint (half to even), zeros padding
-          const float nx = nearbyintf(ix), ny = nearbyintf(iy);
-          // rgb: grid_sample(rgb_2, mode="bilinear"), zeros padding (colour comes from frame 2)
-          const float x0f = floorf(ix), y0f = floorf(iy);
-          const float tw = __fsub_rn(ix, x0f), te = __fsub_rn(1.0f, tw);
-          const float tn = __fsub_rn(iy, y0f), ts = __fsub_rn(1.0f, tn);
-          const int x0 = (int)x0f, y0 = (int)y0f;
-          wgt[k][0] = __fmul_rn(ts, te);
-          wgt[k][1] = __fmul_rn(ts, tw);
-          wgt[k][2] = __fmul_rn(tn, te);
-          wgt[k][3] = __fmul_rn(tn, tw);
-          // the nearest pixel is one of the 4 bilinear taps
-          near_tap[k] = ((ny != y0f) ? 2 : 0) + ((nx != x0f) ? 1 : 0);
-          if (rgbd2 != nullptr) {
+  for (int k0 = 0; k0 < 4; k0 += 2) {
+    float uf[2], vf[2], u2a[2], v2a[2], wgt[2][4];
+    float4 tap[2][4];
+    int near_tap[2];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
-              const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
-              tap[k][t] = make_float4(0.f, 0.f, 0.f, 0.f);  // zeros padding
-              if (inb) tap[k][t] = __ldg(rgbd2 + (int64_t)ys * p.W + xs);
-            }
-          } else {
+    for (int kk = 0; kk < 2; ++kk) {
+      const int k = k0 + kk;
+      uf[kk] = (float)uu;
+      vf[kk] = (float)vv;
+      if (++uu == p.W) { uu = 0; ++vv; }
+      near_tap[kk] = 0;
+      if (lerp) {
+        const bool ok = (valid >> k) & 1u;
+        const float u2 = __fadd_rn(uf[kk], fl[2 * k]), v2 = __fadd_rn(vf[kk], fl[2 * k + 1]);
+        u2a[kk] = u2;
+        v2a[kk] = v2;
+        const float ix = grid_unnormalize(u2, (float)p.W);
+        const float iy = grid_unnormalize(v2, (float)p.H);
+        // depth_2: grid_sample(mode="nearest"): nearbyint (half to even), zeros padding
+        const float nx = nearbyintf(ix), ny = nearbyintf(iy);
+        // rgb: grid_sample(rgb_2, mode="bilinear"), zeros padding (colour comes from frame 2)
+        const float x0f = floorf(ix), y0f = floorf(iy);
+        const float tw = __fsub_rn(ix, x0f), te = __fsub_rn(1.0f, tw);
+        const float tn = __fsub_rn(iy, y0f), ts = __fsub_rn(1.0f, tn);
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        wgt[kk][0] = __fmul_rn(ts, te);
+        wgt[kk][1] = __fmul_rn(ts, tw);
+        wgt[kk][2] = __fmul_rn(tn, te);
+        wgt[kk][3] = __fmul_rn(tn, tw);
+        // the nearest pixel is one of the 4 bilinear taps
+        near_tap[kk] = ((ny != y0f) ? 2 : 0) + ((nx != x0f) ? 1 : 0);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
-              const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
-              tap[k][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (inb) {
-                const int64_t o = (int64_t)ys * p.W + xs;
-                tap[k][t] = make_float4(__ldg(J.rgb2 + o * 3), __ldg(J.rgb2 + o * 3 + 1),
-                                        __ldg(J.rgb2 + o * 3 + 2), __ldg(J.depth2 + o));
-              }
-            }
+        for (int t = 0; t < 4; ++t) {
+          const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
+          const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
+          tap[kk][t] = make_float4(0.f, 0.f, 0.f, 0.f);  // zeros padding
+          if (inb) {
+            const int64_t o = (int64_t)ys * p.W + xs;
+            if (rgbd2 != nullptr)
+              tap[kk][t] = __ldg(rgbd2 + o);
+            else
+              tap[kk][t] = make_float4(__ldg(J.rgb2 + o * 3), __ldg(J.rgb2 + o * 3 + 1),
+                                       __ldg(J.rgb2 + o * 3 + 2), __ldg(J.depth2 + o));
           }
         }
       }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int kk = 0; kk < 2; ++kk) {
+      const int k = k0 + kk;
+      if (!((valid >> k) & 1u)) continue;
+      const float u = uf[kk], v = vf[kk];
+      // rays_d = (c2w[:3,:3] @ K^-1) @ [u, v, 1]
+      float wx = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
+      float wy = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
+      float wz = J.o1[2] + (J.M1[6] * u + J.M1[7] * v + J.M1[8]) * d1[k];
+      float cr, cg, cb;
       if (!lerp) {
-        cr[k] = c1[3 * k];
-        cg[k] = c1[3 * k + 1];
-        cb[k] = c1[3 * k + 2];
+        cr = c1[3 * k];
+        cg = c1[3 * k + 1];
+        cb = c1[3 * k + 2];
       } else {
+        cr = cg = cb = 0.0f;
+        float dep2 = 0.0f;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          cr[k] = __fadd_rn(cr[k], __fmul_rn(tap[k][t].x, wgt[k][t]));
-          cg[k] = __fadd_rn(cg[k], __fmul_rn(tap[k][t].y, wgt[k][t]));
-          cb[k] = __fadd_rn(cb[k], __fmul_rn(tap[k][t].z, wgt[k][t]));
-          if (t == near_tap[k]) dep2[k] = tap[k][t].w;
+          cr = __fadd_rn(cr, __fmul_rn(tap[kk][t].x, wgt[kk][t]));
+          cg = __fadd_rn(cg, __fmul_rn(tap[kk][t].y, wgt[kk][t]));
+          cb = __fadd_rn(cb, __fmul_rn(tap[kk][t].z, wgt[kk][t]));
+          if (t == near_tap[kk]) dep2 = tap[kk][t].w;
         }
         // pcl_2 = o_2 + (R_2 @ (K_2^-1 @ [u2, v2, 1])) * depth_2
-        const float u2 = u2a[k], v2 = v2a[k];
+        const float u2 = u2a[kk], v2 = v2a[kk];
         const float kx = J.K2inv[0] * u2 + J.K2inv[1] * v2 + J.K2inv[2];
         const float ky = J.K2inv[3] * u2 + J.K2inv[4] * v2 + J.K2inv[5];
         const float kz = J.K2inv[6] * u2 + J.K2inv[7] * v2 + J.K2inv[8];
-        const float qx = J.o2[0] + (J.R2[0] * kx + J.R2[1] * ky + J.R2[2] * kz) * dep2[k];
-        const float qy = J.o2[1] + (J.R2[3] * kx + J.R2[4] * ky + J.R2[5] * kz) * dep2[k];
-        const float qz = J.o2[2] + (J.R2[6] * kx + J.R2[7] * ky + J.R2[8] * kz) * dep2[k];
-        wx[k] = J.w1 * wx[k] + J.w2 * qx;
-        wy[k] = J.w1 * wy[k] + J.w2 * qy;
-        wz[k] = J.w1 * wz[k] + J.w2 * qz;
+        const float qx = J.o2[0] + (J.R2[0] * kx + J.R2[1] * ky + J.R2[2] * kz) * dep2;
+        const float qy = J.o2[1] + (J.R2[3] * kx + J.R2[4] * ky + J.R2[5] * kz) * dep2;
+        const float qz = J.o2[2] + (J.R2[6] * kx + J.R2[7] * ky + J.R2[8] * kz) * dep2;
+        wx = J.w1 * wx + J.w2 * qx;
+        wy = J.w1 * wy + J.w2 * qy;
+        wz = J.w1 * wz + J.w2 * qz;
       }
-      const float3 ndc = world_to_ndc(cam, wx[k], wy[k], wz[k]);
-      ox[k] = ndc.x;
-      oy[k] = ndc.y;
-      oz[k] = ndc.z;
-    }
-  }
-
-  // ------------------------------------------------------------ order between tiles
-  if (warp == 0) {
-    long long prefix = 0;
-    if (tile != 0) {
-      int look = tile - 1;
-      while (true) {
-        const int idx = look - lane;
-        unsigned long long st = kUFlagPrefix;  // lanes past the start act as a zero prefix
-        if (idx >= 0) {
-          do {
-            st = *reinterpret_cast<volatile unsigned long long*>(p.state + idx);
-          } while ((st >> 32) == 0);
-        }
-        const unsigned has_prefix = __ballot_sync(0xffffffffu, (st >> 32) == 2);
-        int val = (int)(unsigned int)(st & 0xffffffffull);
-        if (has_prefix) {
-          const int firstp = __ffs(has_prefix) - 1;
-          if (lane > firstp) val = 0;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-        prefix += val;
-        if (has_prefix) break;
-        look -= 32;
+      const float3 ndc = world_to_ndc(cam, wx, wy, wz);
+      if (FUSED) {
+        const int cell = point_cell(p.g, J.view, ndc.x, ndc.y, ndc.z);
+        if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
+        p.cell_of[out] = cell;
+        p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
+        p.preB[out] = make_float4(cr, cg, cb, 0.0f);
       }
-      if (lane == 0)
-        atomicExch(p.state + tile, kUFlagPrefix | (unsigned int)(prefix + aggregate));
+      if (p.xyz_ndc) {
+        p.xyz_ndc[out * 3 + 0] = ndc.x;
+        p.xyz_ndc[out * 3 + 1] = ndc.y;
+        p.xyz_ndc[out * 3 + 2] = ndc.z;
+      }
+      if (p.rgb) {
+        p.rgb[out * 3 + 0] = cr;
+        p.rgb[out * 3 + 1] = cg;
+        p.rgb[out * 3 + 2] = cb;
+      }
+      if (p.xyz_world) {
+        p.xyz_world[out * 3 + 0] = wx;
+        p.xyz_world[out * 3 + 1] = wy;
+        p.xyz_world[out * 3 + 2] = wz;
+      }
+      if (p.src_pix) p.src_pix[out] = (int32_t)(pix0 + k);
+      ++out;
     }
-    if (lane == 0) {
-      s_prefix = prefix;
-      if (jt == 0) p.job_start[job_i] = prefix;
-      if ((int64_t)tile == p.n_tiles - 1) p.job_start[p.n_jobs] = prefix + aggregate;
-    }
-  }
-  __syncthreads();
-  if (!any_valid) return;
-  int64_t out = s_prefix + s_warp[warp] + (inc - cnt);
-
-  // ------------------------------------------------------------ stores, in packed order
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (!((valid >> k) & 1u)) continue;
-    if (FUSED) {
-      const int cell = point_cell(p.g, J.view, ox[k], oy[k], oz[k]);
-      if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
-      p.cell_of[out] = cell;
-      p.preA[out] = make_float4(ox[k], oy[k], oz[k], __int_as_float((int)out));
-      p.preB[out] = make_float4(cr[k], cg[k], cb[k], 0.0f);
-    }
-    if (p.xyz_ndc) {
-      p.xyz_ndc[out * 3 + 0] = ox[k];
-      p.xyz_ndc[out * 3 + 1] = oy[k];
-      p.xyz_ndc[out * 3 + 2] = oz[k];
-    }
-    if (p.rgb) {
-      p.rgb[out * 3 + 0] = cr[k];
-      p.rgb[out * 3 + 1] = cg[k];
-      p.rgb[out * 3 + 2] = cb[k];
-    }
-    if (p.xyz_world) {
-      p.xyz_world[out * 3 + 0] = wx[k];
-      p.xyz_world[out * 3 + 1] = wy[k];
-      p.xyz_world[out * 3 + 2] = wz[k];
-    }
-    if (p.src_pix) p.src_pix[out] = (int32_t)(pix0 + k);
-    ++out;
   }
 }
 
-// per-view first index / count from the per-job starts (jobs are sorted by view)
-__global__ void k_uwp_finalize(const PgdvsUwpJob* jobs, int n_jobs, int n_views,
-                               const int64_t* job_start, int64_t* first_idx, int64_t* num_points,
+// per-view first index / count / total from the scanned tile offsets (jobs sorted by view)
+__global__ void k_uwp_finalize(const PgdvsUwpJob* jobs, int n_jobs, int n_views, const int* tile_off,
+                               int tiles_per_job, int64_t* first_idx, int64_t* num_points,
                                int64_t* total) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v == 0 && total) *total = job_start[n_jobs];
+  if (v == 0 && total) *total = tile_off[(int64_t)n_jobs * tiles_per_job];
   if (v >= n_views) return;
   int a = n_jobs, b = n_jobs;
   for (int j = n_jobs - 1; j >= 0; --j) {
@@ -329,8 +301,9 @@ __global__ void k_uwp_finalize(const PgdvsUwpJob* jobs, int n_jobs, int n_views,
     if (jv >= v) a = j;
     if (jv >= v + 1) b = j;
   }
-  if (first_idx) first_idx[v] = job_start[a];
-  if (num_points) num_points[v] = job_start[b] - job_start[a];
+  const int64_t sa = tile_off[(int64_t)a * tiles_per_job], sb = tile_off[(int64_t)b * tiles_per_job];
+  if (first_idx) first_idx[v] = sa;
+  if (num_points) num_points[v] = sb - sa;
 }
 
 // (r,g,b) [HW,3] + depth [HW] -> (r,g,b,depth) float4 [HW] for a batch of frames
@@ -346,8 +319,9 @@ __global__ void __launch_bounds__(256) k_pack_rgbd(const PgdvsFramePack* frames,
 
 struct UwpLayout {
   int tiles_per_job;
-  int64_t n_tiles;
-  size_t off_state, off_ticket, off_job_start, total;
+  int64_t n_tiles;       // pixel tiles
+  int64_t n_scan_tiles;  // k_scan tiles covering n_tiles + 1 ints
+  size_t off_tile_off, off_state, off_ticket, off_zero_end, total;
 };
 
 static inline UwpLayout make_uwp_layout(int n_jobs, int H, int W) {
@@ -355,13 +329,15 @@ static inline UwpLayout make_uwp_layout(int n_jobs, int H, int W) {
   const int64_t HW = (int64_t)H * W;
   L.tiles_per_job = (int)((HW + kUwpTile - 1) / kUwpTile);
   L.n_tiles = (int64_t)L.tiles_per_job * n_jobs;
+  L.n_scan_tiles = (L.n_tiles + 1 + kScanTile - 1) / kScanTile;
   size_t o = 0;
+  L.off_tile_off = o;
+  o = align256(o + sizeof(int) * (size_t)(L.n_scan_tiles * kScanTile));
   L.off_state = o;
-  o = align256(o + sizeof(unsigned long long) * (size_t)(L.n_tiles > 0 ? L.n_tiles : 1));
+  o = align256(o + sizeof(unsigned long long) * (size_t)L.n_scan_tiles);
   L.off_ticket = o;
   o = align256(o + 256);
-  L.off_job_start = o;
-  o = align256(o + sizeof(int64_t) * (size_t)(n_jobs + 1));
+  L.off_zero_end = o;
   L.total = o;
   return L;
 }
@@ -371,8 +347,9 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
                    int64_t* first_idx, int64_t* num_points, int64_t* total_points, char* ws,
                    const UwpLayout& L, const CellGrid* grid, int* cell_count, int* cell_of, float4* preA,
                    float4* preB, cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(ws, 0, L.total, stream);
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.off_zero_end, stream);
   if (e != cudaSuccess) return (int)e;
+  int* tile_off = reinterpret_cast<int*>(ws + L.off_tile_off);
   if (n_jobs > 0) {
     UwpParams p = {};
     p.jobs = jobs;
@@ -382,13 +359,17 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
     p.W = W;
     p.tiles_per_job = L.tiles_per_job;
     p.n_tiles = L.n_tiles;
+    p.tile_off = tile_off;
     p.xyz_ndc = xyz_ndc;
     p.rgb = rgb;
     p.xyz_world = xyz_world;
     p.src_pix = src_pix;
-    p.state = reinterpret_cast<unsigned long long*>(ws + L.off_state);
-    p.ticket = reinterpret_cast<int*>(ws + L.off_ticket);
-    p.job_start = reinterpret_cast<int64_t*>(ws + L.off_job_start);
+    k_uwp_count<<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
+    if (int rc = check_launch()) return rc;
+    if (int rc = scan_exclusive_inplace(tile_off, L.n_scan_tiles,
+                                        reinterpret_cast<unsigned long long*>(ws + L.off_state),
+                                        reinterpret_cast<int*>(ws + L.off_ticket), stream))
+      return rc;
     if (grid != nullptr) {
       p.g = *grid;
       p.cell_count = cell_count;
@@ -401,10 +382,10 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
     }
     if (int rc = check_launch()) return rc;
   }
-  // always run: also publishes total_points (0 when there are no jobs: job_start is zeroed)
-  k_uwp_finalize<<<(n_views + 128) / 128, 128, 0, stream>>>(
-      jobs, n_jobs, n_views, reinterpret_cast<const int64_t*>(ws + L.off_job_start), first_idx,
-      num_points, total_points);
+  // always run: also publishes total_points (0 when there are no jobs: tile_off is zeroed)
+  k_uwp_finalize<<<(n_views + 128) / 128, 128, 0, stream>>>(jobs, n_jobs, n_views, tile_off,
+                                                            L.tiles_per_job, first_idx, num_points,
+                                                            total_points);
   return check_launch();
 }
 
@@ -467,7 +448,7 @@ extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCam
   if (n_jobs > 0 && (!jobs || !cameras)) return PGDVS_E_BADARG;
   if (n_views == 0) return PGDVS_OK;
   char* ws = static_cast<char*>(workspace);
-  // cell counters, scan state and ticket sit contiguously at the front of the bin layout
+  // front pad, cell counters, scan state and ticket sit contiguously at the front
   cudaError_t e = cudaMemsetAsync(ws, 0, B.off_zero_end, stream);
   if (e != cudaSuccess) return (int)e;
   const CellGrid g = make_cell_grid(H, W, B.halo);

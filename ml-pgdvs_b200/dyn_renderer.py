@@ -222,7 +222,7 @@ def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=
             src_pix.data_ptr() if want_src_pix else None, first_idx.data_ptr(), num_points.data_ptr(),
             total.data_ptr(), ops._aligned_ptr(ws), nbytes.value, ops._stream_ptr(device)),
             "pgdvs_unproject_warp_project")
-    ops.LAUNCHES["count"] += 2  # k_uwp + k_uwp_finalize
+    ops.LAUNCHES["count"] += 4  # k_uwp_count, k_scan, k_uwp, k_uwp_finalize
     return {"xyz_ndc": xyz_ndc, "rgb": rgb, "xyz_world": xyz_world, "src_pix": src_pix,
             "first_idx": first_idx, "num_points": num_points, "total": total, "_keepalive": prep}
 
@@ -269,7 +269,7 @@ def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int
             xyz_ndc.data_ptr() if xyz_ndc is not None else None, rgb.data_ptr() if rgb is not None else None,
             first_idx.data_ptr(), num_points.data_ptr(), total.data_ptr(), ws_ptr, nbytes.value,
             ops._stream_ptr(dev)), "pgdvs_uwp_bin")
-    ops.LAUNCHES["count"] += 4  # k_uwp, k_uwp_finalize, k_scan, k_fill_pre
+    ops.LAUNCHES["count"] += 6  # k_uwp_count, k_scan, k_uwp, k_uwp_finalize, k_scan, k_fill_pre
     out = ops.rasterize_workspace(ws_ptr, nbytes.value, dev, n_views, cap, H, W, K, float(radius), False, 3,
                                   ops._COMPOSITORS[compositor], float(radius) * float(radius),
                                   (0.0, 0.0, 0.0), static_rgb, return_fragments, True, raster_events)

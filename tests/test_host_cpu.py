@@ -38,8 +38,8 @@ def test_error_strings_and_host_side_validation(lib):
     assert b"150" in lib.pgdvs_error_string(-2)
     n = ctypes.c_size_t(0)
     assert lib.pgdvs_bin_workspace_bytes(1, 288, 544, 313344, 0.01, ctypes.byref(n)) == 0
-    # counters for (288+2)*(544+2) cells + rank (8 B) + two float4 records per point
-    assert n.value >= 290 * 546 * 4 + 313344 * (8 + 16 + 16)
+    # counters for (288+2)*(544+2) cells + cell id (4 B) + two float4 records per point
+    assert n.value >= 290 * 546 * 4 + 313344 * (4 + 16 + 16)
     assert lib.pgdvs_bin_workspace_bytes(1, 0, 544, 10, 0.01, ctypes.byref(n)) == -1
     assert lib.pgdvs_bin_workspace_bytes(1, 8, 8, 10, -1.0, ctypes.byref(n)) == -1
     assert lib.pgdvs_uwp_workspace_bytes(4, 288, 544, ctypes.byref(n)) == 0 and n.value > 0
