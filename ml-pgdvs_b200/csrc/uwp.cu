@@ -61,44 +61,49 @@ __device__ __forceinline__ float grid_unnormalize(float c, float size) {
   return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), size), 1.0f), 0.5f);
 }
 
-__device__ __forceinline__ void load4(const float* p, int64_t i, bool vec, int64_t limit, float o[4]) {
-  if (vec) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = (i + k < limit) ? __ldg(p + i + k) : 0.0f;
-  }
-}
+// Thread t of a tile owns the 4 pixels  tile0 + k*256 + t  (k = 0..3): for a fixed k the 32
+// lanes of a warp touch 32 CONSECUTIVE source pixels, so the streaming reads (mask, flow as
+// float2, depth) are perfectly coalesced, the frame-2 taps of neighbouring lanes share
+// sectors, and — because survivors keep pixel order — consecutive lanes write consecutive
+// float4 records.
+struct PixelSet {
+  int64_t pix[kUwpPix];
+  int u[kUwpPix], v[kUwpPix];
+  float2 flow[kUwpPix];
+  unsigned valid;  // bit k: pixel k survives
+};
 
-// Which of this thread's 4 pixels survive (pgdvs_renderer_dyn.py:304-316, 438-440); also
-// returns the flow of the 4 pixels, which the geometry needs again.
-__device__ __forceinline__ unsigned pixel_validity(const UwpParams& p, const PgdvsUwpJob& J, int64_t pix0,
-                                                   int u0, int v0, bool in_range, bool vec, float fl[8]) {
+// Which of this thread's pixels survive (pgdvs_renderer_dyn.py:304-316, 438-440).
+__device__ __forceinline__ void pixel_validity(const UwpParams& p, const PgdvsUwpJob& J, int64_t tile0,
+                                               PixelSet& s) {
   const int64_t HW = (int64_t)p.H * p.W;
-  unsigned valid = 0;
-  if (in_range) {
-    float m[4], oc[4] = {0, 0, 0, 0};
-    load4(J.mask1, pix0, vec, HW, m);
-    load4(J.flow12, pix0 * 2, vec, HW * 2, fl);
-    load4(J.flow12, pix0 * 2 + 4, vec, HW * 2, fl + 4);
-    if (J.occ12 != nullptr) load4(J.occ12, pix0, vec, HW, oc);
-    int uu = u0, vv = v0;
+  s.valid = 0;
+  const int64_t first = tile0 + threadIdx.x;
+  int v = (int)(first / p.W), u = (int)(first - (int64_t)v * p.W);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t pix = pix0 + k;
-      if (pix < HW) {
-        bool ok = (m[k] != 0.0f);                            // dyn_mask.bool()
-        if (J.occ12 != nullptr) ok = ok && !(oc[k] > 0.0f);  // ~(occ > 0) & mask
-        const float u2 = __fadd_rn((float)uu, fl[2 * k]), v2 = __fadd_rn((float)vv, fl[2 * k + 1]);
-        ok = ok && (u2 >= 0.0f) && (u2 <= (float)(p.W - 1)) && (v2 >= 0.0f) && (v2 <= (float)(p.H - 1));
-        if (ok && J.keep != nullptr) ok = (J.keep[pix] != 0);
-        if (ok) valid |= 1u << k;
-      }
-      if (++uu == p.W) { uu = 0; ++vv; }
+  for (int k = 0; k < kUwpPix; ++k) {
+    const int64_t pix = first + (int64_t)k * kUwpThreads;
+    s.pix[k] = pix;
+    s.u[k] = u;
+    s.v[k] = v;
+    s.flow[k] = make_float2(0.f, 0.f);
+    if (pix < HW) {
+      const float m = __ldg(J.mask1 + pix);
+      const float2 fl = __ldg(reinterpret_cast<const float2*>(J.flow12) + pix);
+      s.flow[k] = fl;
+      bool ok = (m != 0.0f);                                                  // dyn_mask.bool()
+      if (J.occ12 != nullptr) ok = ok && !(__ldg(J.occ12 + pix) > 0.0f);      // ~(occ > 0) & mask
+      const float u2 = __fadd_rn((float)u, fl.x), v2 = __fadd_rn((float)v, fl.y);
+      ok = ok && (u2 >= 0.0f) && (u2 <= (float)(p.W - 1)) && (v2 >= 0.0f) && (v2 <= (float)(p.H - 1));
+      if (ok && J.keep != nullptr) ok = (J.keep[pix] != 0);
+      if (ok) s.valid |= 1u << k;
+    }
+    u += kUwpThreads;  // next pixel of this thread is 256 further along the row-major order
+    while (u >= p.W) {
+      u -= p.W;
+      ++v;
     }
   }
-  return valid;
 }
 
 __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant__ UwpParams p) {
@@ -107,13 +112,9 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant
   const int job_i = tile / p.tiles_per_job;
   const int jt = tile - job_i * p.tiles_per_job;
   const PgdvsUwpJob& J = p.jobs[job_i];
-  const int64_t HW = (int64_t)p.H * p.W;
-  const int64_t pix0 = (int64_t)jt * kUwpTile + (int64_t)threadIdx.x * kUwpPix;
-  const bool in_range = pix0 < HW;
-  const bool vec = ((HW & 3) == 0) && in_range;
-  const int v0 = (int)(pix0 / p.W), u0 = (int)(pix0 - (int64_t)v0 * p.W);
-  float fl[8];
-  int cnt = __popc(pixel_validity(p, J, pix0, u0, v0, in_range, vec, fl));
+  PixelSet s;
+  pixel_validity(p, J, (int64_t)jt * kUwpTile, s);
+  int cnt = __popc(s.valid);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
   if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
@@ -128,68 +129,64 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant
 
 template <bool FUSED>
 __global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ UwpParams p) {
-  __shared__ int s_warp[kUwpThreads / 32];
+  constexpr int kWarps = kUwpThreads / 32;
+  __shared__ int s_cnt[kUwpPix * kWarps];  // survivors of (k, warp), k-major == pixel order
   const int tile = blockIdx.x;
   const int job_i = tile / p.tiles_per_job;
   const int jt = tile - job_i * p.tiles_per_job;
   const PgdvsUwpJob& J = p.jobs[job_i];
-  const int64_t HW = (int64_t)p.H * p.W;
-  const int64_t pix0 = (int64_t)jt * kUwpTile + (int64_t)threadIdx.x * kUwpPix;
-  const bool in_range = pix0 < HW;
-  const bool vec = ((HW & 3) == 0) && in_range;  // host guarantees 16-byte aligned planes
-  // (u, v) of the first pixel; the other three follow by incrementing (one div per thread)
-  const int v0 = (int)(pix0 / p.W), u0 = (int)(pix0 - (int64_t)v0 * p.W);
   const int tile_base = __ldg(p.tile_off + tile);
 
-  float fl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const unsigned valid = pixel_validity(p, J, pix0, u0, v0, in_range, vec, fl);
-  const int cnt = __popc(valid);
+  PixelSet s;
+  pixel_validity(p, J, (int64_t)jt * kUwpTile, s);
 
-  // ------------------------------------------------------------ order inside the tile
+  // ------------------------------------------------------------ order inside the tile:
+  // warp ballots give each survivor its rank inside (k, warp); a 32-entry prefix over the
+  // (k, warp) counts gives the rest
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int inc = cnt;
+  int rank[kUwpPix];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += o;
+  for (int k = 0; k < kUwpPix; ++k) {
+    const unsigned m = __ballot_sync(0xffffffffu, (s.valid >> k) & 1u);
+    rank[k] = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_cnt[k * kWarps + warp] = __popc(m);
   }
-  if (lane == 31) s_warp[warp] = inc;
   __syncthreads();
-  int warp_off = 0;
+  {
+    // every warp redundantly scans the 32 counts (one shuffle scan; cheaper than a 2nd barrier)
+    const int c = s_cnt[lane];
+    int inc = c;
 #pragma unroll
-  for (int w = 0; w < kUwpThreads / 32; ++w)
-    if (w < warp) warp_off += s_warp[w];
-  if (valid == 0) return;
-  int64_t out = (int64_t)tile_base + warp_off + (inc - cnt);
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int excl = inc - c;
+#pragma unroll
+    for (int k = 0; k < kUwpPix; ++k) rank[k] += __shfl_sync(0xffffffffu, excl, k * kWarps + warp);
+  }
+  if (s.valid == 0) return;
 
   // ------------------------------------------------------------ geometry for survivors
-  float d1[4], c1[12];
-  load4(J.depth1, pix0, vec, HW, d1);
   const PgdvsCamera cam = p.cams[J.view];
   const bool lerp = (J.same_time == 0);
-  if (!lerp) {
-    load4(J.rgb1, pix0 * 3, vec, HW * 3, c1);
-    load4(J.rgb1, pix0 * 3 + 4, vec, HW * 3, c1 + 4);
-    load4(J.rgb1, pix0 * 3 + 8, vec, HW * 3, c1 + 8);
-  }
   const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
-  int uu = u0, vv = v0;
+  float d1[kUwpPix];
+#pragma unroll
+  for (int k = 0; k < kUwpPix; ++k) d1[k] = ((s.valid >> k) & 1u) ? __ldg(J.depth1 + s.pix[k]) : 0.0f;
   // two pixels at a time: their 8 frame-2 taps are issued back to back before any is consumed
 #pragma unroll
-  for (int k0 = 0; k0 < 4; k0 += 2) {
-    float uf[2], vf[2], u2a[2], v2a[2], wgt[2][4];
+  for (int k0 = 0; k0 < kUwpPix; k0 += 2) {
+    float u2a[2], v2a[2], wgt[2][4];
     float4 tap[2][4];
     int near_tap[2];
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       const int k = k0 + kk;
-      uf[kk] = (float)uu;
-      vf[kk] = (float)vv;
-      if (++uu == p.W) { uu = 0; ++vv; }
       near_tap[kk] = 0;
       if (lerp) {
-        const bool ok = (valid >> k) & 1u;
-        const float u2 = __fadd_rn(uf[kk], fl[2 * k]), v2 = __fadd_rn(vf[kk], fl[2 * k + 1]);
+        const bool ok = (s.valid >> k) & 1u;
+        const float u2 = __fadd_rn((float)s.u[k], s.flow[k].x), v2 = __fadd_rn((float)s.v[k], s.flow[k].y);
         u2a[kk] = u2;
         v2a[kk] = v2;
         const float ix = grid_unnormalize(u2, (float)p.W);
@@ -226,17 +223,18 @@ __global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ 
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       const int k = k0 + kk;
-      if (!((valid >> k) & 1u)) continue;
-      const float u = uf[kk], v = vf[kk];
+      if (!((s.valid >> k) & 1u)) continue;
+      const float u = (float)s.u[k], v = (float)s.v[k];
       // rays_d = (c2w[:3,:3] @ K^-1) @ [u, v, 1]
       float wx = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
       float wy = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
       float wz = J.o1[2] + (J.M1[6] * u + J.M1[7] * v + J.M1[8]) * d1[k];
       float cr, cg, cb;
       if (!lerp) {
-        cr = c1[3 * k];
-        cg = c1[3 * k + 1];
-        cb = c1[3 * k + 2];
+        const float* c1 = J.rgb1 + s.pix[k] * 3;
+        cr = __ldg(c1);
+        cg = __ldg(c1 + 1);
+        cb = __ldg(c1 + 2);
       } else {
         cr = cg = cb = 0.0f;
         float dep2 = 0.0f;
@@ -260,6 +258,7 @@ __global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ 
         wz = J.w1 * wz + J.w2 * qz;
       }
       const float3 ndc = world_to_ndc(cam, wx, wy, wz);
+      const int64_t out = (int64_t)tile_base + rank[k];
       if (FUSED) {
         const int cell = point_cell(p.g, J.view, ndc.x, ndc.y, ndc.z);
         if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
@@ -282,8 +281,7 @@ __global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ 
         p.xyz_world[out * 3 + 1] = wy;
         p.xyz_world[out * 3 + 2] = wz;
       }
-      if (p.src_pix) p.src_pix[out] = (int32_t)(pix0 + k);
-      ++out;
+      if (p.src_pix) p.src_pix[out] = (int32_t)s.pix[k];
     }
   }
 }
