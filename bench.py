@@ -218,7 +218,7 @@ def run_ours(args):
     from pgdvs_b200 import ops, synthetic
     from pgdvs_b200.dyn_renderer import prepare_views, render_prepared
 
-    wl = synthetic.make_workload(args.workload, dev, n_views=args.views, seed=1234 + rank)
+    wl = synthetic.make_workload(args.workload, dev, n_views=args.views, seed=1234 + rank, flow_mode=args.flow)
     V, H, W, K, radius = wl.n_views, wl.H, wl.W, wl.K, wl.radius
     pairs, cams = wl.jobs(range(V))
     prep = prepare_views(pairs, cams, H, W, dev)
@@ -360,6 +360,8 @@ def run_ours(args):
                        "source_frames_per_view": wl.meta["S"], "points_per_view": total_points // V,
                        "points_per_pixel": K, "radius": radius, "compositor": "norm_weighted+mask+static_blend",
                        "fragments_written": bool(args.fragments),
+                       "synthetic_flow": ("9x9-box-smoothed N(0,3px) + 0.1px jitter (piecewise-smooth motion)"
+                                          if args.flow == "smooth" else "i.i.d. N(0,3px) per pixel (incoherent stress case)"),
                        "parallelism": f"views sharded over {world} GPU(s); NCCL gather of frames to rank 0" if world > 1 else "1 GPU",
                        "cache": f"L2 flushed with a {L2_FLUSH_BYTES >> 20} MiB memset before every step (inside the timed bracket); "
                                 f"per-step working set ~{(b_rc + 72 * total_points) / 1e9:.1f} GB >> 126 MB L2"},
@@ -392,6 +394,8 @@ def main():
     ap.add_argument("--no-fragments", dest="fragments", action="store_false",
                     help="do not materialise idx/zbuf/dists (fused-only mode; B_rc drops the 12*K*H*W term)")
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
+    ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"],
+                    help="synthetic optical flow: piecewise-smooth (default) or i.i.d. per pixel (stress)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

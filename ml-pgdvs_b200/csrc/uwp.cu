@@ -57,7 +57,11 @@ struct UwpParams {
 //   g = 2*c/size - 1 ;  ix = ((g + 1) * size - 1) / 2          (every op rounded to fp32;
 // identical to ATen's CPU `(g + 1) * (size/2) - 0.5`, checked in tests)
 __device__ __forceinline__ float grid_unnormalize(float c, float size) {
+#ifdef PGDVS_EXP_FAST_DIV
+  const float g = __fsub_rn(__fdividef(__fmul_rn(2.0f, c), size), 1.0f);
+#else
   const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, c), size), 1.0f);
+#endif
   return __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), size), 1.0f), 0.5f);
 }
 
@@ -209,7 +213,11 @@ __global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ 
           const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
           const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
           tap[kk][t] = make_float4(0.f, 0.f, 0.f, 0.f);  // zeros padding
+#ifdef PGDVS_EXP_NO_TAPS
+          if (false) {
+#else
           if (inb) {
+#endif
             const int64_t o = (int64_t)ys * p.W + xs;
             if (rgbd2 != nullptr)
               tap[kk][t] = __ldg(rgbd2 + o);
@@ -261,10 +269,18 @@ __global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ 
       const int64_t out = (int64_t)tile_base + rank[k];
       if (FUSED) {
         const int cell = point_cell(p.g, J.view, ndc.x, ndc.y, ndc.z);
+#ifndef PGDVS_EXP_NO_ATOMIC
         if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
-        p.cell_of[out] = cell;
-        p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
-        p.preB[out] = make_float4(cr, cg, cb, 0.0f);
+#endif
+#ifdef PGDVS_EXP_NO_STORE
+        if (ndc.x == 12345.678f) {
+#else
+        {
+#endif
+          p.cell_of[out] = cell;
+          p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
+          p.preB[out] = make_float4(cr, cg, cb, 0.0f);
+        }
       }
       if (p.xyz_ndc) {
         p.xyz_ndc[out * 3 + 0] = ndc.x;

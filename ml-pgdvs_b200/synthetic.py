@@ -91,7 +91,8 @@ def _rot_x(a):
     return np.array([[1, 0, 0], [0, c, -s], [0, s, c]], np.float32)
 
 
-def make_scene(H, W, frames, device, seed=1234, mask_mode="full", flow_std=3.0, smooth=True) -> Scene:
+def make_scene(H, W, frames, device, seed=1234, mask_mode="full", flow_std=3.0, smooth=True,
+               flow_mode="smooth") -> Scene:
     g = torch.Generator(device=device).manual_seed(seed)
     rgb = torch.rand((frames, H, W, 3), generator=g, device=device)
     depth = 1.0 + 9.0 * torch.rand((frames, H, W, 1), generator=g, device=device)
@@ -108,7 +109,18 @@ def make_scene(H, W, frames, device, seed=1234, mask_mode="full", flow_std=3.0, 
         raise ValueError(mask_mode)
 
     def flow():
-        f = flow_std * torch.randn((frames, H, W, 2), generator=g, device=device)
+        f = torch.randn((frames, H, W, 2), generator=g, device=device)
+        if flow_mode == "smooth":
+            # piecewise-smooth motion like real optical flow: low-pass the noise with the same 9x9
+            # box used for depth, rescale to the requested std, add a little sub-pixel jitter
+            f = _box_smooth(f.reshape(frames, H, W, 2).permute(0, 3, 1, 2).reshape(frames * 2, H, W, 1))
+            f = f.reshape(frames, 2, H, W).permute(0, 2, 3, 1)
+            f = f / f.std().clamp_min(1e-6)
+            f = flow_std * f + 0.1 * torch.randn((frames, H, W, 2), generator=g, device=device)
+        elif flow_mode == "iid":
+            f = flow_std * f  # stress case: every pixel moves independently (incoherent gathers)
+        else:
+            raise ValueError(flow_mode)
         uu = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
         vv = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
         # clip so that uv + flow stays inside the image (most points survive the validity test)
@@ -150,13 +162,13 @@ def _pair(scene: Scene, a: int, b: int, t_tgt: float) -> SourcePair:
 
 def make_workload(name: str, device, n_views: Optional[int] = None, seed: int = 1234,
                   K: Optional[int] = None, radius: Optional[float] = None, mask_mode: str = "full",
-                  with_static: bool = True) -> Workload:
+                  with_static: bool = True, flow_mode: str = "smooth") -> Workload:
     cfg = dict(CONFIGS[name])
     H, W, F, S = cfg["H"], cfg["W"], cfg["frames"], cfg["S"]
     V = n_views if n_views is not None else cfg["views"]
     K = K if K is not None else cfg["K"]
     radius = radius if radius is not None else cfg["radius"]
-    scene = make_scene(H, W, F, device, seed=seed, mask_mode=mask_mode)
+    scene = make_scene(H, W, F, device, seed=seed, mask_mode=mask_mode, flow_mode=flow_mode)
     view_pairs, view_cams = [], []
     n_cams = 12 if name.startswith("c2") else max(V, 1)
     for v in range(V):
@@ -189,4 +201,4 @@ def make_workload(name: str, device, n_views: Optional[int] = None, seed: int = 
         g = torch.Generator(device=device).manual_seed(seed + 1)
         static = torch.rand((V, H, W, 3), generator=g, device=device)
     return Workload(name, H, W, K, radius, scene, view_pairs, view_cams, static,
-                    meta=dict(S=S, frames=F, mask_mode=mask_mode, seed=seed))
+                    meta=dict(S=S, frames=F, mask_mode=mask_mode, seed=seed, flow_mode=flow_mode))
