@@ -214,6 +214,10 @@ int pgdvs_knn_workspace_bytes(int64_t Q, int64_t R, size_t* bytes);
 int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* ref, int64_t R, int K,
                         int skip_first, float* mean_out, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* Full `pytorch3d.ops.knn_points` result for one cloud pair: squared distances f32 [Q,K]
+ * (ascending) and reference indices i64 [Q,K]; slots beyond R hold (0, -1).  K <= 64. */
+int pgdvs_knn_points(const float* query, int64_t Q, const float* ref, int64_t R, int K,
+                     float* dists_out, int64_t* idx_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "pgdvs_rasterize_composite", "pgdvs_composite", "pgdvs_uwp_workspace_bytes",
     "pgdvs_unproject_warp_project", "pgdvs_project_points", "pgdvs_merge_blend",
     "pgdvs_uwp_bin_workspace_bytes", "pgdvs_uwp_bin", "pgdvs_pack_rgbd",
-    "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist",
+    "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist", "pgdvs_knn_points",
 )
 
 
@@ -102,6 +102,8 @@ def lib():
     L.pgdvs_knn_mean_dist.restype = c_int
     L.pgdvs_knn_mean_dist.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p,
                                       c_void_p, c_size_t, c_void_p]
+    L.pgdvs_knn_points.restype = c_int
+    L.pgdvs_knn_points.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     if L.pgdvs_abi_version() != 1:
         raise ImportError("libpgdvs_b200.so ABI version mismatch; rebuild it")
     lay = (c_int32 * 4)()

@@ -1,11 +1,12 @@
-// Statistical-outlier support: mean squared distance to the K nearest neighbours.
+// Statistical-outlier support: K nearest neighbours by brute force.
 //
 // Replaces `pytorch3d.ops.knn_points(p1, p2, K=knn+1, return_nn=True)` followed by
 // `torch.mean(nn_dists[..., skip:], dim=1)` at pgdvs_renderer_dyn.py:405-419 and
-// pgdvs_renderer_dyn_track.py:303-318, 345-361 (squared L2, ascending, brute force).
-// Only the K smallest squared distances are needed (not the indices / neighbours, which the
-// reference computes and discards), so each query keeps a sorted K-list of distances in
-// registers while reference points stream through shared memory in float4 tiles.
+// pgdvs_renderer_dyn_track.py:303-318, 345-361 (squared L2, ascending).  The reference only
+// consumes the mean of the K smallest squared distances (it computes and discards the indices
+// and neighbours), so the fast entry point keeps a sorted K-list of distances in registers
+// while reference points stream through shared memory in float4 tiles.  The full
+// (dists, idx) variant backs the pytorch3d-compatible `knn_points` facade.
 #include "common.cuh"
 
 namespace pgdvs {
@@ -14,9 +15,12 @@ constexpr int kKnnThreads = 128;
 constexpr int kKnnTile = 1024;
 constexpr int kKnnMaxK = 64;
 
-__global__ void __launch_bounds__(kKnnThreads) k_knn_mean(const float* __restrict__ query, int64_t Q,
-                                                          const float* __restrict__ ref, int64_t R,
-                                                          int K, int skip, float* __restrict__ out) {
+template <bool WITH_IDX>
+__global__ void __launch_bounds__(kKnnThreads) k_knn(const float* __restrict__ query, int64_t Q,
+                                                     const float* __restrict__ ref, int64_t R, int K,
+                                                     int skip, float* __restrict__ mean_out,
+                                                     float* __restrict__ dists_out,
+                                                     int64_t* __restrict__ idx_out) {
   __shared__ float4 tile[kKnnTile];
   const int64_t qi = (int64_t)blockIdx.x * kKnnThreads + threadIdx.x;
   const bool active = qi < Q;
@@ -27,8 +31,12 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn_mean(const float* __restric
     qz = __ldg(query + qi * 3 + 2);
   }
   float best[kKnnMaxK];
+  int bidx[WITH_IDX ? kKnnMaxK : 1];
 #pragma unroll
-  for (int i = 0; i < kKnnMaxK; ++i) best[i] = __int_as_float(0x7f800000);
+  for (int i = 0; i < kKnnMaxK; ++i) {
+    best[i] = __int_as_float(0x7f800000);
+    if (WITH_IDX) bidx[i] = -1;
+  }
   // only the first K slots matter; kth = best[K-1] is tracked in a scalar
   float kth = __int_as_float(0x7f800000);
 
@@ -46,8 +54,9 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn_mean(const float* __restric
       const float dx = qx - r.x, dy = qy - r.y, dz = qz - r.z;
       const float d = dx * dx + dy * dy + dz * dz;
       if (d < kth) {
-        // sorted insert into best[0..K-1]
+        // sorted insert into best[0..K-1] (strict <: earlier index first among equal distances)
         float c = d;
+        int ci = (int)(base + i);
 #pragma unroll
         for (int j = 0; j < kKnnMaxK; ++j) {
           if (j < K) {
@@ -55,9 +64,13 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn_mean(const float* __restric
             const bool lt = c < b;
             best[j] = lt ? c : b;
             c = lt ? b : c;
+            if (WITH_IDX) {
+              const int bi = bidx[j];
+              bidx[j] = lt ? ci : bi;
+              ci = lt ? bi : ci;
+            }
           }
         }
-        // kth = best[K-1]
         float k2 = best[0];
 #pragma unroll
         for (int j = 1; j < kKnnMaxK; ++j)
@@ -68,12 +81,24 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn_mean(const float* __restric
   }
   if (!active) return;
   const int kk = (int)(R < (int64_t)K ? R : (int64_t)K);
-  float sum = 0.f;
+  if (mean_out) {
+    float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < kKnnMaxK; ++j)
-    if (j >= skip && j < kk) sum += best[j];
-  const int cnt = kk - skip;
-  out[qi] = cnt > 0 ? sum / (float)cnt : 0.f;
+    for (int j = 0; j < kKnnMaxK; ++j)
+      if (j >= skip && j < kk) sum += best[j];
+    const int cnt = kk - skip;
+    mean_out[qi] = cnt > 0 ? sum / (float)cnt : 0.f;
+  }
+  if (WITH_IDX) {
+#pragma unroll
+    for (int j = 0; j < kKnnMaxK; ++j) {
+      if (j < K) {
+        // pytorch3d pads with 0 / -1... the facade documents: slots beyond R hold (0, -1)
+        dists_out[qi * K + j] = (j < kk) ? best[j] : 0.f;
+        idx_out[qi * K + j] = (j < kk) ? (int64_t)bidx[j] : (int64_t)-1;
+      }
+    }
+  }
 }
 
 }  // namespace pgdvs
@@ -96,6 +121,19 @@ extern "C" int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* r
   if (Q == 0) return PGDVS_OK;
   if (!query || !mean_out || (R > 0 && !ref)) return PGDVS_E_BADARG;
   const unsigned grid = (unsigned)((Q + kKnnThreads - 1) / kKnnThreads);
-  k_knn_mean<<<grid, kKnnThreads, 0, (cudaStream_t)stream>>>(query, Q, ref, R, K, skip_first, mean_out);
+  k_knn<false><<<grid, kKnnThreads, 0, (cudaStream_t)stream>>>(query, Q, ref, R, K, skip_first, mean_out,
+                                                               nullptr, nullptr);
+  return check_launch();
+}
+
+extern "C" int pgdvs_knn_points(const float* query, int64_t Q, const float* ref, int64_t R, int K,
+                                float* dists_out, int64_t* idx_out, void* stream) {
+  if (Q < 0 || R < 0 || K < 1) return PGDVS_E_BADARG;
+  if (K > kKnnMaxK) return PGDVS_E_K_TOO_LARGE;
+  if (Q == 0) return PGDVS_OK;
+  if (!query || !dists_out || !idx_out || (R > 0 && !ref)) return PGDVS_E_BADARG;
+  const unsigned grid = (unsigned)((Q + kKnnThreads - 1) / kKnnThreads);
+  k_knn<true><<<grid, kKnnThreads, 0, (cudaStream_t)stream>>>(query, Q, ref, R, K, 0, nullptr, dists_out,
+                                                              idx_out);
   return check_launch();
 }

@@ -290,6 +290,35 @@ def knn_mean_dist(query: torch.Tensor, ref: torch.Tensor, K: int, skip_first: in
     return out
 
 
+class _KNN(tuple):
+    """(dists, idx, knn) like pytorch3d.ops.knn._KNN."""
+    dists = property(lambda s: s[0])
+    idx = property(lambda s: s[1])
+    knn = property(lambda s: s[2])
+
+
+def knn_points(p1: torch.Tensor, p2: torch.Tensor, K: int = 1, return_nn: bool = False, **_ignored):
+    """pytorch3d.ops.knn_points for equal-length batches: p1 [N,P1,3], p2 [N,P2,3] ->
+    (dists [N,P1,K] squared L2 ascending, idx [N,P1,K] int64, knn [N,P1,K,3] or None)."""
+    _require_cuda(p1, "p1")
+    dev = p1.device
+    if p1.ndim != 3 or p2.ndim != 3 or p1.shape[0] != p2.shape[0]:
+        raise ValueError("pts1 and pts2 must have the same batch dimension.")
+    N, P1, _ = p1.shape
+    dists = torch.empty((N, P1, K), dtype=torch.float32, device=dev)
+    idx = torch.empty((N, P1, K), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        for n in range(N):
+            q, r = _f32c(p1[n]), _f32c(p2[n].to(dev))
+            _cabi.check(_cabi.lib().pgdvs_knn_points(q.data_ptr(), P1, r.data_ptr(), r.shape[0], int(K),
+                                                     dists[n].data_ptr(), idx[n].data_ptr(), _stream_ptr(dev)),
+                        "pgdvs_knn_points")
+    nn = None
+    if return_nn:
+        nn = torch.stack([p2[n][idx[n].clamp_min(0)] for n in range(N)], dim=0)
+    return _KNN((dists, idx, nn))
+
+
 def merge_blend(dyn_rgb, dyn_mask, track_rgb=None, track_mask=None, static_rgb=None):
     """pgdvs_renderer_dyn.py:229-235 (+ pgdvs_renderer.py:169-172 when static_rgb is given).
     Channels-first [B,3,H,W] / [B,1,H,W].  Returns (rgb, mask, combined-or-None)."""

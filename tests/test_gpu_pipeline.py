@@ -302,6 +302,50 @@ def test_forward_end_to_end_vs_oracle():
     assert torch.equal(comb, e_comb)
 
 
+def test_compat_namespace_runs_the_reference_call_sequence(golden_dir):
+    """`import pgdvs_b200.compat as pytorch3d`: the statement sequence of
+    pgdvs_renderer_dyn.py:676-722 (render_dyn_pcl) and :405-419 (knn statistics), written against
+    the pytorch3d names, runs unchanged and matches the oracle."""
+    import pgdvs_b200.compat as pytorch3d
+    import pgdvs_b200.compat.ops as p3d_ops
+    g = np.load(golden_dir / "dyn_pcl_case0.npz")
+    d = _dev()
+    h, w = int(g["H"]), int(g["W"])
+    flat_cam = T(g["flat_cam_tgt"]).to(d)
+    dyn_pcl, rgbs = T(g["b_points"][0]).to(d), T(g["b_features"][0]).to(d)
+    radius, ppp = float(g["b_radius"]), int(g["b_ppp"])
+    # --- reference statements (names as in the reference) ---
+    K = flat_cam[2:18].reshape((4, 4))
+    c2w = flat_cam[18:34].reshape((4, 4))
+    w2c = torch.inverse(c2w)
+    img_size = torch.LongTensor([h, w]).reshape((1, 2))
+    cameras_pytorch3d = pytorch3d.utils.cameras_from_opencv_projection(
+        w2c[None, :3, :3], w2c[None, :3, 3], K[None, :3, :3], img_size)
+    raster_settings = pytorch3d.renderer.PointsRasterizationSettings(
+        image_size=(h, w), radius=radius, points_per_pixel=ppp, bin_size=0)
+    rasterizer = pytorch3d.renderer.PointsRasterizer(cameras=cameras_pytorch3d, raster_settings=raster_settings)
+    point_renderer = pytorch3d.renderer.PointsRenderer(
+        rasterizer=rasterizer, compositor=pytorch3d.renderer.NormWeightedCompositor(background_color=(0, 0, 0)))
+    dy_mesh = pytorch3d.structures.Pointclouds(points=dyn_pcl[None, ...], features=rgbs[None, ...])
+    mesh_img = point_renderer(dy_mesh)[0, :, :, :3]
+    dy_mesh.features = torch.ones_like(rgbs)[None, ...]
+    mesh_mask = (point_renderer(dy_mesh)[0, :, :, :1] > 0.0).float()
+    nn_dists, nn_idxs, nn_pts = p3d_ops.knn_points(dyn_pcl[None, ...], dyn_pcl[None, ...], K=9, return_nn=True)
+    avg_nn_dist = torch.mean(nn_dists[0, :, 1:], dim=1)
+    # --- checks ---
+    e_img, e_mask = ref.render_dyn_pcl(H=h, W=w, dyn_pcl=dyn_pcl.cpu(), rgbs=rgbs.cpu(), flat_cam=flat_cam.cpu(),
+                                       radius=radius, points_per_pixel=ppp)
+    assert (mesh_mask.cpu() == e_mask).float().mean() > 0.995
+    diff = (mesh_img.cpu() - e_img).abs().max(dim=-1).values
+    assert (diff < 1e-4).float().mean() > 0.99
+    _, _, e_avg = ref.knn_outlier_flags(dyn_pcl.cpu(), knn=8)
+    np.testing.assert_allclose(avg_nn_dist.cpu().numpy(), e_avg.numpy(), rtol=2e-5, atol=1e-7)
+    assert nn_idxs.shape == (1, dyn_pcl.shape[0], 9) and nn_pts.shape == (1, dyn_pcl.shape[0], 9, 3)
+    assert torch.equal(nn_idxs[0, :, 0].cpu(), torch.arange(dyn_pcl.shape[0]))  # nearest neighbour is the point itself
+    d2 = ((dyn_pcl[:, None] - nn_pts[0]) ** 2).sum(-1)
+    np.testing.assert_allclose(d2.cpu().numpy(), nn_dists[0].cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
 def test_pytorch3d_facade_generic_equals_fused():
     """The pytorch3d-shaped classes: the generic two-step path (rasterize -> torch weights ->
     stand-alone compositor, any C) and the fused path give the same image."""
