@@ -80,7 +80,10 @@ __global__ void __launch_bounds__(256) k_fill(BinParams p) {
 // Fused path: the uwp kernel already produced the cell of every point and the packed-order
 // records.  Each thread moves kFillUnroll points with all loads, then all atomics, then all
 // stores issued back to back.
-constexpr int kFillUnroll = 4;
+#ifndef PGDVS_FILL_UNROLL
+#define PGDVS_FILL_UNROLL 4
+#endif
+constexpr int kFillUnroll = PGDVS_FILL_UNROLL;
 __global__ void __launch_bounds__(256) k_fill_pre(BinParams p) {
   const int64_t total = *p.total;
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x) * kFillUnroll + threadIdx.x;

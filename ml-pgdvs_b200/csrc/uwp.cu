@@ -132,7 +132,10 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kUwpThreads, 3) k_uwp(const __grid_constant__ UwpParams p) {
+#ifndef PGDVS_UWP_MINBLOCKS
+#define PGDVS_UWP_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const __grid_constant__ UwpParams p) {
   constexpr int kWarps = kUwpThreads / 32;
   __shared__ int s_cnt[kUwpPix * kWarps];  // survivors of (k, warp), k-major == pixel order
   const int tile = blockIdx.x;

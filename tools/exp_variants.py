@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Developer experiment harness: build variants of the CUDA library with -D switches and time one
-C-ABI stage per variant with CUDA events on the C2 workload.  Not part of the product.
+"""Developer experiment harness: build variants of the CUDA library with -D switches and time the
+C-ABI stages per variant with CUDA events on the C2 workload.  Not part of the product.
 
     python tools/exp_variants.py build   (here, needs nvcc)
     python tools/exp_variants.py run     (on the GPU box)
@@ -12,10 +12,13 @@ sys.path.insert(0, str(ROOT))
 OUT = ROOT / "exp_libs"
 VARIANTS = {
     "base": [],
-    "no_atomic": ["-DPGDVS_EXP_NO_ATOMIC"],
-    "no_taps": ["-DPGDVS_EXP_NO_TAPS"],
-    "no_store": ["-DPGDVS_EXP_NO_STORE"],
-    "no_geom_div": ["-DPGDVS_EXP_FAST_DIV"],
+    "uwp_mb4": ["-DPGDVS_UWP_MINBLOCKS=4"],
+    "uwp_mb5": ["-DPGDVS_UWP_MINBLOCKS=5"],
+    "fill_u1": ["-DPGDVS_FILL_UNROLL=1"],
+    "fill_u2": ["-DPGDVS_FILL_UNROLL=2"],
+    "fill_u8": ["-DPGDVS_FILL_UNROLL=8"],
+    "ras_mb5": ["-DPGDVS_RASTER_MINBLOCKS=5"],
+    "ras_mb6": ["-DPGDVS_RASTER_MINBLOCKS=6"],
 }
 SRCS = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu"]
 
@@ -27,7 +30,7 @@ def build():
         cmd = ["nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
                "-Xcompiler", "-fPIC", "-shared", "-o", str(OUT / f"lib_{name}.so")] + flags + \
               [str(ROOT / "ml-pgdvs_b200" / "csrc" / s) for s in SRCS]
-        procs.append((name, subprocess.Popen(cmd)))
+        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)))
     for name, p in procs:
         assert p.wait() == 0, name
 
@@ -35,42 +38,66 @@ def build():
 def run():
     import torch
     import pgdvs_b200
-    from pgdvs_b200 import synthetic, ops, _cabi
+    from pgdvs_b200 import synthetic
     from pgdvs_b200.dyn_renderer import prepare_views
     dev = torch.device("cuda:0")
-    wl = synthetic.make_workload("c2_nvidia_seq", dev)
+    flow = os.environ.get("FLOW", "smooth")
+    wl = synthetic.make_workload("c2_nvidia_seq", dev, flow_mode=flow)
     pairs, cams = wl.jobs(range(wl.n_views))
     prep = prepare_views(pairs, cams, wl.H, wl.W, dev)
     prep.pack_frames()
-    n_jobs, n_views, H, W = prep.n_jobs, prep.n_views, prep.H, prep.W
+    n_jobs, n_views, H, W, K = prep.n_jobs, prep.n_views, prep.H, prep.W, wl.K
+    cap = n_jobs * H * W
     first = torch.empty(n_views, dtype=torch.int64, device=dev)
     num = torch.empty(n_views, dtype=torch.int64, device=dev)
     total = torch.empty(1, dtype=torch.int64, device=dev)
+    idx = torch.empty((n_views, H, W, K), dtype=torch.int32, device=dev)
+    zbuf = torch.empty((n_views, H, W, K), dtype=torch.float32, device=dev)
+    dists = torch.empty((n_views, H, W, K), dtype=torch.float32, device=dev)
+    image = torch.empty((n_views, H, W, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((n_views, H, W, 1), dtype=torch.float32, device=dev)
+    V = ctypes.c_void_p
     for name in VARIANTS:
         L = ctypes.CDLL(str(OUT / f"lib_{name}.so"))
         L.pgdvs_uwp_bin_workspace_bytes.argtypes = [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.POINTER(ctypes.c_size_t)]
-        L.pgdvs_uwp_bin.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                    ctypes.c_float] + [ctypes.c_void_p] * 6 + [ctypes.c_size_t, ctypes.c_void_p]
+        L.pgdvs_uwp_bin.argtypes = [V, ctypes.c_int, V, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_float] + [V] * 6 + [ctypes.c_size_t, V]
+        L.pgdvs_rasterize_composite.argtypes = [V, ctypes.c_size_t, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_float, V, V, V, V, V, V, V, V]
         nb = ctypes.c_size_t(0)
         assert L.pgdvs_uwp_bin_workspace_bytes(n_jobs, n_views, H, W, wl.radius, ctypes.byref(nb)) == 0
         ws = torch.empty(nb.value + 256, dtype=torch.uint8, device=dev)
         wp = (ws.data_ptr() + 255) & ~255
         st = torch.cuda.current_stream().cuda_stream
 
-        def call():
+        def uwp():
             rc = L.pgdvs_uwp_bin(prep.jobs_dev.data_ptr(), n_jobs, prep.cams_dev.data_ptr(), n_views, H, W, wl.radius,
                                  None, None, first.data_ptr(), num.data_ptr(), total.data_ptr(), wp, nb.value, st)
             assert rc == 0, rc
-        for _ in range(3):
-            call()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            call()
-        e1.record()
-        torch.cuda.synchronize()
-        print(f"{name:14s} uwp_bin total {e0.elapsed_time(e1) / 5:.3f} ms  (points {int(total)})", flush=True)
+
+        def ras(frag=True):
+            rc = L.pgdvs_rasterize_composite(wp, nb.value, n_views, cap, H, W, K, wl.radius, 0, 3, 2,
+                                             wl.radius * wl.radius, None, wl.static_rgb.data_ptr(),
+                                             idx.data_ptr() if frag else None, zbuf.data_ptr() if frag else None,
+                                             dists.data_ptr() if frag else None, image.data_ptr(), mask.data_ptr(), st)
+            assert rc == 0, rc
+
+        def timeit(fn, n=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        t_u = timeit(uwp)
+        t_r = timeit(ras)
+        t_r0 = timeit(lambda: ras(False))
+        print(f"{name:10s} flow={flow} uwp_bin {t_u:.3f} ms   raster {t_r:.3f} ms   raster(no frags) {t_r0:.3f} ms", flush=True)
 
 
 if __name__ == "__main__":
