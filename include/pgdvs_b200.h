@@ -157,12 +157,20 @@ int pgdvs_uwp_workspace_bytes(int n_jobs, int H, int W, size_t* bytes);
  *  xyz_world     f32 [.,3] or NULL;  src_pix i32 [.] or NULL (flat source pixel of each point)
  *  first_idx/num_points  i64 [n_views] outputs (cloud_to_packed_first_idx / num_points_per_cloud)
  *  total_points  i64 [1] device output
+ *
+ *  Job groups (optional; pass NULL, NULL, 0 for none): jobs that share the source pair, its
+ *  geometry and the lerp weights and differ only in the target camera — e.g. the 12 cameras the
+ *  NVIDIA benchmark renders per time step (datasets/nvidia_eval.py:53).  The world point and
+ *  colour of a source pixel are then computed once per group and only projected per member.
+ *  group_first i32 [n_groups+1] (device), group_members i32 [n_jobs] (device, job indices).
+ *  Results are identical with and without grouping.
  */
 int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras,
                                  int n_views, int H, int W, float* xyz_ndc, float* rgb,
                                  float* xyz_world, int32_t* src_pix, int64_t* first_idx,
-                                 int64_t* num_points, int64_t* total_points, void* workspace,
-                                 size_t workspace_bytes, void* stream);
+                                 int64_t* num_points, int64_t* total_points,
+                                 const int32_t* group_first, const int32_t* group_members,
+                                 int n_groups, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Fused variant used by the batched renderer: the same kernel additionally files every point
  * under its raster cell, then the cell counters are scanned and the records scattered, i.e.
@@ -173,7 +181,8 @@ int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs, const Pgdv
 int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int W, float radius, size_t* bytes);
 int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras, int n_views, int H,
                   int W, float radius, float* xyz_ndc, float* rgb, int64_t* first_idx,
-                  int64_t* num_points, int64_t* total_points, void* workspace, size_t workspace_bytes,
+                  int64_t* num_points, int64_t* total_points, const int32_t* group_first,
+                  const int32_t* group_members, int n_groups, void* workspace, size_t workspace_bytes,
                   void* stream);
 
 /* Pack source frames as (r,g,b,depth) float4 planes so that the warp stage fetches frame-2

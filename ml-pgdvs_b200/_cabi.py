@@ -84,12 +84,13 @@ def lib():
     L.pgdvs_unproject_warp_project.restype = c_int
     L.pgdvs_unproject_warp_project.argtypes = [
         c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]
     L.pgdvs_uwp_bin_workspace_bytes.restype = c_int
     L.pgdvs_uwp_bin_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_float, POINTER(c_size_t)]
     L.pgdvs_uwp_bin.restype = c_int
     L.pgdvs_uwp_bin.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                c_void_p, c_size_t, c_void_p]
     L.pgdvs_pack_rgbd.restype = c_int
     L.pgdvs_pack_rgbd.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p]
     L.pgdvs_project_points.restype = c_int

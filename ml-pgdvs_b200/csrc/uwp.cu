@@ -40,6 +40,8 @@ struct UwpParams {
   int tiles_per_job;
   int64_t n_tiles;
   int* tile_off;     // [n_tiles + 1]: counts, then exclusive offsets; [n_tiles] = total
+  const int32_t* group_first;    // [n_groups + 1] or null (every job its own group)
+  const int32_t* group_members;  // [n_jobs] job indices, grouped
   float* xyz_ndc;    // [cap,3] or null
   float* rgb;        // [cap,3] or null
   float* xyz_world;  // [cap,3] or null
@@ -110,12 +112,23 @@ __device__ __forceinline__ void pixel_validity(const UwpParams& p, const PgdvsUw
   }
 }
 
+// Job groups: jobs that share the source pair, the pair geometry and the lerp weights differ
+// only in the target camera (the NVIDIA benchmark renders all 12 cameras of a time step:
+// datasets/nvidia_eval.py:53).  Validity, frame-2 gathers, bilinear colour and the world point
+// are then computed ONCE per source pixel and only projection + filing + stores repeat per
+// member.  Without grouping (group_first == NULL) every job is its own group.
+__device__ __forceinline__ int group_size(const UwpParams& p, int g) {
+  return p.group_first ? (p.group_first[g + 1] - p.group_first[g]) : 1;
+}
+__device__ __forceinline__ int group_member(const UwpParams& p, int g, int m) {
+  return p.group_first ? p.group_members[p.group_first[g] + m] : g;
+}
+
 __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant__ UwpParams p) {
   __shared__ int s_warp[kUwpThreads / 32];
-  const int tile = blockIdx.x;
-  const int job_i = tile / p.tiles_per_job;
-  const int jt = tile - job_i * p.tiles_per_job;
-  const PgdvsUwpJob& J = p.jobs[job_i];
+  const int g = blockIdx.x / p.tiles_per_job;
+  const int jt = blockIdx.x - g * p.tiles_per_job;
+  const PgdvsUwpJob& J = p.jobs[group_member(p, g, 0)];
   PixelSet s;
   pixel_validity(p, J, (int64_t)jt * kUwpTile, s);
   int cnt = __popc(s.valid);
@@ -123,26 +136,24 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant
   for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
   if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
+  int t = 0;
 #pragma unroll
-    for (int w = 0; w < kUwpThreads / 32; ++w) t += s_warp[w];
-    p.tile_off[tile] = t;
-  }
+  for (int w = 0; w < kUwpThreads / 32; ++w) t += s_warp[w];
+  // the survivors of a tile are the same for every member of the group
+  for (int m = threadIdx.x; m < group_size(p, g); m += kUwpThreads)
+    p.tile_off[(int64_t)group_member(p, g, m) * p.tiles_per_job + jt] = t;
 }
 
-template <bool FUSED>
 #ifndef PGDVS_UWP_MINBLOCKS
 #define PGDVS_UWP_MINBLOCKS 3
 #endif
+template <bool FUSED>
 __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const __grid_constant__ UwpParams p) {
   constexpr int kWarps = kUwpThreads / 32;
   __shared__ int s_cnt[kUwpPix * kWarps];  // survivors of (k, warp), k-major == pixel order
-  const int tile = blockIdx.x;
-  const int job_i = tile / p.tiles_per_job;
-  const int jt = tile - job_i * p.tiles_per_job;
-  const PgdvsUwpJob& J = p.jobs[job_i];
-  const int tile_base = __ldg(p.tile_off + tile);
+  const int g = blockIdx.x / p.tiles_per_job;
+  const int jt = blockIdx.x - g * p.tiles_per_job;
+  const PgdvsUwpJob& J = p.jobs[group_member(p, g, 0)];
 
   PixelSet s;
   pixel_validity(p, J, (int64_t)jt * kUwpTile, s);
@@ -174,13 +185,13 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
   }
   if (s.valid == 0) return;
 
-  // ------------------------------------------------------------ geometry for survivors
-  const PgdvsCamera cam = p.cams[J.view];
+  // ------------------------------------------------------------ world point + colour, once
   const bool lerp = (J.same_time == 0);
   const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
   float d1[kUwpPix];
 #pragma unroll
   for (int k = 0; k < kUwpPix; ++k) d1[k] = ((s.valid >> k) & 1u) ? __ldg(J.depth1 + s.pix[k]) : 0.0f;
+  float wx[kUwpPix], wy[kUwpPix], wz[kUwpPix], cr[kUwpPix], cg[kUwpPix], cb[kUwpPix];
   // two pixels at a time: their 8 frame-2 taps are issued back to back before any is consumed
 #pragma unroll
   for (int k0 = 0; k0 < kUwpPix; k0 += 2) {
@@ -216,11 +227,7 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
           const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
           const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
           tap[kk][t] = make_float4(0.f, 0.f, 0.f, 0.f);  // zeros padding
-#ifdef PGDVS_EXP_NO_TAPS
-          if (false) {
-#else
           if (inb) {
-#endif
             const int64_t o = (int64_t)ys * p.W + xs;
             if (rgbd2 != nullptr)
               tap[kk][t] = __ldg(rgbd2 + o);
@@ -234,26 +241,25 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       const int k = k0 + kk;
-      if (!((s.valid >> k) & 1u)) continue;
       const float u = (float)s.u[k], v = (float)s.v[k];
       // rays_d = (c2w[:3,:3] @ K^-1) @ [u, v, 1]
-      float wx = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
-      float wy = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
-      float wz = J.o1[2] + (J.M1[6] * u + J.M1[7] * v + J.M1[8]) * d1[k];
-      float cr, cg, cb;
+      wx[k] = J.o1[0] + (J.M1[0] * u + J.M1[1] * v + J.M1[2]) * d1[k];
+      wy[k] = J.o1[1] + (J.M1[3] * u + J.M1[4] * v + J.M1[5]) * d1[k];
+      wz[k] = J.o1[2] + (J.M1[6] * u + J.M1[7] * v + J.M1[8]) * d1[k];
+      cr[k] = cg[k] = cb[k] = 0.0f;
+      if (!((s.valid >> k) & 1u)) continue;
       if (!lerp) {
         const float* c1 = J.rgb1 + s.pix[k] * 3;
-        cr = __ldg(c1);
-        cg = __ldg(c1 + 1);
-        cb = __ldg(c1 + 2);
+        cr[k] = __ldg(c1);
+        cg[k] = __ldg(c1 + 1);
+        cb[k] = __ldg(c1 + 2);
       } else {
-        cr = cg = cb = 0.0f;
         float dep2 = 0.0f;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          cr = __fadd_rn(cr, __fmul_rn(tap[kk][t].x, wgt[kk][t]));
-          cg = __fadd_rn(cg, __fmul_rn(tap[kk][t].y, wgt[kk][t]));
-          cb = __fadd_rn(cb, __fmul_rn(tap[kk][t].z, wgt[kk][t]));
+          cr[k] = __fadd_rn(cr[k], __fmul_rn(tap[kk][t].x, wgt[kk][t]));
+          cg[k] = __fadd_rn(cg[k], __fmul_rn(tap[kk][t].y, wgt[kk][t]));
+          cb[k] = __fadd_rn(cb[k], __fmul_rn(tap[kk][t].z, wgt[kk][t]));
           if (t == near_tap[kk]) dep2 = tap[kk][t].w;
         }
         // pcl_2 = o_2 + (R_2 @ (K_2^-1 @ [u2, v2, 1])) * depth_2
@@ -264,26 +270,31 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
         const float qx = J.o2[0] + (J.R2[0] * kx + J.R2[1] * ky + J.R2[2] * kz) * dep2;
         const float qy = J.o2[1] + (J.R2[3] * kx + J.R2[4] * ky + J.R2[5] * kz) * dep2;
         const float qz = J.o2[2] + (J.R2[6] * kx + J.R2[7] * ky + J.R2[8] * kz) * dep2;
-        wx = J.w1 * wx + J.w2 * qx;
-        wy = J.w1 * wy + J.w2 * qy;
-        wz = J.w1 * wz + J.w2 * qz;
+        wx[k] = J.w1 * wx[k] + J.w2 * qx;
+        wy[k] = J.w1 * wy[k] + J.w2 * qy;
+        wz[k] = J.w1 * wz[k] + J.w2 * qz;
       }
-      const float3 ndc = world_to_ndc(cam, wx, wy, wz);
+    }
+  }
+
+  // ------------------------------------------------------------ per member: project, file, store
+  const int n_members = group_size(p, g);
+  for (int m = 0; m < n_members; ++m) {
+    const int job_m = group_member(p, g, m);
+    const int view = p.jobs[job_m].view;
+    const PgdvsCamera cam = p.cams[view];
+    const int tile_base = __ldg(p.tile_off + (int64_t)job_m * p.tiles_per_job + jt);
+#pragma unroll
+    for (int k = 0; k < kUwpPix; ++k) {
+      if (!((s.valid >> k) & 1u)) continue;
+      const float3 ndc = world_to_ndc(cam, wx[k], wy[k], wz[k]);
       const int64_t out = (int64_t)tile_base + rank[k];
       if (FUSED) {
-        const int cell = point_cell(p.g, J.view, ndc.x, ndc.y, ndc.z);
-#ifndef PGDVS_EXP_NO_ATOMIC
+        const int cell = point_cell(p.g, view, ndc.x, ndc.y, ndc.z);
         if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
-#endif
-#ifdef PGDVS_EXP_NO_STORE
-        if (ndc.x == 12345.678f) {
-#else
-        {
-#endif
-          p.cell_of[out] = cell;
-          p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
-          p.preB[out] = make_float4(cr, cg, cb, 0.0f);
-        }
+        p.cell_of[out] = cell;
+        p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
+        p.preB[out] = make_float4(cr[k], cg[k], cb[k], 0.0f);
       }
       if (p.xyz_ndc) {
         p.xyz_ndc[out * 3 + 0] = ndc.x;
@@ -291,14 +302,14 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
         p.xyz_ndc[out * 3 + 2] = ndc.z;
       }
       if (p.rgb) {
-        p.rgb[out * 3 + 0] = cr;
-        p.rgb[out * 3 + 1] = cg;
-        p.rgb[out * 3 + 2] = cb;
+        p.rgb[out * 3 + 0] = cr[k];
+        p.rgb[out * 3 + 1] = cg[k];
+        p.rgb[out * 3 + 2] = cb[k];
       }
       if (p.xyz_world) {
-        p.xyz_world[out * 3 + 0] = wx;
-        p.xyz_world[out * 3 + 1] = wy;
-        p.xyz_world[out * 3 + 2] = wz;
+        p.xyz_world[out * 3 + 0] = wx[k];
+        p.xyz_world[out * 3 + 1] = wy[k];
+        p.xyz_world[out * 3 + 2] = wz[k];
       }
       if (p.src_pix) p.src_pix[out] = (int32_t)s.pix[k];
     }
@@ -363,12 +374,17 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
                    int W, float* xyz_ndc, float* rgb, float* xyz_world, int32_t* src_pix,
                    int64_t* first_idx, int64_t* num_points, int64_t* total_points, char* ws,
                    const UwpLayout& L, const CellGrid* grid, int* cell_count, int* cell_of, float4* preA,
-                   float4* preB, cudaStream_t stream) {
+                   float4* preB, const int32_t* group_first, const int32_t* group_members, int n_groups,
+                   cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(ws, 0, L.off_zero_end, stream);
   if (e != cudaSuccess) return (int)e;
   int* tile_off = reinterpret_cast<int*>(ws + L.off_tile_off);
+  const bool grouped = group_first != nullptr && group_members != nullptr && n_groups > 0;
+  const unsigned grid_blocks = (unsigned)((int64_t)(grouped ? n_groups : n_jobs) * L.tiles_per_job);
   if (n_jobs > 0) {
     UwpParams p = {};
+    p.group_first = grouped ? group_first : nullptr;
+    p.group_members = grouped ? group_members : nullptr;
     p.jobs = jobs;
     p.cams = cameras;
     p.n_jobs = n_jobs;
@@ -381,7 +397,7 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
     p.rgb = rgb;
     p.xyz_world = xyz_world;
     p.src_pix = src_pix;
-    k_uwp_count<<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
+    k_uwp_count<<<grid_blocks, kUwpThreads, 0, stream>>>(p);
     if (int rc = check_launch()) return rc;
     if (int rc = scan_exclusive_inplace(tile_off, L.n_scan_tiles,
                                         reinterpret_cast<unsigned long long*>(ws + L.off_state),
@@ -393,9 +409,9 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
       p.cell_of = cell_of;
       p.preA = preA;
       p.preB = preB;
-      k_uwp<true><<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
+      k_uwp<true><<<grid_blocks, kUwpThreads, 0, stream>>>(p);
     } else {
-      k_uwp<false><<<(unsigned)L.n_tiles, kUwpThreads, 0, stream>>>(p);
+      k_uwp<false><<<grid_blocks, kUwpThreads, 0, stream>>>(p);
     }
     if (int rc = check_launch()) return rc;
   }
@@ -421,8 +437,10 @@ extern "C" int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs,
                                             float* xyz_ndc, float* rgb, float* xyz_world,
                                             int32_t* src_pix, int64_t* first_idx,
                                             int64_t* num_points, int64_t* total_points,
-                                            void* workspace, size_t workspace_bytes, void* stream_) {
-  if (n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !workspace) return PGDVS_E_BADARG;
+                                            const int32_t* group_first, const int32_t* group_members,
+                                            int n_groups, void* workspace, size_t workspace_bytes,
+                                            void* stream_) {
+  if (n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !workspace || n_groups < 0) return PGDVS_E_BADARG;
   if (n_views > 0 && (!first_idx || !num_points)) return PGDVS_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;
   UwpLayout L = make_uwp_layout(n_jobs, H, W);
@@ -431,7 +449,7 @@ extern "C" int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs,
   if (n_jobs > 0 && (!jobs || !cameras || !xyz_ndc || !rgb)) return PGDVS_E_BADARG;
   return run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, xyz_world, src_pix, first_idx,
                  num_points, total_points, static_cast<char*>(workspace), L, nullptr, nullptr, nullptr,
-                 nullptr, nullptr, (cudaStream_t)stream_);
+                 nullptr, nullptr, group_first, group_members, n_groups, (cudaStream_t)stream_);
 }
 
 extern "C" int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int W, float radius,
@@ -450,9 +468,11 @@ extern "C" int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int
 extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras,
                              int n_views, int H, int W, float radius, float* xyz_ndc, float* rgb,
                              int64_t* first_idx, int64_t* num_points, int64_t* total_points,
+                             const int32_t* group_first, const int32_t* group_members, int n_groups,
                              void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !workspace || !(radius >= 0.0f) || !total_points)
+  if (n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !workspace || !(radius >= 0.0f) || !total_points ||
+      n_groups < 0)
     return PGDVS_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;
   const int64_t cap = (int64_t)n_jobs * H * W;
@@ -473,7 +493,7 @@ extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCam
                    num_points, total_points, ws + T.total, U, &g,
                    reinterpret_cast<int*>(ws + B.off_cells), reinterpret_cast<int*>(ws + B.off_cell_of),
                    reinterpret_cast<float4*>(ws + T.off_preA), reinterpret_cast<float4*>(ws + T.off_preB),
-                   stream);
+                   group_first, group_members, n_groups, stream);
   if (rc) return rc;
   return bin_scan_fill_fused(ws, B, T, cap, total_points, stream);
 }

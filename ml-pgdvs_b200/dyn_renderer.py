@@ -104,6 +104,15 @@ class SourcePair:
             self.w1 = (t2 - tt) / (t2 - t1)  # pgdvs_renderer_dyn.py:385-386 (fp32 like torch)
             self.w2 = (tt - t1) / (t2 - t1)
 
+    def group_key(self):
+        """Everything of a job except the target camera / view index."""
+        ptr = lambda t: t.data_ptr() if t is not None else 0  # noqa: E731
+        return (ptr(self.depth_1), ptr(self.rgb_1), ptr(self.mask_1), ptr(self.flow_12), ptr(self.occ_12),
+                ptr(self.depth_2), ptr(self.rgb_2), ptr(self.keep), self.M1.tobytes(),
+                np.asarray(self.o1, np.float32).tobytes(), self.K2inv.tobytes(),
+                np.asarray(self.R2, np.float32).tobytes(), np.asarray(self.o2, np.float32).tobytes(),
+                float(self.w1), float(self.w2), self.same_time)
+
     def to_struct(self) -> _cabi.PgdvsUwpJob:
         j = _cabi.PgdvsUwpJob()
         j.depth1, j.rgb1, j.mask1 = self.depth_1.data_ptr(), self.rgb_1.data_ptr(), self.mask_1.data_ptr()
@@ -136,7 +145,7 @@ class PreparedViews:
     can be re-run with zero host<->device traffic."""
 
     def __init__(self, pairs: Sequence[SourcePair], cams_p3d: Sequence, H: int, W: int, device,
-                 pack_frames: bool = True):
+                 pack_frames: bool = True, group_jobs: bool = True):
         self.n_jobs, self.n_views, self.H, self.W = len(pairs), len(cams_p3d), H, W
         self.device = torch.device(device)
         assert all(pairs[i].view <= pairs[i + 1].view for i in range(self.n_jobs - 1)), \
@@ -173,11 +182,32 @@ class PreparedViews:
                         p.rgbd_2 = self.rgbd[uniq[(p.rgb_2.data_ptr(), p.depth_2.data_ptr())][0]]
                 self.frames_dev = _upload_structs(packs, _cabi.PgdvsFramePack, device)
                 self.n_frames = len(uniq)
+        # job groups: jobs that differ only in the target camera share validity, gathers and the
+        # world point (e.g. the 12 cameras per time step of the NVIDIA benchmark)
+        self.n_groups = 0
+        self.group_first_dev = self.group_members_dev = None
+        if group_jobs and self.n_jobs > 1:
+            groups = {}
+            for i, p in enumerate(pairs):
+                groups.setdefault(p.group_key(), []).append(i)
+            if len(groups) < self.n_jobs:
+                first, members = [0], []
+                for idxs in groups.values():
+                    members += idxs
+                    first.append(len(members))
+                self.n_groups = len(groups)
+                self.group_first_dev = torch.tensor(first, dtype=torch.int32).to(device)
+                self.group_members_dev = torch.tensor(members, dtype=torch.int32).to(device)
         self.jobs_dev = _upload_structs([p.to_struct() for p in pairs], _cabi.PgdvsUwpJob, device)
         self.cams_dev = _upload_structs(cam_structs, _cabi.PgdvsCamera, device)
         self._keepalive = list(pairs)
         self.h2d_bytes = self.jobs_dev.numel() + self.cams_dev.numel() + \
             (self.frames_dev.numel() if self.frames_dev is not None else 0)
+
+    def group_args(self):
+        if self.n_groups:
+            return self.group_first_dev.data_ptr(), self.group_members_dev.data_ptr(), self.n_groups
+        return None, None, 0
 
     def pack_frames(self):
         """(r,g,b) + depth -> (r,g,b,depth) planes for the distinct frame-2 images (1 launch)."""
@@ -188,10 +218,11 @@ class PreparedViews:
             ops.LAUNCHES["count"] += 1
 
 
-def prepare_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, device) -> PreparedViews:
+def prepare_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, device,
+                  group_jobs: bool = True) -> PreparedViews:
     """tgt_cams: per view (K44, c2w44) in OpenCV convention (flat_cam[2:18], flat_cam[18:34])."""
     cams = [opencv_to_p3d_camera(K, c2w, H, W) for (K, c2w) in tgt_cams]
-    return PreparedViews(pairs, cams, H, W, device)
+    return PreparedViews(pairs, cams, H, W, device, group_jobs=group_jobs)
 
 
 def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=None,
@@ -220,7 +251,7 @@ def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=
             prep.jobs_dev.data_ptr(), n_jobs, prep.cams_dev.data_ptr(), n_views, H, W, xyz_ndc.data_ptr(),
             rgb.data_ptr(), xyz_world.data_ptr() if want_world else None,
             src_pix.data_ptr() if want_src_pix else None, first_idx.data_ptr(), num_points.data_ptr(),
-            total.data_ptr(), ops._aligned_ptr(ws), nbytes.value, ops._stream_ptr(device)),
+            total.data_ptr(), *prep.group_args(), ops._aligned_ptr(ws), nbytes.value, ops._stream_ptr(device)),
             "pgdvs_unproject_warp_project")
     ops.LAUNCHES["count"] += 4  # k_uwp_count, k_scan, k_uwp, k_uwp_finalize
     return {"xyz_ndc": xyz_ndc, "rgb": rgb, "xyz_world": xyz_world, "src_pix": src_pix,
@@ -267,8 +298,8 @@ def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int
         _cabi.check(L.pgdvs_uwp_bin(
             prep.jobs_dev.data_ptr(), n_jobs, prep.cams_dev.data_ptr(), n_views, H, W, float(radius),
             xyz_ndc.data_ptr() if xyz_ndc is not None else None, rgb.data_ptr() if rgb is not None else None,
-            first_idx.data_ptr(), num_points.data_ptr(), total.data_ptr(), ws_ptr, nbytes.value,
-            ops._stream_ptr(dev)), "pgdvs_uwp_bin")
+            first_idx.data_ptr(), num_points.data_ptr(), total.data_ptr(), *prep.group_args(), ws_ptr,
+            nbytes.value, ops._stream_ptr(dev)), "pgdvs_uwp_bin")
     ops.LAUNCHES["count"] += 6  # k_uwp_count, k_scan, k_uwp, k_uwp_finalize, k_scan, k_fill_pre
     out = ops.rasterize_workspace(ws_ptr, nbytes.value, dev, n_views, cap, H, W, K, float(radius), False, 3,
                                   ops._COMPOSITORS[compositor], float(radius) * float(radius),

@@ -176,6 +176,33 @@ def test_fused_pipeline_equals_staged(name, views):
     assert np.array_equal(a["dists"].cpu().numpy(), ref_frags[2])
 
 
+def test_job_groups_do_not_change_results():
+    """24 views = 2 time steps x 12 cameras: the jobs of a time step form a group (shared source
+    pair, different target camera).  Grouped and ungrouped runs must be bit-identical."""
+    from pgdvs_b200 import synthetic
+    from pgdvs_b200.dyn_renderer import prepare_views, render_prepared
+    dev = _dev()
+    wl = synthetic.make_workload("c2_nvidia_seq", dev, n_views=24, mask_mode="ellipse")
+    pairs, cams = wl.jobs(range(24))
+    a_prep = prepare_views(pairs, cams, wl.H, wl.W, dev, group_jobs=True)
+    b_prep = prepare_views(pairs, cams, wl.H, wl.W, dev, group_jobs=False)
+    assert a_prep.n_groups == 4 and b_prep.n_groups == 0  # 2 steps x (fwd, bwd) pairs
+    kw = dict(radius=wl.radius, points_per_pixel=wl.K, compositor="norm", static_rgb=wl.static_rgb,
+              return_fragments=True, return_cloud=True)
+    a = render_prepared(a_prep, **kw)
+    b = render_prepared(b_prep, **kw)
+    c = render_prepared(a_prep, fused=False, **{k: v for k, v in kw.items() if k != "return_cloud"})
+    torch.cuda.synchronize()
+    P = int(a["cloud"]["total"])
+    assert P == int(b["cloud"]["total"]) == int(c["cloud"]["total"]) and P > 0
+    for x in (b, c):
+        assert torch.equal(a["first_idx"], x["first_idx"]) and torch.equal(a["num_points"], x["num_points"])
+        assert torch.equal(a["cloud"]["xyz_ndc"][:P], x["cloud"]["xyz_ndc"][:P])
+        assert torch.equal(a["cloud"]["rgb"][:P], x["cloud"]["rgb"][:P])
+        for k in ("idx", "zbuf", "dists", "image", "mask"):
+            assert torch.equal(a[k], x[k]), k
+
+
 @pytest.mark.parametrize("mode,fn", [("alpha", "alpha_composite"), ("norm", "norm_weighted_sum"), ("wsum", "weighted_sum")])
 def test_standalone_compositors(mode, fn):
     import pgdvs_b200
