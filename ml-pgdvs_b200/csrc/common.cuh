@@ -72,12 +72,17 @@ struct BinLayout {
   size_t off_ticket;  // int32 [4]           scan ticket counter (+pad)
   size_t off_zero_end;  // everything in [0, off_zero_end) is zeroed before each binning
   size_t off_cell_of; // int32  [P]          cell of every packed point (-1 = never rasterized)
-  size_t off_recA;    // float4 [P]          (x_ndc, y_ndc, z, packed idx as int bits)
-  size_t off_recB;    // float4 [P]          features (C<=4) or (f0,f1,f2,radius)
+  size_t off_recA;    // float4 [P] stride kRecStride: (x_ndc, y_ndc, z, packed idx as int bits)
+  size_t off_recB;    // float4 [P] stride kRecStride: features (C<=4) or (f0,f1,f2,radius)
   size_t total;
 };
 
 constexpr int kScanTile = 4096;  // ints per scan tile (1024 threads x int4)
+#ifndef PGDVS_REC_STRIDE
+#define PGDVS_REC_STRIDE 2
+#endif
+// 2: recA/recB interleaved as one 32-byte record per point; 1: two separate float4 arrays
+constexpr int kRecStride = PGDVS_REC_STRIDE;
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -104,10 +109,11 @@ inline BinLayout make_bin_layout(int N, int H, int W, int64_t P, float radius_ma
   L.off_zero_end = o;
   L.off_cell_of = o;
   o = align256(o + sizeof(int32_t) * (size_t)(P > 0 ? P : 1));
+  // records of one point sit next to each other (one full 32 B sector per point): the fill
+  // pass's scatter then never leaves half-written sectors behind
   L.off_recA = o;
-  o = align256(o + sizeof(float4) * (size_t)(P > 0 ? P : 1));
-  L.off_recB = o;
-  o = align256(o + sizeof(float4) * (size_t)(P > 0 ? P : 1));
+  L.off_recB = o + (kRecStride == 2 ? sizeof(float4) : align256(sizeof(float4) * (size_t)(P > 0 ? P : 1)));
+  o = align256(o + 2 * align256(sizeof(float4) * (size_t)(P > 0 ? P : 1)));
   L.total = o;
   return L;
 }

@@ -42,7 +42,7 @@ __device__ __forceinline__ bool cand_less(float z, int idx, float ze, int se,
                                           const float4* __restrict__ recA) {
   bool lt = z < ze;
   if (z == ze) {  // exact fp32 z tie -> smaller packed index first
-    lt = (se < 0) ? true : (idx < __float_as_int(recA[se].w));
+    lt = (se < 0) ? true : (idx < __float_as_int(recA[kRecStride * se].w));
   }
   return lt;
 }
@@ -116,7 +116,7 @@ __device__ __forceinline__ bool hit_test(const PixelCtx& c, const float4 a,
   const float d2 = dist2_rn(a.x, a.y, c.xf, c.yf);
   float r2 = c.r2;
   if (PPR) {
-    const float r = __ldg(&recB[j].w);
+    const float r = __ldg(&recB[kRecStride * j].w);
     r2 = __fmul_rn(r, r);
   }
   return d2 < r2;
@@ -134,7 +134,7 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
     const int s = __ldg(p.cell_end + cell0 - 1);
     const int e = __ldg(p.cell_end + cell0 + span - 1);
     for (int j = s; j < e; ++j) {
-      const float4 a = __ldg(p.recA + j);
+      const float4 a = __ldg(p.recA + kRecStride * j);
       if (hit_test<PPR>(c, a, p.recB, j)) q.insert_exact(a.z, __float_as_int(a.w), j, p.recA);
     }
   }
@@ -235,12 +235,12 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
     const int tmax = __reduce_max_sync(full, total);  // warp-uniform trip count
     // software-pipelined: the record of iteration t+1 is in flight while t is processed
     int j = (0 < c0 ? s0 : (0 < c01 ? o1 : o2));
-    float4 a = (total > 0) ? __ldg(recA + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a = (total > 0) ? __ldg(recA + kRecStride * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = 0; t < tmax; ++t) {
       const int tn = t + 1;
       const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
       float4 an = a;
-      if (tn < total) an = __ldg(recA + jn);
+      if (tn < total) an = __ldg(recA + kRecStride * jn);
       consider(t < total, a, j);
       a = an;
       j = jn;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
       for (int i = 0; i < lmax; ++i) {
         const bool live = i < len;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) a = __ldg(recA + s + i);
+        if (live) a = __ldg(recA + kRecStride * (s + i));
         consider(live, a, s + i);
       }
     }
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
         w[k] = 0.f;
         const int sl = (k < K) ? q.s[k] : -1;
         if (sl >= 0) {
-          const float4 a = __ldg(recA + sl);
+          const float4 a = __ldg(recA + kRecStride * sl);
           o_d[kk] = dist2_rn(a.x, a.y, c.xf, c.yf);
           o_idx[kk] = __float_as_int(a.w);
           o_z[kk] = a.z;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
     if (k < K && q.s[k] >= 0) {
-      const float4 f4 = __ldg(recB + q.s[k]);
+      const float4 f4 = __ldg(recB + kRecStride * q.s[k]);
       float wk = w[k];
       if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
         wk = __fmul_rn(wk, inv_t);
