@@ -1,4 +1,4 @@
-// Tiled rasterize-and-composite over the cell-sorted records produced by bin.cu.
+// Tiled rasterize-and-composite over the cell-sorted records produced by bin.cu / uwp.cu.
 //
 // Replaces pytorch3d's RasterizePointsNaiveCudaKernel (O(N*H*W*P), reached from
 // pgdvs_renderer_dyn.py:690-717 with bin_size=0), PointsRenderer's weight computation,
@@ -7,20 +7,28 @@
 //   * each thread owns one pixel and keeps its K nearest hits as a z-sorted list of
 //     (z, record slot) pairs in registers;
 //   * candidates are only the records filed under cells within `halo` of the pixel — for
-//     every window row that is one contiguous run of the cell-sorted arrays;
+//     every window row that is one contiguous run of the cell-sorted record array;
 //   * the hit test reproduces the reference arithmetic bit for bit (dist2_rn, strict <);
 //   * the common-case insertion is a branch-free compare-exchange chain on z alone; exact
 //     fp32 z ties (which the CPU rasterizer's (z, idx, dist2) priority queue orders by the
 //     smaller packed index) are DETECTED in the fast path and the few affected pixels are
 //     redone by a tie-aware slow path, so idx/zbuf/dists stay deterministic and bit-exact.
+//
+// Two kernels share that logic:
+//   k_raster_tile  (3x3 windows, scalar radius — every PGDVS configuration with r_px < 1.5):
+//                  a 32x8-pixel CTA fetches the 10 row runs its pixels can touch into shared
+//                  memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier; the runs ARE
+//                  contiguous because records are sorted by cell), then every lookup of the
+//                  candidate loop and of the epilogue is a shared-memory read.
+//   k_raster_cells (any halo, per-point radii): candidates are read through L1.
 #include "common.cuh"
 
 namespace pgdvs {
 
 struct RasterParams {
   const int* cell_end;  // per-cell END offsets; start(c) = cell_end[c - 1] (cell_end[-1] == 0)
-  const float4* recA;
-  const float4* recB;
+  const float4* recA;   // records, stride kRecStride float4: (x_ndc, y_ndc, z, packed idx)
+  const float4* recB;   //                                     (f0, f1, f2, f3 | radius)
   int N, H, W, K, C, halo, GW, GH;
   NdcAxis ax, ay;
   float r2;          // scalar radius^2 (fp32 r*r) or < 0: per-point radius in recB.w
@@ -33,9 +41,11 @@ struct RasterParams {
   float* dists;
   float* image;
   float* mask;
+  int smem_records;  // capacity of the staging buffer of k_raster_tile, in records
 };
 
 constexpr float kInf = __builtin_huge_valf();
+static_assert(kRecStride == 2, "the rasterizer expects interleaved 32-byte records (A at 2j, B at 2j+1)");
 
 // candidate (z, idx) strictly before list element (ze, slot se)?  Total order (z, idx).
 __device__ __forceinline__ bool cand_less(float z, int idx, float ze, int se,
@@ -122,7 +132,8 @@ __device__ __forceinline__ bool hit_test(const PixelCtx& c, const float4 a,
   return d2 < r2;
 }
 
-// Tie-aware rescan of one pixel (rare).  Kept out of line so the fast path stays small.
+// Tie-aware rescan of one pixel over the GLOBAL records (rare).  Out of line so that the fast
+// path stays small; returns global record slots.
 template <int KP, bool PPR>
 __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx& c, int n, int x,
                                           int y, float* zout, int* sout) {
@@ -145,133 +156,14 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
   }
 }
 
-#ifndef PGDVS_RASTER_MINBLOCKS
-#define PGDVS_RASTER_MINBLOCKS 1
-#endif
-#ifndef PGDVS_RASTER_QUEUE
-#define PGDVS_RASTER_QUEUE 16
-#endif
-constexpr int kQueueCap = PGDVS_RASTER_QUEUE;  // hits buffered per pixel between two drains
-
-// Two-phase pixel loop.  Testing a candidate is cheap (~15 instructions) but inserting a hit
-// into the z-sorted list is a KP-slot compare-exchange chain, and in SIMT a chain costs the same
-// whether 3 or 32 lanes need it.  So hits are first appended to a lane-private column of a
-// shared-memory queue (phase 1, no chain in the loop); then the warp drains the queues
-// (phase 2): the chain now runs max_lanes(#hits) times with most lanes active instead of once
-// per candidate iteration with ~40 % of the lanes.  Columns are private to a thread, so no
-// synchronisation is needed; a full column triggers a drain for the whole warp.
-template <int KP, bool PPR>
-__global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(const __grid_constant__ RasterParams p) {
-  // Measured on B200 (C2 workload): the queue's own overhead (vote + smem round trip per
-  // candidate) outweighs the better chain utilisation — 3.34 ms queued vs 2.80 ms direct — so the
-  // direct path is the default; the queued path is kept behind a build flag for dense / large-K
-  // experiments.
-#ifdef PGDVS_RASTER_USE_QUEUE
-  constexpr bool QUEUED = (KP >= 4) && (KP <= 64);
-#else
-  constexpr bool QUEUED = false;
-#endif
-  __shared__ float s_qz[QUEUED ? kQueueCap : 1][256];
-  __shared__ int s_qs[QUEUED ? kQueueCap : 1][256];
-  const unsigned full = 0xffffffffu;
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = blockIdx.y * 8 + threadIdx.y;
-  const int n = blockIdx.z;
-  // out-of-image lanes stay alive (warp votes below) but scan nothing and store nothing
-  const bool inside = (x < p.W) && (y < p.H);
-  PixelCtx c;
-  c.xf = pixel_center_ndc(p.ax, x);
-  c.yf = pixel_center_ndc(p.ay, y);
-  c.r2 = p.r2;
-  const float4* __restrict__ recA = p.recA;
-  const float4* __restrict__ recB = p.recB;
-
-  KList<KP> q;
-  q.init();
-  bool tie = false;
-  int cnt = 0;
-
-  auto drain = [&]() {
-    const int nmax = __reduce_max_sync(full, cnt);
-    for (int i = 0; i < nmax; ++i) {
-      if (i < cnt) tie |= q.insert_fast(s_qz[i][tid], s_qs[i][tid]);
-    }
-    cnt = 0;
-  };
-  // phase-1 body for one candidate (record a at slot j)
-  auto consider = [&](bool live, const float4& a, int j) {
-    bool hit = live && hit_test<PPR>(c, a, recB, j);
-    if (QUEUED) {
-      if (hit) {
-        // early reject against the current K-th nearest; an exact tie is left to the slow path
-        tie |= (a.z == q.z[KP - 1]);
-        hit = a.z < q.z[KP - 1];
-      }
-      if (hit) {
-        s_qz[cnt][tid] = a.z;
-        s_qs[cnt][tid] = j;
-        ++cnt;
-      }
-      if (__any_sync(full, cnt == kQueueCap)) drain();
-    } else {
-      if (hit) tie |= q.insert_fast(a.z, j);
-    }
-  };
-
-  const int span = 2 * p.halo + 1;
-  // cs[c] = start of cell (x + c) of the first window row = cell_end[... - 1]
-  const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + (inside ? y : 0)) * p.GW + (inside ? x : 0) - 1;
-  if (p.halo == 1) {
-    // 3x3 cell window (every PGDVS configuration with r_px < 1.5): the three row runs are
-    // walked by ONE flattened loop so that lanes with uneven rows do not wait for each other
-    // three times.
-    const int s0 = __ldg(cs), e0 = __ldg(cs + 3);
-    const int s1 = __ldg(cs + p.GW), e1 = __ldg(cs + p.GW + 3);
-    const int s2 = __ldg(cs + 2 * p.GW), e2 = __ldg(cs + 2 * p.GW + 3);
-    const int c0 = e0 - s0, c01 = c0 + (e1 - s1);
-    const int total = inside ? c01 + (e2 - s2) : 0;
-    const int o1 = s1 - c0, o2 = s2 - c01;
-    const int tmax = __reduce_max_sync(full, total);  // warp-uniform trip count
-    // software-pipelined: the record of iteration t+1 is in flight while t is processed
-    int j = (0 < c0 ? s0 : (0 < c01 ? o1 : o2));
-    float4 a = (total > 0) ? __ldg(recA + kRecStride * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < tmax; ++t) {
-      const int tn = t + 1;
-      const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
-      float4 an = a;
-      if (tn < total) an = __ldg(recA + kRecStride * jn);
-      consider(t < total, a, j);
-      a = an;
-      j = jn;
-    }
-  } else {
-    for (int ry = 0; ry < span; ++ry) {
-      const int s = __ldg(cs + (int64_t)ry * p.GW);
-      const int len = inside ? __ldg(cs + (int64_t)ry * p.GW + span) - s : 0;
-      const int lmax = __reduce_max_sync(full, len);
-      for (int i = 0; i < lmax; ++i) {
-        const bool live = i < len;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) a = __ldg(recA + kRecStride * (s + i));
-        consider(live, a, s + i);
-      }
-    }
-  }
-  if (QUEUED) drain();
-  if (!inside) return;
-  if (tie || q.has_adjacent_tie()) {
-    float zt[KP];
-    int st[KP];
-    rescan_exact<KP, PPR>(p, c, n, x, y, zt, st);
-#pragma unroll
-    for (int i = 0; i < KP; ++i) {
-      q.z[i] = zt[i];
-      q.s[i] = st[i];
-    }
-  }
-
-  // ---------------------------------------------------------------- epilogue
+// ---------------------------------------------------------------------------------------
+// Epilogue shared by both kernels.  `rec` points at the records the slots of `q` refer to
+// (generic pointer: global array or the CTA's shared-memory staging buffer).
+// ---------------------------------------------------------------------------------------
+template <int KP>
+__device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const KList<KP>& q,
+                                               const PixelCtx& c, int n, int x, int y,
+                                               const float4* rec) {
   const int K = p.K;
   const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
   const int mode = p.compositor;
@@ -293,7 +185,7 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
         w[k] = 0.f;
         const int sl = (k < K) ? q.s[k] : -1;
         if (sl >= 0) {
-          const float4 a = __ldg(recA + kRecStride * sl);
+          const float4 a = rec[kRecStride * sl];
           o_d[kk] = dist2_rn(a.x, a.y, c.xf, c.yf);
           o_idx[kk] = __float_as_int(a.w);
           o_z[kk] = a.z;
@@ -333,7 +225,7 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
     if (k < K && q.s[k] >= 0) {
-      const float4 f4 = __ldg(recB + kRecStride * q.s[k]);
+      const float4 f4 = rec[kRecStride * q.s[k] + (kRecStride == 2 ? 1 : 0)];
       float wk = w[k];
       if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
         wk = __fmul_rn(wk, inv_t);
@@ -365,14 +257,235 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
   }
 }
 
+#ifndef PGDVS_RASTER_MINBLOCKS
+#define PGDVS_RASTER_MINBLOCKS 1
+#endif
+
+// ---------------------------------------------------------------------------------------
+// Generic kernel: any halo, optional per-point radii, candidates read through L1.
+// ---------------------------------------------------------------------------------------
+template <int KP, bool PPR>
+__global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(const __grid_constant__ RasterParams p) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = blockIdx.y * 8 + threadIdx.y;
+  const int n = blockIdx.z;
+  if (x >= p.W || y >= p.H) return;
+  PixelCtx c;
+  c.xf = pixel_center_ndc(p.ax, x);
+  c.yf = pixel_center_ndc(p.ay, y);
+  c.r2 = p.r2;
+  const float4* __restrict__ recA = p.recA;
+  const float4* __restrict__ recB = p.recB;
+
+  KList<KP> q;
+  q.init();
+  bool tie = false;
+  const int span = 2 * p.halo + 1;
+  // cs[c] = start of cell (x + c) of the first window row = cell_end[... - 1]
+  const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+  for (int ry = 0; ry < span; ++ry) {
+    const int s = __ldg(cs + (int64_t)ry * p.GW);
+    const int e = __ldg(cs + (int64_t)ry * p.GW + span);
+    for (int j = s; j < e; ++j) {
+      const float4 a = __ldg(recA + kRecStride * j);
+      if (hit_test<PPR>(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
+    }
+  }
+  if (tie || q.has_adjacent_tie()) {
+    float zt[KP];
+    int st[KP];
+    rescan_exact<KP, PPR>(p, c, n, x, y, zt, st);
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      q.z[i] = zt[i];
+      q.s[i] = st[i];
+    }
+  }
+  pixel_epilogue<KP>(p, q, c, n, x, y, recA);
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA-staged tile kernel: halo == 1 (3x3 cell windows), scalar radius.
+// ---------------------------------------------------------------------------------------
+constexpr int kTileW = 32, kTileH = 8, kTileRows = kTileH + 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
 template <int KP>
-static int launch_raster(const RasterParams& p, cudaStream_t stream) {
+__global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_raster_tile(const __grid_constant__ RasterParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* s_rec = reinterpret_cast<float4*>(smem_raw);  // staged records (kRecStride float4 each)
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_delta[kTileRows];  // smem record index = global record index + s_delta[row]
+  __shared__ int s_staged;            // 1: the tile's runs fit and are being copied
+
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int n = blockIdx.z;
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+
+  // ---- warp 0: size the 10 row runs, decide, arm the barrier, issue the bulk copies
+  if (tid == 0) {
+    // one arrival (the expect_tx below); the copies complete the transaction count
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    const int lane = threadIdx.x;
+    // extended-grid row (y0 + lane) holds image row y0 + lane - 1; cells x0 .. x0+33 (clamped)
+    const int row = y0 + lane;
+    int gs = 0, ge = 0;
+    if (lane < kTileRows && row < p.GH) {
+      const int64_t rb = ((int64_t)n * p.GH + row) * p.GW;
+      const int xe = min(x0 + kTileW + 1, p.GW - 1);
+      gs = __ldg(p.cell_end + rb + x0 - 1);
+      ge = __ldg(p.cell_end + rb + xe);
+    }
+    const int len = ge - gs;
+    int inc = len;  // inclusive prefix over the rows -> smem offsets
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, kTileRows - 1);
+    const bool fits = total <= p.smem_records;
+    if (lane < kTileRows) s_delta[lane] = fits ? (inc - len) - gs : 0;
+    if (lane == 0) {
+      s_staged = fits ? 1 : 0;
+      if (fits) {
+        const uint32_t bytes = (uint32_t)total * (uint32_t)(kRecStride * sizeof(float4));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes)
+                     : "memory");
+      }
+    }
+    __syncwarp();
+    if (fits && lane < kTileRows && len > 0) {
+      const float4* src = p.recA + (int64_t)kRecStride * gs;
+      float4* dst = s_rec + (int64_t)kRecStride * (inc - len);
+      const uint32_t bytes = (uint32_t)len * (uint32_t)(kRecStride * sizeof(float4));
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(dst)),
+          "l"(src), "r"(bytes), "r"(smem_u32(&s_bar))
+          : "memory");
+    }
+  }
+
+  // ---- every thread: its pixel constants and window runs (overlaps the copies)
+  const bool inside = (x < p.W) && (y < p.H);
+  PixelCtx c;
+  c.xf = pixel_center_ndc(p.ax, x);
+  c.yf = pixel_center_ndc(p.ay, y);
+  c.r2 = p.r2;
+  int s0 = 0, s1 = 0, s2 = 0, c0 = 0, c01 = 0, total = 0;
+  if (inside) {
+    const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+    s0 = __ldg(cs);
+    const int e0 = __ldg(cs + 3);
+    s1 = __ldg(cs + p.GW);
+    const int e1 = __ldg(cs + p.GW + 3);
+    s2 = __ldg(cs + 2 * p.GW);
+    const int e2 = __ldg(cs + 2 * p.GW + 3);
+    c0 = e0 - s0;
+    c01 = c0 + (e1 - s1);
+    total = c01 + (e2 - s2);
+  }
+  __syncthreads();  // s_staged / s_delta visible
+  const bool staged = s_staged != 0;
+  const float4* rec = p.recA;  // generic pointer to the records the slots refer to
+  if (staged) {
+    // wait for the bulk copies (phase 0 of the barrier)
+    const uint32_t bar = smem_u32(&s_bar);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, P1;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+    rec = s_rec;
+    const int ly = threadIdx.y;
+    s0 += s_delta[ly];
+    s1 += s_delta[ly + 1];
+    s2 += s_delta[ly + 2];
+  }
+
+  KList<KP> q;
+  q.init();
+  bool tie = false;
+  {
+    // the three row runs are walked by ONE flattened loop so that lanes with uneven rows do not
+    // wait for each other three times
+    const int o1 = s1 - c0, o2 = s2 - c01;
+    if (staged) {
+      for (int t = 0; t < total; ++t) {
+        const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
+        const float4 a = s_rec[kRecStride * j];
+        if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+      }
+    } else {
+      // software-pipelined global reads: record t+1 is in flight while t is processed
+      int j = (0 < c0 ? s0 : (0 < c01 ? o1 : o2));
+      float4 a = (total > 0) ? __ldg(p.recA + kRecStride * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int t = 0; t < total; ++t) {
+        const int tn = t + 1;
+        const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
+        float4 an = a;
+        if (tn < total) an = __ldg(p.recA + kRecStride * jn);
+        if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+        a = an;
+        j = jn;
+      }
+    }
+  }
+  if (!inside) return;
+  if (tie || q.has_adjacent_tie()) {
+    float zt[KP];
+    int st[KP];
+    rescan_exact<KP, false>(p, c, n, x, y, zt, st);
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      q.z[i] = zt[i];
+      q.s[i] = st[i];
+    }
+    rec = p.recA;  // the rescan returns global slots
+  }
+  pixel_epilogue<KP>(p, q, c, n, x, y, rec);
+}
+
+#ifndef PGDVS_RASTER_SMEM_BYTES
+#define PGDVS_RASTER_SMEM_BYTES (40 * 1024)
+#endif
+
+template <int KP>
+static int launch_raster(RasterParams& p, cudaStream_t stream) {
   dim3 block(32, 8);
   dim3 grid((p.W + 31) / 32, (p.H + 7) / 8, p.N);
-  if (p.r2 < 0.0f)
+  if (p.r2 < 0.0f) {
     k_raster_cells<KP, true><<<grid, block, 0, stream>>>(p);
-  else
+  } else if (p.halo == 1 && kRecStride == 2 && KP <= 32) {
+#ifndef PGDVS_RASTER_NO_TMA
+    const int smem = PGDVS_RASTER_SMEM_BYTES;
+    p.smem_records = smem / (int)(kRecStride * sizeof(float4));
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_raster_tile<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    k_raster_tile<KP><<<grid, block, smem, stream>>>(p);
+#else
     k_raster_cells<KP, false><<<grid, block, 0, stream>>>(p);
+#endif
+  } else {
+    k_raster_cells<KP, false><<<grid, block, 0, stream>>>(p);
+  }
   return check_launch();
 }
 
@@ -428,6 +541,7 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   p.dists = dists;
   p.image = image;
   p.mask = mask;
+  p.smem_records = 0;
 
   if (K <= 1) return launch_raster<1>(p, stream);
   if (K <= 2) return launch_raster<2>(p, stream);

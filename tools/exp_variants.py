@@ -11,14 +11,12 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 OUT = ROOT / "exp_libs"
 VARIANTS = {
-    "base": [],
-    "uwp_mb4": ["-DPGDVS_UWP_MINBLOCKS=4"],
-    "uwp_mb5": ["-DPGDVS_UWP_MINBLOCKS=5"],
+    "sort_row": [],
+    "nosort_row": ["-DPGDVS_RASTER_NO_SORT"],
+    "nosort_8x4": ["-DPGDVS_RASTER_NO_SORT", "-DPGDVS_RASTER_WARP_8X4"],
+    "sort_8x4": ["-DPGDVS_RASTER_WARP_8X4"],
     "fill_u1": ["-DPGDVS_FILL_UNROLL=1"],
     "fill_u2": ["-DPGDVS_FILL_UNROLL=2"],
-    "fill_u8": ["-DPGDVS_FILL_UNROLL=8"],
-    "ras_mb5": ["-DPGDVS_RASTER_MINBLOCKS=5"],
-    "ras_mb6": ["-DPGDVS_RASTER_MINBLOCKS=6"],
 }
 SRCS = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu"]
 
@@ -61,7 +59,7 @@ def run():
         L = ctypes.CDLL(str(OUT / f"lib_{name}.so"))
         L.pgdvs_uwp_bin_workspace_bytes.argtypes = [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.POINTER(ctypes.c_size_t)]
         L.pgdvs_uwp_bin.argtypes = [V, ctypes.c_int, V, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                    ctypes.c_float] + [V] * 6 + [ctypes.c_size_t, V]
+                                    ctypes.c_float] + [V] * 5 + [V, V, ctypes.c_int] + [V, ctypes.c_size_t, V]
         L.pgdvs_rasterize_composite.argtypes = [V, ctypes.c_size_t, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_float, V, V, V, V, V, V, V, V]
@@ -73,7 +71,8 @@ def run():
 
         def uwp():
             rc = L.pgdvs_uwp_bin(prep.jobs_dev.data_ptr(), n_jobs, prep.cams_dev.data_ptr(), n_views, H, W, wl.radius,
-                                 None, None, first.data_ptr(), num.data_ptr(), total.data_ptr(), wp, nb.value, st)
+                                 None, None, first.data_ptr(), num.data_ptr(), total.data_ptr(), *prep.group_args(),
+                                 wp, nb.value, st)
             assert rc == 0, rc
 
         def ras(frag=True):
