@@ -324,7 +324,51 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const int n = blockIdx.z;
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+#ifndef PGDVS_RASTER_NO_SORT
+  // balance the warps: hand the tile's pixels to threads in order of their candidate count
+  // (counting sort in shared memory) so that the lanes of a warp walk runs of similar length
+  // (measured on C2: 2.64 -> 2.39 ms compute, +0.1 ms for the now scattered fragment stores)
+  {
+    __shared__ int s_hist[64];
+    __shared__ int s_max;
+    __shared__ unsigned char s_perm[256];
+    int work = 0;
+    if (x < p.W && y < p.H) {
+      const int* __restrict__ c0p = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+#pragma unroll
+      for (int ry = 0; ry < 3; ++ry) work += __ldg(c0p + ry * p.GW + 3) - __ldg(c0p + ry * p.GW);
+    }
+    if (tid < 64) s_hist[tid] = 0;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, work);
+    if ((tid & 31) == 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int width = s_max / 64 + 1;
+    const int bin = 63 - work / width;  // heaviest pixels first
+    const int my_rank = atomicAdd(&s_hist[bin], 1);
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 64 bins by one warp (2 per lane)
+      const int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1];
+      int inc = a0 + a1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (tid >= d) inc += o;
+      }
+      s_hist[2 * tid] = inc - a0 - a1;
+      s_hist[2 * tid + 1] = inc - a1;
+    }
+    __syncthreads();
+    s_perm[s_hist[bin] + my_rank] = (unsigned char)tid;
+    __syncthreads();
+    const int mine = s_perm[tid];
+    x = x0 + (mine & 31);
+    y = y0 + (mine >> 5);
+  }
+#endif
+  const int ly = y - y0;  // local row of this thread's pixel
 
   // ---- warp 0: size the 10 row runs, decide, arm the barrier, issue the bulk copies
   if (tid == 0) {
@@ -411,7 +455,6 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
           : "memory");
     }
     rec = s_rec;
-    const int ly = threadIdx.y;
     s0 += s_delta[ly];
     s1 += s_delta[ly + 1];
     s2 += s_delta[ly + 2];

@@ -11,12 +11,11 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 OUT = ROOT / "exp_libs"
 VARIANTS = {
-    "sort_row": [],
-    "nosort_row": ["-DPGDVS_RASTER_NO_SORT"],
-    "nosort_8x4": ["-DPGDVS_RASTER_NO_SORT", "-DPGDVS_RASTER_WARP_8X4"],
-    "sort_8x4": ["-DPGDVS_RASTER_WARP_8X4"],
-    "fill_u1": ["-DPGDVS_FILL_UNROLL=1"],
-    "fill_u2": ["-DPGDVS_FILL_UNROLL=2"],
+    "tma": [],
+    "tma_sort": ["-DPGDVS_RASTER_SORT"],
+    "no_tma": ["-DPGDVS_RASTER_NO_TMA"],
+    "tma_64k": ["-DPGDVS_RASTER_SMEM_BYTES=65536"],
+    "tma_24k": ["-DPGDVS_RASTER_SMEM_BYTES=24576"],
 }
 SRCS = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu"]
 
