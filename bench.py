@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -218,7 +218,8 @@ def run_ours(args):
     from pgdvs_b200 import ops, synthetic
     from pgdvs_b200.dyn_renderer import prepare_views, render_prepared
 
-    wl = synthetic.make_workload(args.workload, dev, n_views=args.views, seed=1234 + rank, flow_mode=args.flow)
+    wl = synthetic.make_workload(args.workload, dev, n_views=args.views, seed=1234 + rank, flow_mode=args.flow,
+                                 K=args.K, radius=args.radius)
     V, H, W, K, radius = wl.n_views, wl.H, wl.W, wl.K, wl.radius
     pairs, cams = wl.jobs(range(V))
     prep = prepare_views(pairs, cams, H, W, dev)
@@ -412,11 +413,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_nvidia_seq")
     ap.add_argument("--views", type=int, default=None, help="views per GPU (default: the config's)")
+    ap.add_argument("--K", type=int, default=None, help="points per pixel (default: the config's)")
+    ap.add_argument("--radius", type=float, default=None, help="splat radius in NDC (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fragments", dest="fragments", action="store_false",
                     help="do not materialise idx/zbuf/dists (fused-only mode; B_rc drops the 12*K*H*W term)")

@@ -305,21 +305,24 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
 }
 
 // ---------------------------------------------------------------------------------------
-// TMA-staged tile kernel: halo == 1 (3x3 cell windows), scalar radius.
+// TMA-staged tile kernel: small halos (compile-time HALO = 1..3), scalar radius.
 // ---------------------------------------------------------------------------------------
-constexpr int kTileW = 32, kTileH = 8, kTileRows = kTileH + 2;
+constexpr int kTileW = 32, kTileH = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-template <int KP>
+template <int KP, int HALO>
 __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_raster_tile(const __grid_constant__ RasterParams p) {
+  constexpr int SPAN = 2 * HALO + 1;     // window rows / cells per pixel
+  constexpr int ROWS = kTileH + 2 * HALO;  // extended-grid rows the tile's pixels can touch
+  static_assert(ROWS <= 32, "one lane per tile row");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_rec = reinterpret_cast<float4*>(smem_raw);  // staged records (kRecStride float4 each)
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_delta[kTileRows];  // smem record index = global record index + s_delta[row]
-  __shared__ int s_staged;            // 1: the tile's runs fit and are being copied
+  __shared__ int s_delta[ROWS];  // smem record index = global record index + s_delta[row]
+  __shared__ int s_staged;       // 1: the tile's runs fit and are being copied
 
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     if (x < p.W && y < p.H) {
       const int* __restrict__ c0p = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
 #pragma unroll
-      for (int ry = 0; ry < 3; ++ry) work += __ldg(c0p + ry * p.GW + 3) - __ldg(c0p + ry * p.GW);
+      for (int ry = 0; ry < SPAN; ++ry) work += __ldg(c0p + ry * p.GW + SPAN) - __ldg(c0p + ry * p.GW);
     }
     if (tid < 64) s_hist[tid] = 0;
     if (tid == 0) s_max = 0;
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
 #endif
   const int ly = y - y0;  // local row of this thread's pixel
 
-  // ---- warp 0: size the 10 row runs, decide, arm the barrier, issue the bulk copies
+  // ---- warp 0: size the row runs, decide, arm the barrier, issue the bulk copies
   if (tid == 0) {
     // one arrival (the expect_tx below); the copies complete the transaction count
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
@@ -379,25 +382,25 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
   __syncthreads();
   if (threadIdx.y == 0) {
     const int lane = threadIdx.x;
-    // extended-grid row (y0 + lane) holds image row y0 + lane - 1; cells x0 .. x0+33 (clamped)
+    // extended-grid row (y0 + lane) holds image row y0 + lane - HALO; cells x0 .. x0+31+2*HALO
     const int row = y0 + lane;
     int gs = 0, ge = 0;
-    if (lane < kTileRows && row < p.GH) {
+    if (lane < ROWS && row < p.GH) {
       const int64_t rb = ((int64_t)n * p.GH + row) * p.GW;
-      const int xe = min(x0 + kTileW + 1, p.GW - 1);
+      const int xe = min(x0 + kTileW - 1 + 2 * HALO, p.GW - 1);
       gs = __ldg(p.cell_end + rb + x0 - 1);
       ge = __ldg(p.cell_end + rb + xe);
     }
     const int len = ge - gs;
     int inc = len;  // inclusive prefix over the rows -> smem offsets
 #pragma unroll
-    for (int d = 1; d < 16; d <<= 1) {
+    for (int d = 1; d < 32; d <<= 1) {
       const int o = __shfl_up_sync(0xffffffffu, inc, d);
       if (lane >= d) inc += o;
     }
-    const int total = __shfl_sync(0xffffffffu, inc, kTileRows - 1);
+    const int total = __shfl_sync(0xffffffffu, inc, ROWS - 1);
     const bool fits = total <= p.smem_records;
-    if (lane < kTileRows) s_delta[lane] = fits ? (inc - len) - gs : 0;
+    if (lane < ROWS) s_delta[lane] = fits ? (inc - len) - gs : 0;
     if (lane == 0) {
       s_staged = fits ? 1 : 0;
       if (fits) {
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
       }
     }
     __syncwarp();
-    if (fits && lane < kTileRows && len > 0) {
+    if (fits && lane < ROWS && len > 0) {
       const float4* src = p.recA + (int64_t)kRecStride * gs;
       float4* dst = s_rec + (int64_t)kRecStride * (inc - len);
       const uint32_t bytes = (uint32_t)len * (uint32_t)(kRecStride * sizeof(float4));
@@ -425,18 +428,19 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
   c.xf = pixel_center_ndc(p.ax, x);
   c.yf = pixel_center_ndc(p.ay, y);
   c.r2 = p.r2;
-  int s0 = 0, s1 = 0, s2 = 0, c0 = 0, c01 = 0, total = 0;
+  int rs[SPAN], rl[SPAN];  // start (global record index) and length of each window-row run
+#pragma unroll
+  for (int r = 0; r < SPAN; ++r) {
+    rs[r] = 0;
+    rl[r] = 0;
+  }
   if (inside) {
     const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
-    s0 = __ldg(cs);
-    const int e0 = __ldg(cs + 3);
-    s1 = __ldg(cs + p.GW);
-    const int e1 = __ldg(cs + p.GW + 3);
-    s2 = __ldg(cs + 2 * p.GW);
-    const int e2 = __ldg(cs + 2 * p.GW + 3);
-    c0 = e0 - s0;
-    c01 = c0 + (e1 - s1);
-    total = c01 + (e2 - s2);
+#pragma unroll
+    for (int r = 0; r < SPAN; ++r) {
+      rs[r] = __ldg(cs + r * p.GW);
+      rl[r] = __ldg(cs + r * p.GW + SPAN) - rs[r];
+    }
   }
   __syncthreads();  // s_staged / s_delta visible
   const bool staged = s_staged != 0;
@@ -455,18 +459,18 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
           : "memory");
     }
     rec = s_rec;
-    s0 += s_delta[ly];
-    s1 += s_delta[ly + 1];
-    s2 += s_delta[ly + 2];
+#pragma unroll
+    for (int r = 0; r < SPAN; ++r) rs[r] += s_delta[ly + r];
   }
 
   KList<KP> q;
   q.init();
   bool tie = false;
-  {
+  if (HALO == 1) {
     // the three row runs are walked by ONE flattened loop so that lanes with uneven rows do not
     // wait for each other three times
-    const int o1 = s1 - c0, o2 = s2 - c01;
+    const int c0 = rl[0], c01 = rl[0] + rl[1], total = c01 + rl[2];
+    const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
     if (staged) {
       for (int t = 0; t < total; ++t) {
         const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
@@ -485,6 +489,22 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
         if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
         a = an;
         j = jn;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < SPAN; ++r) {
+      const int s = rs[r], e = rs[r] + rl[r];
+      if (staged) {
+        for (int j = s; j < e; ++j) {
+          const float4 a = s_rec[kRecStride * j];
+          if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+        }
+      } else {
+        for (int j = s; j < e; ++j) {
+          const float4 a = __ldg(p.recA + kRecStride * j);
+          if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+        }
       }
     }
   }
@@ -506,28 +526,46 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
 #ifndef PGDVS_RASTER_SMEM_BYTES
 #define PGDVS_RASTER_SMEM_BYTES (40 * 1024)
 #endif
+#ifndef PGDVS_RASTER_SMEM_BYTES_WIDE
+#define PGDVS_RASTER_SMEM_BYTES_WIDE (100 * 1024)
+#endif
+
+template <int KP, int HALO>
+static void launch_tile(RasterParams& p, dim3 grid, dim3 block, cudaStream_t stream) {
+  const int smem = (HALO == 1) ? PGDVS_RASTER_SMEM_BYTES : PGDVS_RASTER_SMEM_BYTES_WIDE;
+  p.smem_records = smem / (int)(kRecStride * sizeof(float4));
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_raster_tile<KP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  k_raster_tile<KP, HALO><<<grid, block, smem, stream>>>(p);
+}
 
 template <int KP>
 static int launch_raster(RasterParams& p, cudaStream_t stream) {
   dim3 block(32, 8);
   dim3 grid((p.W + 31) / 32, (p.H + 7) / 8, p.N);
-  if (p.r2 < 0.0f) {
-    k_raster_cells<KP, true><<<grid, block, 0, stream>>>(p);
-  } else if (p.halo == 1 && kRecStride == 2 && KP <= 32) {
+  bool done = false;
 #ifndef PGDVS_RASTER_NO_TMA
-    const int smem = PGDVS_RASTER_SMEM_BYTES;
-    p.smem_records = smem / (int)(kRecStride * sizeof(float4));
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_raster_tile<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr_set = true;
+  if (p.r2 >= 0.0f && KP <= 32) {
+    if (p.halo == 1) {
+      launch_tile<KP, 1>(p, grid, block, stream);
+      done = true;
+    } else if (p.halo == 2) {
+      launch_tile<KP, 2>(p, grid, block, stream);
+      done = true;
+    } else if (p.halo == 3) {
+      launch_tile<KP, 3>(p, grid, block, stream);
+      done = true;
     }
-    k_raster_tile<KP><<<grid, block, smem, stream>>>(p);
-#else
-    k_raster_cells<KP, false><<<grid, block, 0, stream>>>(p);
+  }
 #endif
-  } else {
-    k_raster_cells<KP, false><<<grid, block, 0, stream>>>(p);
+  if (!done) {
+    if (p.r2 < 0.0f)
+      k_raster_cells<KP, true><<<grid, block, 0, stream>>>(p);
+    else
+      k_raster_cells<KP, false><<<grid, block, 0, stream>>>(p);
   }
   return check_launch();
 }
