@@ -42,6 +42,7 @@ struct RasterParams {
   float* image;
   float* mask;
   int smem_records;  // capacity of the staging buffer of k_raster_tile, in records
+  double density;    // host-side hint: mean points per pixel (sizes the staging buffer)
 };
 
 constexpr float kInf = __builtin_huge_valf();
@@ -531,15 +532,26 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
 #endif
 
 template <int KP, int HALO>
-static void launch_tile(RasterParams& p, dim3 grid, dim3 block, cudaStream_t stream) {
-  const int smem = (HALO == 1) ? PGDVS_RASTER_SMEM_BYTES : PGDVS_RASTER_SMEM_BYTES_WIDE;
+static bool launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, cudaStream_t stream) {
+  // size the staging buffer from the mean point density (points per pixel of the batch) with
+  // 1.5x head-room; tiles that still overflow fall back to global reads inside the kernel.
+  // If even the mean tile would not fit in PGDVS_RASTER_SMEM_BYTES_WIDE, the generic kernel
+  // (more resident CTAs, no staging) is the better choice.
+  const double tile_cells = (double)(kTileW + 2 * HALO) * (kTileH + 2 * HALO);
+  const double need = 1.5 * density * tile_cells * (double)(kRecStride * sizeof(float4));
+  if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) return false;
+  int smem = (int)need;
+  if (smem < 24 * 1024) smem = 24 * 1024;
+  smem = (smem + 8191) & ~8191;
+  if (HALO == 1 && smem < PGDVS_RASTER_SMEM_BYTES) smem = PGDVS_RASTER_SMEM_BYTES;
   p.smem_records = smem / (int)(kRecStride * sizeof(float4));
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static int attr_smem = 0;  // per instantiation: raise the opt-in limit when needed
+  if (smem > attr_smem) {
     cudaFuncSetAttribute(k_raster_tile<KP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
+    attr_smem = smem;
   }
   k_raster_tile<KP, HALO><<<grid, block, smem, stream>>>(p);
+  return true;
 }
 
 template <int KP>
@@ -549,16 +561,13 @@ static int launch_raster(RasterParams& p, cudaStream_t stream) {
   bool done = false;
 #ifndef PGDVS_RASTER_NO_TMA
   if (p.r2 >= 0.0f && KP <= 32) {
-    if (p.halo == 1) {
-      launch_tile<KP, 1>(p, grid, block, stream);
-      done = true;
-    } else if (p.halo == 2) {
-      launch_tile<KP, 2>(p, grid, block, stream);
-      done = true;
-    } else if (p.halo == 3) {
-      launch_tile<KP, 3>(p, grid, block, stream);
-      done = true;
-    }
+    const double density = p.density;
+    if (p.halo == 1)
+      done = launch_tile<KP, 1>(p, grid, block, density, stream);
+    else if (p.halo == 2)
+      done = launch_tile<KP, 2>(p, grid, block, density, stream);
+    else if (p.halo == 3)
+      done = launch_tile<KP, 3>(p, grid, block, density, stream);
   }
 #endif
   if (!done) {
@@ -623,6 +632,8 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   p.image = image;
   p.mask = mask;
   p.smem_records = 0;
+  // mean points per pixel of the batch (P is the capacity of the packed cloud: an upper bound)
+  p.density = (double)P / ((double)N * (double)H * (double)W);
 
   if (K <= 1) return launch_raster<1>(p, stream);
   if (K <= 2) return launch_raster<2>(p, stream);
