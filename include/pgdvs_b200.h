@@ -212,6 +212,30 @@ int pgdvs_merge_blend(const float* dyn_rgb, const float* dyn_mask, const float* 
                       float* out_rgb, float* out_mask, float* out_combined, void* stream);
 
 /* --------------------------------------------------------------------------------------
+ * 5b. Track branch: 2-D point tracks -> 3-D cloud at the target time.  Replaces
+ *     PGDVSDynamicTrackRenderer.compute_pcl_for_tgt up to its KNN filters
+ *     (pgdvs_renderer_dyn_track.py:98-284).  Tracker inference itself (TAPIR / CoTracker) is
+ *     out of scope: tracks and visibilities are inputs.
+ *
+ *  tracks f32 [Q,F,2] (col,row); visibles u8 [Q,F]; frames_dev device array [F] (F <= 32)
+ *  closest_mask / real_mask: bit f set <=> frame f is in data_for_track["idx_temporal_closest"] /
+ *  ["idx_real_track"];  outputs pcl/rgb f32 [Q,3] capacity, track_id i32 [Q] or NULL, count i64 [1]
+ * ------------------------------------------------------------------------------------ */
+typedef struct PgdvsTrackFrame {
+  const float* rgb;   /* [H,W,3] */
+  const float* depth; /* [H,W]   */
+  float M[9];         /* c2w[:3,:3] @ inv(K[:3,:3]) */
+  float o[3];         /* c2w[:3,3] */
+  float time;
+  float _pad;
+} PgdvsTrackFrame;
+int pgdvs_track_workspace_bytes(int64_t Q, size_t* bytes);
+int pgdvs_track_points(const float* tracks, const uint8_t* visibles, int64_t Q, int F,
+                       const PgdvsTrackFrame* frames_dev, uint32_t closest_mask, uint32_t real_mask,
+                       float time_tgt, int H, int W, float* pcl, float* rgb, int32_t* track_id,
+                       int64_t* count_dev, void* workspace, size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------
  * 6. Statistical outlier support ("next" row 1 of the scope table): mean squared distance
  *    from each query point to its K nearest reference points, dropping the first
  *    `skip_first` of them.  Replaces `pytorch3d.ops.knn_points(q, r, K, return_nn=True)` +

@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libpgdvs_b200.so"
 OBJ_DIR = LIB_DIR / "obj"
-SOURCES = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu"]
+SOURCES = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu", "track.cu"]
 HEADERS = [CSRC / "common.cuh", PKG_DIR.parent / "include" / "pgdvs_b200.h"]
 
 NVCC_FLAGS = [

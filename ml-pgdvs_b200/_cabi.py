@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = (
     "pgdvs_unproject_warp_project", "pgdvs_project_points", "pgdvs_merge_blend",
     "pgdvs_uwp_bin_workspace_bytes", "pgdvs_uwp_bin", "pgdvs_pack_rgbd",
     "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist", "pgdvs_knn_points",
+    "pgdvs_track_workspace_bytes", "pgdvs_track_points",
 )
 
 
@@ -42,6 +43,11 @@ class PgdvsUwpJob(ctypes.Structure):
 
 class PgdvsFramePack(ctypes.Structure):
     _fields_ = [("rgb", c_void_p), ("depth", c_void_p), ("rgbd", c_void_p)]
+
+
+class PgdvsTrackFrame(ctypes.Structure):
+    _fields_ = [("rgb", c_void_p), ("depth", c_void_p), ("M", c_float * 9), ("o", c_float * 3),
+                ("time", c_float), ("_pad", c_float)]
 
 
 class PgdvsError(RuntimeError):
@@ -103,6 +109,12 @@ def lib():
     L.pgdvs_knn_mean_dist.restype = c_int
     L.pgdvs_knn_mean_dist.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p,
                                       c_void_p, c_size_t, c_void_p]
+    L.pgdvs_track_workspace_bytes.restype = c_int
+    L.pgdvs_track_workspace_bytes.argtypes = [c_int64, POINTER(c_size_t)]
+    L.pgdvs_track_points.restype = c_int
+    L.pgdvs_track_points.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, ctypes.c_uint32,
+                                     ctypes.c_uint32, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]
     L.pgdvs_knn_points.restype = c_int
     L.pgdvs_knn_points.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     if L.pgdvs_abi_version() != 1:

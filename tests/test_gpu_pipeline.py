@@ -373,6 +373,81 @@ def test_compat_namespace_runs_the_reference_call_sequence(golden_dir):
     np.testing.assert_allclose(d2.cpu().numpy(), nn_dists[0].cpu().numpy(), rtol=1e-4, atol=1e-6)
 
 
+def test_track_points_match_reference_golden(golden_dir):
+    """Track branch kernel vs the cloud the REAL reference computed (fixture) and vs the oracle on
+    a larger random case (order of survivors exact, positions / colours within tolerance)."""
+    from pgdvs_b200 import track
+    d = _dev()
+    g = np.load(golden_dir / "track_pcl.npz")
+    kw = dict(tracks=T(g["tracks"]), visibles=T(g["visibles"]), rgbs=T(g["rgbs"]), depths=T(g["depths"]),
+              flat_cams=T(g["flat_cams"]), times=T(g["times"]), time_tgt=T(g["time_tgt"]),
+              idx_temporal_closest=g["idx_temporal_closest"].tolist(), idx_real_track=g["idx_real_track"].tolist())
+    pcl, rgb, tid = track.track_points(**{k: (v.to(d) if torch.is_tensor(v) and k not in ("time_tgt",) else v)
+                                          for k, v in kw.items()}, return_track_id=True)
+    assert pcl.shape[0] == g["out_pcl"].shape[0] > 0
+    np.testing.assert_allclose(pcl.cpu().numpy(), g["out_pcl"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(rgb.cpu().numpy(), g["out_rgb"], atol=5e-6, rtol=0)
+    _, _, e_tid = ref.compute_pcl_for_tgt(**kw)
+    assert torch.equal(tid.cpu(), e_tid)
+    # larger random case against the oracle
+    gen = torch.Generator().manual_seed(4)
+    H, W, F, Q = 36, 52, 8, 5000
+    rgbs = torch.rand(F, H, W, 3, generator=gen)
+    depths = 1 + 4 * torch.rand(F, H, W, 1, generator=gen)
+    Kc = torch.eye(4)
+    Kc[0, 0] = Kc[1, 1] = 0.9 * W
+    Kc[0, 2], Kc[1, 2] = W / 2, H / 2
+    flat = []
+    for f in range(F):
+        c2w = torch.eye(4)
+        c2w[:3, 3] = torch.tensor([0.03 * f, -0.01 * f, 0.0])
+        flat.append(torch.cat([torch.tensor([float(H), float(W)]), Kc.reshape(-1), c2w.reshape(-1)]))
+    flat = torch.stack(flat)
+    uv0 = torch.stack([torch.rand(Q, generator=gen) * (W - 1), torch.rand(Q, generator=gen) * (H - 1)], 1)
+    tracks = uv0[:, None, :] + torch.cumsum(0.7 * torch.randn(Q, F, 2, generator=gen), dim=1)
+    visibles = torch.rand(Q, F, generator=gen) < 0.6
+    times = torch.arange(F, dtype=torch.float32)
+    kw = dict(tracks=tracks, visibles=visibles, rgbs=rgbs, depths=depths, flat_cams=flat, times=times,
+              time_tgt=torch.tensor(3.3), idx_temporal_closest=[3, 4], idx_real_track=[0, 1, 2, 5, 6, 7])
+    e_pcl, e_rgb, e_tid = ref.compute_pcl_for_tgt(**kw)
+    pcl, rgb, tid = track.track_points(**{k: (v.to(d) if torch.is_tensor(v) and k != "time_tgt" else v)
+                                          for k, v in kw.items()}, return_track_id=True)
+    assert torch.equal(tid.cpu(), e_tid) and e_tid.numel() > 100
+    # |dt| ties between two frames may be ordered differently by torch.argsort: the interpolated
+    # point is the same up to rounding, so compare with a tolerance
+    np.testing.assert_allclose(pcl.cpu().numpy(), e_pcl.numpy(), rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(rgb.cpu().numpy(), e_rgb.numpy(), atol=5e-6, rtol=0)
+
+
+def test_static_geo_point_renderer():
+    """StaticGeoPointRenderer.forward (st_geo_renderer.py:26-122) vs the oracle render."""
+    import pgdvs_b200
+    from types import SimpleNamespace
+    d = _dev()
+    gen = torch.Generator().manual_seed(8)
+    H, W, P = 30, 44, 6000
+    pts = torch.randn(P, 3, generator=gen) * torch.tensor([1.2, 0.8, 0.6]) + torch.tensor([0.0, 0.0, 4.0])
+    cols = torch.rand(P, 3, generator=gen)
+    Kc = torch.eye(4)
+    Kc[0, 0] = Kc[1, 1] = 0.9 * W
+    Kc[0, 2], Kc[1, 2] = W / 2, H / 2
+    flat = torch.cat([torch.tensor([float(H), float(W)]), Kc.reshape(-1), torch.eye(4).reshape(-1)])
+    cfg = SimpleNamespace(st_pcl_remove_outlier=False, st_render_pcl_pt_radius=0.03, st_render_pcl_pts_per_pixel=3)
+    r = pgdvs_b200.StaticGeoPointRenderer()
+    img, mask = r(tgt_h=H, tgt_w=W, flat_tgt_cam=flat.to(d), st_pcl_rgb=torch.cat([pts, cols], 1).to(d), render_cfg=cfg)
+    e_img, e_mask = ref.render_dyn_pcl(H=H, W=W, dyn_pcl=pts, rgbs=cols, flat_cam=flat, radius=0.03, points_per_pixel=3)
+    assert (mask.cpu() == e_mask).float().mean() > 0.995
+    diff = (img.cpu() - e_img).abs().max(dim=-1).values
+    assert (diff < 1e-4).float().mean() > 0.99
+    cfg.st_pcl_remove_outlier, cfg.st_pcl_outlier_knn, cfg.st_pcl_outlier_std_thres = True, 20, 0.1
+    img2, mask2 = r(tgt_h=H, tgt_w=W, flat_tgt_cam=flat.to(d), st_pcl_rgb=torch.cat([pts, cols], 1).to(d), render_cfg=cfg)
+    flags, _, _ = ref.knn_outlier_flags(pts, knn=20, std_thres=0.1)
+    e_img2, e_mask2 = ref.render_dyn_pcl(H=H, W=W, dyn_pcl=pts[flags], rgbs=cols[flags], flat_cam=flat, radius=0.03,
+                                         points_per_pixel=3)
+    assert (mask2.cpu() == e_mask2).float().mean() > 0.99
+    assert float(mask2.sum()) < float(mask.sum())  # outliers removed -> fewer covered pixels
+
+
 def test_pytorch3d_facade_generic_equals_fused():
     """The pytorch3d-shaped classes: the generic two-step path (rasterize -> torch weights ->
     stand-alone compositor, any C) and the fused path give the same image."""
