@@ -226,21 +226,29 @@ def run_ours(args):
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     gather_list = None
+    gdtype = torch.float32 if args.gather == "f32" else torch.uint8
     if world > 1 and rank == 0:
-        gather_list = [torch.empty((V, H, W, 3), dtype=torch.float32, device=dev) for _ in range(world)]
-    keep = []
+        gather_list = [torch.empty((V, H, W, 3), dtype=gdtype, device=dev) for _ in range(world)]
+    frames_u8 = [torch.empty((V, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    state_g = {"i": 0}
 
     def step(ev=None):
         out = render_prepared(prep, radius=radius, points_per_pixel=K, compositor="norm",
                               static_rgb=wl.static_rgb, raster_events=ev, return_fragments=args.fragments)
         if world > 1:
-            # frames are gathered on rank 0 over NCCL/NVLink, overlapped with the next step
+            # finished frames are gathered on rank 0 over NCCL/NVLink on a side stream, overlapped
+            # with the next step; by default as the 8-bit frames the reference's evaluator / video
+            # writer consume (engines/evaluator_pgdvs.py:75-77), --gather f32 sends raw floats
+            payload = out["image"]
+            if args.gather == "u8":
+                payload = ops.quantize_u8(out["image"], out=frames_u8[state_g["i"] & 1])
+                state_g["i"] += 1
             done = torch.cuda.Event()
             done.record()
             comm_stream.wait_event(done)
             with torch.cuda.stream(comm_stream):
-                out["image"].record_stream(comm_stream)
-                dist.gather(out["image"], gather_list, dst=0)
+                payload.record_stream(comm_stream)
+                dist.gather(payload, gather_list, dst=0)
         return out
 
     def barrier():
@@ -389,7 +397,8 @@ def run_ours(args):
                        "fragments_written": bool(args.fragments),
                        "synthetic_flow": ("9x9-box-smoothed N(0,3px) + 0.1px jitter (piecewise-smooth motion)"
                                           if args.flow == "smooth" else "i.i.d. N(0,3px) per pixel (incoherent stress case)"),
-                       "parallelism": f"views sharded over {world} GPU(s); NCCL gather of frames to rank 0" if world > 1 else "1 GPU",
+                       "parallelism": (f"views sharded over {world} GPU(s); NCCL gather of {args.gather} frames to rank 0, "
+                                       "overlapped with the next step") if world > 1 else "1 GPU",
                        "cache": f"L2 flushed with a {L2_FLUSH_BYTES >> 20} MiB memset before every step (inside the timed bracket); "
                                 f"per-step working set ~{(b_rc + 72 * total_points) / 1e9:.1f} GB >> 126 MB L2"},
             "mpoints_per_s": value * (total_points / V) / 1e6,
@@ -424,6 +433,8 @@ def main():
     ap.add_argument("--no-fragments", dest="fragments", action="store_false",
                     help="do not materialise idx/zbuf/dists (fused-only mode; B_rc drops the 12*K*H*W term)")
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
+    ap.add_argument("--gather", default="u8", choices=["u8", "f32"],
+                    help="N>1: gather 8-bit frames (what the reference writes / scores) or raw fp32 on rank 0")
     ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"],
                     help="synthetic optical flow: piecewise-smooth (default) or i.i.d. per pixel (stress)")
     args = ap.parse_args()

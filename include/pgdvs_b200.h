@@ -211,6 +211,11 @@ int pgdvs_merge_blend(const float* dyn_rgb, const float* dyn_mask, const float* 
                       const float* track_mask, const float* static_rgb, int B, int H, int W,
                       float* out_rgb, float* out_mask, float* out_combined, void* stream);
 
+/* 8-bit frames as the reference's evaluator / visualizer consume them
+ * (pgdvs/engines/evaluator_pgdvs.py:51-77): NaN -> 0, clamp to [0,1], (x*255).byte().
+ * in f32 [n] (16-byte aligned), out u8 [n].  Used before gathering frames across GPUs. */
+int pgdvs_quantize_u8(const float* in, uint8_t* out, int64_t n, void* stream);
+
 /* --------------------------------------------------------------------------------------
  * 5b. Track branch: 2-D point tracks -> 3-D cloud at the target time.  Replaces
  *     PGDVSDynamicTrackRenderer.compute_pcl_for_tgt up to its KNN filters

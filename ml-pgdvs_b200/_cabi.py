@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "pgdvs_unproject_warp_project", "pgdvs_project_points", "pgdvs_merge_blend",
     "pgdvs_uwp_bin_workspace_bytes", "pgdvs_uwp_bin", "pgdvs_pack_rgbd",
     "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist", "pgdvs_knn_points",
-    "pgdvs_track_workspace_bytes", "pgdvs_track_points",
+    "pgdvs_track_workspace_bytes", "pgdvs_track_points", "pgdvs_quantize_u8",
 )
 
 
@@ -115,6 +115,8 @@ def lib():
     L.pgdvs_track_points.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, ctypes.c_uint32,
                                      ctypes.c_uint32, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_size_t, c_void_p]
+    L.pgdvs_quantize_u8.restype = c_int
+    L.pgdvs_quantize_u8.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     L.pgdvs_knn_points.restype = c_int
     L.pgdvs_knn_points.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     if L.pgdvs_abi_version() != 1:

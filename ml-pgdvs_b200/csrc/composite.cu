@@ -91,6 +91,22 @@ __global__ void __launch_bounds__(256) k_merge_blend(const float* __restrict__ d
   }
 }
 
+// 8-bit frames as the reference's evaluator / video writer consume them
+// (engines/evaluator_pgdvs.py:51-77): NaN -> 0, clamp to [0,1], (x * 255).byte() (truncation).
+__global__ void __launch_bounds__(256) k_quantize_u8(const float4* __restrict__ in, uchar4* __restrict__ out,
+                                                     int64_t n4, const float* __restrict__ tail_in,
+                                                     uint8_t* __restrict__ tail_out, int n_tail) {
+  auto q = [](float v) -> unsigned char {
+    v = (v != v) ? 0.0f : fminf(fmaxf(v, 0.0f), 1.0f);
+    return (unsigned char)(int)(v * 255.0f);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    out[i] = make_uchar4(q(v.x), q(v.y), q(v.z), q(v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n_tail) tail_out[threadIdx.x] = q(tail_in[threadIdx.x]);
+}
+
 __global__ void __launch_bounds__(256) k_project(const float* __restrict__ xyz, int64_t P,
                                                  const PgdvsCamera* __restrict__ cam,
                                                  float* __restrict__ out) {
@@ -139,6 +155,18 @@ extern "C" int pgdvs_merge_blend(const float* dyn_rgb, const float* dyn_mask, co
   const int64_t HW = (int64_t)H * W;
   k_merge_blend<<<grid_for((int64_t)B * HW), 256, 0, (cudaStream_t)stream>>>(
       dyn_rgb, dyn_mask, track_rgb, track_mask, static_rgb, B, HW, out_rgb, out_mask, out_combined);
+  return check_launch();
+}
+
+extern "C" int pgdvs_quantize_u8(const float* in, uint8_t* out, int64_t n, void* stream) {
+  if (n < 0) return PGDVS_E_BADARG;
+  if (n == 0) return PGDVS_OK;
+  if (!in || !out) return PGDVS_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 3) != 0) return PGDVS_E_ALIGN;
+  const int64_t n4 = n / 4;
+  const int n_tail = (int)(n - n4 * 4);
+  k_quantize_u8<<<grid_for(n4 > 0 ? n4 : 1), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<uchar4*>(out), n4, in + n4 * 4, out + n4 * 4, n_tail);
   return check_launch();
 }
 

@@ -319,6 +319,21 @@ def knn_points(p1: torch.Tensor, p2: torch.Tensor, K: int = 1, return_nn: bool =
     return _KNN((dists, idx, nn))
 
 
+def quantize_u8(frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """8-bit frames exactly as the reference's evaluator makes them
+    (engines/evaluator_pgdvs.py:51-77): NaN -> 0, clamp(0,1), (x*255).byte()."""
+    _require_cuda(frames, "frames")
+    dev = frames.device
+    f = _f32c(frames)
+    if out is None:
+        out = torch.empty(f.shape, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().pgdvs_quantize_u8(f.data_ptr(), out.data_ptr(), f.numel(), _stream_ptr(dev)),
+                    "pgdvs_quantize_u8")
+    LAUNCHES["count"] += 1
+    return out
+
+
 def merge_blend(dyn_rgb, dyn_mask, track_rgb=None, track_mask=None, static_rgb=None):
     """pgdvs_renderer_dyn.py:229-235 (+ pgdvs_renderer.py:169-172 when static_rgb is given).
     Channels-first [B,3,H,W] / [B,1,H,W].  Returns (rgb, mask, combined-or-None)."""

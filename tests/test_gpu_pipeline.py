@@ -231,6 +231,23 @@ def test_merge_blend():
     assert torch.equal(rgb.cpu(), e_rgb) and torch.equal(m.cpu(), e_m) and torch.equal(comb.cpu(), e_c)
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 7, 3), (1, 288, 544, 3), (3,), (1, 4)])
+def test_quantize_u8_matches_evaluator_rule(shape):
+    """engines/evaluator_pgdvs.py:51-77: nan_to_num, clamp(0,1), (x*255).byte()."""
+    import pgdvs_b200
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(shape, generator=g) * 1.4 - 0.2
+    flat = x.view(-1)
+    flat[0] = float("nan")
+    flat[-1] = 1.0
+    if flat.numel() > 4:
+        flat[1], flat[2], flat[3] = 0.0, 254.999 / 255.0, 1.0 / 255.0
+    exp = (torch.nan_to_num(x, nan=0.0).clamp(0.0, 1.0) * 255).to(torch.uint8)
+    out = pgdvs_b200.ops.quantize_u8(x.to(_dev()))
+    assert out.dtype == torch.uint8 and out.shape == x.shape
+    assert torch.equal(out.cpu(), exp)
+
+
 def test_knn_mean_dist():
     import pgdvs_b200
     g = torch.Generator().manual_seed(1)
