@@ -58,8 +58,95 @@ __device__ __forceinline__ bool cand_less(float z, int idx, float ze, int se,
   return lt;
 }
 
+// Fast path: the K nearest hits of a pixel as ONE sorted 32-bit key per slot.
+//   key = (((bits(z) - base) >> sh) << bits) | t
+// t = ordinal of the candidate in the pixel's own walk (`bits` = ceil(log2(#candidates)), 5 or 6
+// at PGDVS densities).  z >= 0, so its bit pattern orders like the value and so does the
+// integer difference to `base`.  The tile kernel takes base = the smallest z pattern among the
+// records it staged: whenever the tile's z range spans fewer than 2^(32-bits) patterns (z_max
+// / z_min up to ~256 with 6 payload bits) sh is 0 and the key order is the EXACT z order;
+// otherwise (and in the unstaged/generic paths, base = 0) the low `sh` bits are dropped.
+// Insertion is branch-free and carries no payload:
+//   k'[i] = min(max(c, k[i-1]), k[i])        2 integer min/max per slot, all slots independent
+// (a compare-exchange on separate (z, slot) registers costs 5 ALU ops per slot and a serial
+// carry).  A candidate that misses the radius test is inserted as kEmpty, which leaves the
+// list unchanged, so the candidate loop has no divergent branch at all.
+// Keys can only misorder hits whose z agree on all kept bits.  `ambiguous()` detects every
+// such case that could matter — two neighbouring kept keys, or the last kept key and the
+// smallest rejected/evicted one (`rej`), with equal z part — and those pixels (exact fp32 ties
+// included) are redone by rescan_exact() in the full (z, idx) order of the CPU rasterizer's
+// priority queue.  Everything else is provably identical to that order.
+constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+#ifndef PGDVS_RASTER_BRANCHFREE_MAXK
+#define PGDVS_RASTER_BRANCHFREE_MAXK 8
+#endif
+
+struct KeyCode {
+  uint32_t base, mask;
+  int sh, bits;
+  // n_candidates: most candidates any pixel using this code walks; [zlo, zhi]: range of the z
+  // bit patterns it will see (0 .. 0x7fffffff when unknown)
+  __device__ __forceinline__ void init(int n_candidates, uint32_t zlo, uint32_t zhi) {
+    bits = 32 - __clz(max(n_candidates - 1, 0));
+    mask = (1u << bits) - 1u;  // n_candidates < 2^31
+    base = zlo;
+    const uint32_t range = zhi - zlo;
+    sh = max(0, bits - __clz(range));
+    // the all-ones z part with t == mask would collide with kEmpty
+    if (((range >> sh) << bits | mask) == kEmpty) ++sh;
+  }
+  // hit -> key; +0.0f maps -0.0 (which the reference does not cull) onto +0.0
+  __device__ __forceinline__ uint32_t encode(bool hit, float z, uint32_t t) const {
+    const uint32_t zb = __float_as_uint(__fadd_rn(z, 0.0f));
+    return hit ? ((((zb - base) >> sh) << bits) | t) : kEmpty;
+  }
+  __device__ __forceinline__ bool same_z(uint32_t a, uint32_t b) const { return ((a ^ b) & ~mask) == 0u; }
+};
+
 template <int KP>
-struct KList {
+struct KeyList {
+  uint32_t k[KP];
+  uint32_t rej;  // smallest key that was rejected or evicted
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < KP; ++i) k[i] = kEmpty;
+    rej = kEmpty;
+  }
+  __device__ __forceinline__ void insert(uint32_t c) {
+    uint32_t prev = k[0];
+    k[0] = min(c, prev);
+#pragma unroll
+    for (int i = 1; i < KP; ++i) {
+      const uint32_t cur = k[i];
+      k[i] = min(max(c, prev), cur);
+      prev = cur;
+    }
+    rej = min(rej, max(c, prev));
+  }
+  // small K: always the branch-free chain (a miss is kEmpty and changes nothing);
+  // large K: skip the 2*KP-op chain for keys that cannot enter the list
+  __device__ __forceinline__ void push(uint32_t c) {
+    if (KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
+      insert(c);
+    } else if (c < k[KP - 1]) {
+      insert(c);
+    } else {
+      rej = min(rej, c);
+    }
+  }
+  __device__ __forceinline__ bool ambiguous(int K, const KeyCode& kc) const {
+    bool amb = false;
+#pragma unroll
+    for (int i = 1; i < KP; ++i)
+      if (i <= K) amb = amb || (k[i] != kEmpty && kc.same_z(k[i], k[i - 1]));
+    if (K >= KP) amb = amb || (rej != kEmpty && kc.same_z(rej, k[KP - 1]));
+    return amb;
+  }
+};
+
+// Exact path: full (z, idx) order, (z, slot) pairs.
+template <int KP>
+struct ExactList {
   float z[KP];
   int s[KP];
   __device__ __forceinline__ void init() {
@@ -69,35 +156,6 @@ struct KList {
       s[i] = -1;
     }
   }
-  // Fast path: strict-< compare-exchange chain (5 ALU ops per slot, no branches, no loads).
-  // Returns true if an exact z tie was involved in a way that could change the result:
-  //   - the candidate ties with the current last element (it may have to displace it), or
-  //   - the evicted element ties with the new last element (the wrong twin may have left).
-  // Ties that stay inside the list are caught by has_adjacent_tie() at the end.
-  __device__ __forceinline__ bool insert_fast(float cz, int cs) {
-    bool tie = (cz == z[KP - 1]);
-    if (cz < z[KP - 1]) {
-#pragma unroll
-      for (int i = 0; i < KP; ++i) {
-        const bool p = cz < z[i];
-        const float tz = z[i];
-        const int ts = s[i];
-        z[i] = p ? cz : tz;
-        s[i] = p ? cs : ts;
-        cz = p ? tz : cz;
-        cs = p ? ts : cs;
-      }
-      tie = tie || (cs >= 0 && cz == z[KP - 1]);
-    }
-    return tie;
-  }
-  __device__ __forceinline__ bool has_adjacent_tie() const {
-    bool t = false;
-#pragma unroll
-    for (int i = 1; i < KP; ++i) t = t || (s[i] >= 0 && z[i] == z[i - 1]);
-    return t;
-  }
-  // Exact path: full (z, idx) order.
   __device__ __forceinline__ void insert_exact(float cz, int cidx, int cslot,
                                                const float4* __restrict__ recA) {
     if (!cand_less(cz, cidx, z[KP - 1], s[KP - 1], recA)) return;
@@ -133,12 +191,12 @@ __device__ __forceinline__ bool hit_test(const PixelCtx& c, const float4 a,
   return d2 < r2;
 }
 
-// Tie-aware rescan of one pixel over the GLOBAL records (rare).  Out of line so that the fast
-// path stays small; returns global record slots.
+// Exact rescan of one pixel over the GLOBAL records (rare: only pixels KeyList::ambiguous()
+// flags).  Out of line so that the fast path stays small; returns global record slots.
 template <int KP, bool PPR>
 __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx& c, int n, int x,
-                                          int y, float* zout, int* sout) {
-  KList<KP> q;
+                                          int y, int* sout) {
+  ExactList<KP> q;
   q.init();
   const int span = 2 * p.halo + 1;
   for (int ry = 0; ry < span; ++ry) {
@@ -151,18 +209,15 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
     }
   }
 #pragma unroll
-  for (int i = 0; i < KP; ++i) {
-    zout[i] = q.z[i];
-    sout[i] = q.s[i];
-  }
+  for (int i = 0; i < KP; ++i) sout[i] = q.s[i];
 }
 
 // ---------------------------------------------------------------------------------------
-// Epilogue shared by both kernels.  `rec` points at the records the slots of `q` refer to
-// (generic pointer: global array or the CTA's shared-memory staging buffer).
+// Epilogue shared by both kernels.  `rec` points at the records the slots `s` refer to
+// (generic pointer: global array or the CTA's shared-memory staging buffer); s[k] < 0 = empty.
 // ---------------------------------------------------------------------------------------
 template <int KP>
-__device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const KList<KP>& q,
+__device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const int (&s)[KP],
                                                const PixelCtx& c, int n, int x, int y,
                                                const float4* rec) {
   const int K = p.K;
@@ -184,7 +239,7 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const KLis
       o_d[kk] = -1.0f;
       if (k < KP) {
         w[k] = 0.f;
-        const int sl = (k < K) ? q.s[k] : -1;
+        const int sl = (k < K) ? s[k] : -1;
         if (sl >= 0) {
           const float4 a = rec[kRecStride * sl];
           o_d[kk] = dist2_rn(a.x, a.y, c.xf, c.yf);
@@ -225,8 +280,8 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const KLis
   const float inv_t = __frcp_rn(fmaxf(t_alpha, 1e-4f));
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    if (k < K && q.s[k] >= 0) {
-      const float4 f4 = rec[kRecStride * q.s[k] + (kRecStride == 2 ? 1 : 0)];
+    if (k < K && s[k] >= 0) {
+      const float4 f4 = rec[kRecStride * s[k] + (kRecStride == 2 ? 1 : 0)];
       float wk = w[k];
       if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
         wk = __fmul_rn(wk, inv_t);
@@ -242,7 +297,7 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const KLis
       ones_acc = __fadd_rn(ones_acc, wk);
     }
   }
-  const bool is_bg = q.s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
+  const bool is_bg = s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
   const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
   if (p.mask) p.mask[pix] = m;
   if (p.image) {
@@ -278,31 +333,46 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
   const float4* __restrict__ recA = p.recA;
   const float4* __restrict__ recB = p.recB;
 
-  KList<KP> q;
-  q.init();
-  bool tie = false;
   const int span = 2 * p.halo + 1;
   // cs[c] = start of cell (x + c) of the first window row = cell_end[... - 1]
   const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+  int total = 0;
+  for (int ry = 0; ry < span; ++ry)
+    total += __ldg(cs + (int64_t)ry * p.GW + span) - __ldg(cs + (int64_t)ry * p.GW);
+  KeyCode kc;
+  kc.init(total, 0u, 0x7fffffffu);
+
+  KeyList<KP> q;
+  q.init();
+  uint32_t t = 0;
   for (int ry = 0; ry < span; ++ry) {
     const int s = __ldg(cs + (int64_t)ry * p.GW);
     const int e = __ldg(cs + (int64_t)ry * p.GW + span);
-    for (int j = s; j < e; ++j) {
+    for (int j = s; j < e; ++j, ++t) {
       const float4 a = __ldg(recA + kRecStride * j);
-      if (hit_test<PPR>(c, a, recB, j)) tie |= q.insert_fast(a.z, j);
+      q.push(kc.encode(hit_test<PPR>(c, a, recB, j), a.z, t));
     }
   }
-  if (tie || q.has_adjacent_tie()) {
-    float zt[KP];
-    int st[KP];
-    rescan_exact<KP, PPR>(p, c, n, x, y, zt, st);
+  int sl[KP];
+  if (q.ambiguous(p.K, kc)) {
+    rescan_exact<KP, PPR>(p, c, n, x, y, sl);
+  } else {
+    // ordinal -> record slot: walk the window rows once more (cell_end is L1-resident by now)
 #pragma unroll
-    for (int i = 0; i < KP; ++i) {
-      q.z[i] = zt[i];
-      q.s[i] = st[i];
+    for (int i = 0; i < KP; ++i) sl[i] = -1;
+    int base = 0;
+    for (int ry = 0; ry < span; ++ry) {
+      const int s = __ldg(cs + (int64_t)ry * p.GW);
+      const int len = __ldg(cs + (int64_t)ry * p.GW + span) - s;
+#pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        const int o = (int)(q.k[i] & kc.mask) - base;
+        if (q.k[i] != kEmpty && o >= 0 && o < len) sl[i] = s + o;
+      }
+      base += len;
     }
   }
-  pixel_epilogue<KP>(p, q, c, n, x, y, recA);
+  pixel_epilogue<KP>(p, sl, c, n, x, y, recA);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -323,7 +393,8 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
   float4* s_rec = reinterpret_cast<float4*>(smem_raw);  // staged records (kRecStride float4 each)
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_delta[ROWS];  // smem record index = global record index + s_delta[row]
-  __shared__ int s_staged;       // 1: the tile's runs fit and are being copied
+  __shared__ int s_staged;       // records staged (> 0: the tile's runs fit and are being copied)
+  __shared__ uint32_t s_zlo, s_zhi;  // range of the staged z bit patterns (KeyCode)
 
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -379,6 +450,8 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     // one arrival (the expect_tx below); the copies complete the transaction count
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_zlo = 0xFFFFFFFFu;
+    s_zhi = 0u;
   }
   __syncthreads();
   if (threadIdx.y == 0) {
@@ -403,7 +476,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     const bool fits = total <= p.smem_records;
     if (lane < ROWS) s_delta[lane] = fits ? (inc - len) - gs : 0;
     if (lane == 0) {
-      s_staged = fits ? 1 : 0;
+      s_staged = fits ? total : 0;
       if (fits) {
         const uint32_t bytes = (uint32_t)total * (uint32_t)(kRecStride * sizeof(float4));
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes)
@@ -444,7 +517,8 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     }
   }
   __syncthreads();  // s_staged / s_delta visible
-  const bool staged = s_staged != 0;
+  const int n_staged = s_staged;
+  const bool staged = n_staged != 0;
   const float4* rec = p.recA;  // generic pointer to the records the slots refer to
   if (staged) {
     // wait for the bulk copies (phase 0 of the barrier)
@@ -462,21 +536,41 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     rec = s_rec;
 #pragma unroll
     for (int r = 0; r < SPAN; ++r) rs[r] += s_delta[ly + r];
+    // z range of the tile -> keys that order exactly like z (see KeyCode)
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (int i = tid; i < n_staged; i += 256) {
+      const uint32_t zb = __float_as_uint(__fadd_rn(s_rec[kRecStride * i].z, 0.0f));
+      lo = min(lo, zb);
+      hi = max(hi, zb);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((tid & 31) == 0) {
+      atomicMin(&s_zlo, lo);
+      atomicMax(&s_zhi, hi);
+    }
   }
+  __syncthreads();  // (uniform: `staged` is per CTA)
+  const uint32_t zlo = staged ? s_zlo : 0u, zhi = staged ? s_zhi : 0x7fffffffu;
 
-  KList<KP> q;
+  int total = 0;
+#pragma unroll
+  for (int r = 0; r < SPAN; ++r) total += rl[r];
+  KeyCode kc;
+  kc.init(total, zlo, zhi);
+
+  KeyList<KP> q;
   q.init();
-  bool tie = false;
   if (HALO == 1) {
     // the three row runs are walked by ONE flattened loop so that lanes with uneven rows do not
-    // wait for each other three times
-    const int c0 = rl[0], c01 = rl[0] + rl[1], total = c01 + rl[2];
+    // wait for each other three times; the body is branch-free (see KeyList)
+    const int c0 = rl[0], c01 = rl[0] + rl[1];
     const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
     if (staged) {
       for (int t = 0; t < total; ++t) {
         const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
         const float4 a = s_rec[kRecStride * j];
-        if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+        q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
       }
     } else {
       // software-pipelined global reads: record t+1 is in flight while t is processed
@@ -487,41 +581,49 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
         const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
         float4 an = a;
         if (tn < total) an = __ldg(p.recA + kRecStride * jn);
-        if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+        q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
         a = an;
         j = jn;
       }
     }
   } else {
-#pragma unroll 1
+    uint32_t t = 0;
+#pragma unroll
     for (int r = 0; r < SPAN; ++r) {
       const int s = rs[r], e = rs[r] + rl[r];
       if (staged) {
-        for (int j = s; j < e; ++j) {
+        for (int j = s; j < e; ++j, ++t) {
           const float4 a = s_rec[kRecStride * j];
-          if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+          q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
         }
       } else {
-        for (int j = s; j < e; ++j) {
+        for (int j = s; j < e; ++j, ++t) {
           const float4 a = __ldg(p.recA + kRecStride * j);
-          if (hit_test<false>(c, a, nullptr, j)) tie |= q.insert_fast(a.z, j);
+          q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
         }
       }
     }
   }
   if (!inside) return;
-  if (tie || q.has_adjacent_tie()) {
-    float zt[KP];
-    int st[KP];
-    rescan_exact<KP, false>(p, c, n, x, y, zt, st);
+  int sl[KP];
+  if (q.ambiguous(p.K, kc)) {
+    rescan_exact<KP, false>(p, c, n, x, y, sl);
+    rec = p.recA;  // the rescan returns global slots
+  } else {
+    // ordinal -> record slot (shared-memory slot when staged: rs[] already carries s_delta)
 #pragma unroll
     for (int i = 0; i < KP; ++i) {
-      q.z[i] = zt[i];
-      q.s[i] = st[i];
+      int o = (int)(q.k[i] & kc.mask);
+      int j = -1;
+#pragma unroll
+      for (int r = 0; r < SPAN; ++r) {
+        if (j < 0 && o < rl[r]) j = rs[r] + o;
+        o -= rl[r];
+      }
+      sl[i] = (q.k[i] != kEmpty) ? j : -1;
     }
-    rec = p.recA;  // the rescan returns global slots
   }
-  pixel_epilogue<KP>(p, q, c, n, x, y, rec);
+  pixel_epilogue<KP>(p, sl, c, n, x, y, rec);
 }
 
 #ifndef PGDVS_RASTER_SMEM_BYTES
