@@ -33,6 +33,7 @@ struct RasterParams {
   NdcAxis ax, ay;
   float r2;          // scalar radius^2 (fp32 r*r) or < 0: per-point radius in recB.w
   float rr_weight;   // divisor of PointsRenderer's  1 - dists/(r*r)
+  float inv_rr_weight;
   int compositor;
   float bg[4];
   const float* static_rgb;
@@ -134,6 +135,13 @@ struct KeyList {
       rej = min(rej, c);
     }
   }
+  // K == KP
+  __device__ __forceinline__ bool ambiguous_full(const KeyCode& kc) const {
+    bool amb = (rej != kEmpty) & kc.same_z(rej, k[KP - 1]);
+#pragma unroll
+    for (int i = 1; i < KP; ++i) amb |= (k[i] != kEmpty) & kc.same_z(k[i], k[i - 1]);
+    return amb;
+  }
   __device__ __forceinline__ bool ambiguous(int K, const KeyCode& kc) const {
     bool amb = false;
 #pragma unroll
@@ -213,20 +221,35 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
 }
 
 // ---------------------------------------------------------------------------------------
-// Epilogue shared by both kernels.  `rec` points at the records the slots `s` refer to
-// (generic pointer: global array or the CTA's shared-memory staging buffer); s[k] < 0 = empty.
+// Epilogue shared by both kernels.  `rec` points at the records the slots refer to (global
+// array, or the CTA's shared-memory staging buffer — the call sites keep the two apart so that
+// the staged case compiles to LDS); s[k] < 0 = empty.  FULLK: K == KP (every loop bound is a
+// compile-time constant and fragments are written with 128-bit stores).
 // ---------------------------------------------------------------------------------------
 template <int KP>
-__device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const int (&s)[KP],
+struct Slots {
+  int s[KP];
+};
+
+template <int KP, bool FULLK>
+__device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slots<KP>& sl,
                                                const PixelCtx& c, int n, int x, int y,
                                                const float4* rec) {
-  const int K = p.K;
+  const int K = FULLK ? KP : p.K;
   const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
   const int mode = p.compositor;
+  // the static frame is only needed at the very end: fetch it now, use it after the K loop
+  float st[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool blend = (p.static_rgb != nullptr) && (p.image != nullptr) && (mode != PGDVS_COMPOSITE_NONE);
+  if (blend) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      if (ch < p.C) st[ch] = __ldg(p.static_rgb + pix * p.C + ch);
+  }
   // pass 1: fragments (idx / zbuf / dists) and the PointsRenderer weights
   float w[KP];
   float t_alpha = 0.f;
-  const bool vec4 = (KP % 4 == 0) && (K == KP);  // K*4 B per pixel is a multiple of 16 B
+  constexpr bool vec4 = FULLK && (KP % 4 == 0);  // K*4 B per pixel is a multiple of 16 B
 #pragma unroll
   for (int k0 = 0; k0 < KP; k0 += 4) {
     int o_idx[4];
@@ -239,21 +262,21 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const int 
       o_d[kk] = -1.0f;
       if (k < KP) {
         w[k] = 0.f;
-        const int sl = (k < K) ? s[k] : -1;
-        if (sl >= 0) {
-          const float4 a = rec[kRecStride * sl];
+        const int s = (k < K) ? sl.s[k] : -1;
+        if (s >= 0) {
+          const float4 a = rec[kRecStride * s];
           o_d[kk] = dist2_rn(a.x, a.y, c.xf, c.yf);
           o_idx[kk] = __float_as_int(a.w);
           o_z[kk] = a.z;
-          if (mode != PGDVS_COMPOSITE_NONE) {
-            w[k] = __fsub_rn(1.0f, __fdiv_rn(o_d[kk], p.rr_weight));  // 1 - dists/(r*r)
-            t_alpha = __fadd_rn(t_alpha, w[k]);
-          }
+          // PointsRenderer: 1 - dists/(r*r), applied as a multiply by the fp32 reciprocal
+          // (|delta w| <= 2e-7; images are tolerance-matched, fragments are bit-exact)
+          w[k] = __fsub_rn(1.0f, __fmul_rn(o_d[kk], p.inv_rr_weight));
+          t_alpha = __fadd_rn(t_alpha, w[k]);
         }
       }
     }
     if (vec4) {
-      const int64_t o = pix * K + k0;
+      const int64_t o = pix * KP + k0;
       if (p.idx) *reinterpret_cast<int4*>(p.idx + o) = make_int4(o_idx[0], o_idx[1], o_idx[2], o_idx[3]);
       if (p.zbuf) *reinterpret_cast<float4*>(p.zbuf + o) = make_float4(o_z[0], o_z[1], o_z[2], o_z[3]);
       if (p.dists) *reinterpret_cast<float4*>(p.dists + o) = make_float4(o_d[0], o_d[1], o_d[2], o_d[3]);
@@ -270,6 +293,20 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const int 
     }
   }
   if (mode == PGDVS_COMPOSITE_NONE) return;
+  if (t_alpha < 0.25f && sl.s[0] >= 0) {
+    // ill-conditioned normalisation (every hit sits near the rim of its splat): the 1-ulp
+    // slack of the reciprocal would be amplified by 1/sum(w), so redo these few pixels with
+    // the true division
+    t_alpha = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (k < K && sl.s[k] >= 0) {
+        const float4 a = rec[kRecStride * sl.s[k]];
+        w[k] = __fsub_rn(1.0f, __fdiv_rn(dist2_rn(a.x, a.y, c.xf, c.yf), p.rr_weight));
+        t_alpha = __fadd_rn(t_alpha, w[k]);
+      }
+    }
+  }
 
   // pass 2: compositor.  The K-ordered accumulation follows the pytorch3d CPU loops; the
   // norm-weighted division by max(sum w, 1e-4) is applied as one reciprocal multiply
@@ -280,8 +317,8 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const int 
   const float inv_t = __frcp_rn(fmaxf(t_alpha, 1e-4f));
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    if (k < K && s[k] >= 0) {
-      const float4 f4 = rec[kRecStride * s[k] + (kRecStride == 2 ? 1 : 0)];
+    if (k < K && sl.s[k] >= 0) {
+      const float4 f4 = rec[kRecStride * sl.s[k] + 1];
       float wk = w[k];
       if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
         wk = __fmul_rn(wk, inv_t);
@@ -297,20 +334,33 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const int 
       ones_acc = __fadd_rn(ones_acc, wk);
     }
   }
-  const bool is_bg = s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
+  const bool is_bg = sl.s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
   const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
   if (p.mask) p.mask[pix] = m;
   if (p.image) {
-    for (int ch = 0; ch < p.C; ++ch) {
-      float v = is_bg ? p.bg[ch] : acc[ch];
-      if (p.static_rgb) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch < p.C) {
+        float v = is_bg ? p.bg[ch] : acc[ch];
         // combined = (1 - mask) * static + mask * dyn   (pgdvs_renderer.py:169-172)
-        const float st = __ldg(p.static_rgb + pix * p.C + ch);
-        v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st), __fmul_rn(m, v));
+        if (blend) v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st[ch]), __fmul_rn(m, v));
+        p.image[pix * p.C + ch] = v;
       }
-      p.image[pix * p.C + ch] = v;
     }
   }
+}
+
+// Out-of-line finish over the GLOBAL records: pixels whose keys were ambiguous (rescan = true,
+// exact (z, idx) rescan first) and tiles that could not be staged (slots are global already).
+// Keeps the rare paths, and their generic-address loads, out of the hot kernels.
+template <int KP, bool PPR>
+__device__ __noinline__ void finish_global(const RasterParams& p, const PixelCtx c, int n, int x,
+                                           int y, Slots<KP> sl, bool rescan) {
+  if (rescan) rescan_exact<KP, PPR>(p, c, n, x, y, sl.s);
+  if (KP <= 32 && p.K == KP)
+    pixel_epilogue<KP, true>(p, sl, c, n, x, y, p.recA);
+  else
+    pixel_epilogue<KP, false>(p, sl, c, n, x, y, p.recA);
 }
 
 #ifndef PGDVS_RASTER_MINBLOCKS
@@ -353,26 +403,29 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
       q.push(kc.encode(hit_test<PPR>(c, a, recB, j), a.z, t));
     }
   }
-  int sl[KP];
+  Slots<KP> sl;
+#pragma unroll
+  for (int i = 0; i < KP; ++i) sl.s[i] = -1;
   if (q.ambiguous(p.K, kc)) {
-    rescan_exact<KP, PPR>(p, c, n, x, y, sl);
-  } else {
-    // ordinal -> record slot: walk the window rows once more (cell_end is L1-resident by now)
-#pragma unroll
-    for (int i = 0; i < KP; ++i) sl[i] = -1;
-    int base = 0;
-    for (int ry = 0; ry < span; ++ry) {
-      const int s = __ldg(cs + (int64_t)ry * p.GW);
-      const int len = __ldg(cs + (int64_t)ry * p.GW + span) - s;
-#pragma unroll
-      for (int i = 0; i < KP; ++i) {
-        const int o = (int)(q.k[i] & kc.mask) - base;
-        if (q.k[i] != kEmpty && o >= 0 && o < len) sl[i] = s + o;
-      }
-      base += len;
-    }
+    finish_global<KP, PPR>(p, c, n, x, y, sl, true);
+    return;
   }
-  pixel_epilogue<KP>(p, sl, c, n, x, y, recA);
+  // ordinal -> record slot: walk the window rows once more (cell_end is L1-resident by now)
+  int base = 0;
+  for (int ry = 0; ry < span; ++ry) {
+    const int s = __ldg(cs + (int64_t)ry * p.GW);
+    const int len = __ldg(cs + (int64_t)ry * p.GW + span) - s;
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      const int o = (int)(q.k[i] & kc.mask) - base;
+      if (q.k[i] != kEmpty && o >= 0 && o < len) sl.s[i] = s + o;
+    }
+    base += len;
+  }
+  if (KP <= 32 && p.K == KP)
+    pixel_epilogue<KP, true>(p, sl, c, n, x, y, recA);
+  else
+    pixel_epilogue<KP, false>(p, sl, c, n, x, y, recA);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -384,8 +437,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+#ifndef PGDVS_TILE_MINBLOCKS_K8
+#define PGDVS_TILE_MINBLOCKS_K8 4
+#endif
+
 template <int KP, int HALO>
-__global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_raster_tile(const __grid_constant__ RasterParams p) {
+__global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((KP <= 16) ? 2 : 1)) k_raster_tile(const __grid_constant__ RasterParams p) {
   constexpr int SPAN = 2 * HALO + 1;     // window rows / cells per pixel
   constexpr int ROWS = kTileH + 2 * HALO;  // extended-grid rows the tile's pixels can touch
   static_assert(ROWS <= 32, "one lane per tile row");
@@ -395,65 +452,28 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
   __shared__ int s_delta[ROWS];  // smem record index = global record index + s_delta[row]
   __shared__ int s_staged;       // records staged (> 0: the tile's runs fit and are being copied)
   __shared__ uint32_t s_zlo, s_zhi;  // range of the staged z bit patterns (KeyCode)
+  __shared__ int s_max;          // most candidates any pixel of the tile walks
+  __shared__ int s_hist[64];
+  __shared__ unsigned char s_perm[256];
 
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const int n = blockIdx.z;
   int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-#ifndef PGDVS_RASTER_NO_SORT
-  // balance the warps: hand the tile's pixels to threads in order of their candidate count
-  // (counting sort in shared memory) so that the lanes of a warp walk runs of similar length
-  // (measured on C2: 2.64 -> 2.39 ms compute, +0.1 ms for the now scattered fragment stores)
-  {
-    __shared__ int s_hist[64];
-    __shared__ int s_max;
-    __shared__ unsigned char s_perm[256];
-    int work = 0;
-    if (x < p.W && y < p.H) {
-      const int* __restrict__ c0p = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
-#pragma unroll
-      for (int ry = 0; ry < SPAN; ++ry) work += __ldg(c0p + ry * p.GW + SPAN) - __ldg(c0p + ry * p.GW);
-    }
-    if (tid < 64) s_hist[tid] = 0;
-    if (tid == 0) s_max = 0;
-    __syncthreads();
-    const int wmax = __reduce_max_sync(0xffffffffu, work);
-    if ((tid & 31) == 0) atomicMax(&s_max, wmax);
-    __syncthreads();
-    const int width = s_max / 64 + 1;
-    const int bin = 63 - work / width;  // heaviest pixels first
-    const int my_rank = atomicAdd(&s_hist[bin], 1);
-    __syncthreads();
-    if (tid < 32) {  // exclusive scan of the 64 bins by one warp (2 per lane)
-      const int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1];
-      int inc = a0 + a1;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (tid >= d) inc += o;
-      }
-      s_hist[2 * tid] = inc - a0 - a1;
-      s_hist[2 * tid + 1] = inc - a1;
-    }
-    __syncthreads();
-    s_perm[s_hist[bin] + my_rank] = (unsigned char)tid;
-    __syncthreads();
-    const int mine = s_perm[tid];
-    x = x0 + (mine & 31);
-    y = y0 + (mine >> 5);
-  }
-#endif
-  const int ly = y - y0;  // local row of this thread's pixel
 
-  // ---- warp 0: size the row runs, decide, arm the barrier, issue the bulk copies
   if (tid == 0) {
     // one arrival (the expect_tx below); the copies complete the transaction count
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_zlo = 0xFFFFFFFFu;
     s_zhi = 0u;
+    s_max = 0;
   }
+  if (tid < 64) s_hist[tid] = 0;
   __syncthreads();
+
+  // ---- warp 0 first: size the row runs, decide, arm the barrier, issue the bulk copies; they
+  //      are in flight while the CTA sorts its pixels below
   if (threadIdx.y == 0) {
     const int lane = threadIdx.x;
     // extended-grid row (y0 + lane) holds image row y0 + lane - HALO; cells x0 .. x0+31+2*HALO
@@ -496,7 +516,46 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     }
   }
 
-  // ---- every thread: its pixel constants and window runs (overlaps the copies)
+  // ---- balance the warps: hand the tile's pixels to threads in order of their candidate count
+  //      (counting sort in shared memory) so that the lanes of a warp walk runs of similar
+  //      length; the largest count also sizes the payload field of the keys
+  {
+    int work = 0;
+    if (x < p.W && y < p.H) {
+      const int* __restrict__ c0p = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+#pragma unroll
+      for (int ry = 0; ry < SPAN; ++ry) work += __ldg(c0p + ry * p.GW + SPAN) - __ldg(c0p + ry * p.GW);
+    }
+    const int wmax = __reduce_max_sync(0xffffffffu, work);
+    if ((tid & 31) == 0) atomicMax(&s_max, wmax);
+    __syncthreads();  // s_max; also s_staged / s_delta of warp 0
+#ifndef PGDVS_RASTER_NO_SORT
+    const int width = s_max / 64 + 1;
+    const int bin = 63 - work / width;  // heaviest pixels first
+    const int my_rank = atomicAdd(&s_hist[bin], 1);
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 64 bins by one warp (2 per lane)
+      const int a0 = s_hist[2 * tid], a1 = s_hist[2 * tid + 1];
+      int inc = a0 + a1;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (tid >= d) inc += o;
+      }
+      s_hist[2 * tid] = inc - a0 - a1;
+      s_hist[2 * tid + 1] = inc - a1;
+    }
+    __syncthreads();
+    s_perm[s_hist[bin] + my_rank] = (unsigned char)tid;
+    __syncthreads();
+    const int mine = s_perm[tid];
+    x = x0 + (mine & 31);
+    y = y0 + (mine >> 5);
+#endif
+  }
+  const int ly = y - y0;  // local row of this thread's pixel
+
+  // ---- every thread: its pixel constants and window runs
   const bool inside = (x < p.W) && (y < p.H);
   PixelCtx c;
   c.xf = pixel_center_ndc(p.ax, x);
@@ -516,10 +575,8 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
       rl[r] = __ldg(cs + r * p.GW + SPAN) - rs[r];
     }
   }
-  __syncthreads();  // s_staged / s_delta visible
   const int n_staged = s_staged;
   const bool staged = n_staged != 0;
-  const float4* rec = p.recA;  // generic pointer to the records the slots refer to
   if (staged) {
     // wait for the bulk copies (phase 0 of the barrier)
     const uint32_t bar = smem_u32(&s_bar);
@@ -533,7 +590,6 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
           : "r"(bar)
           : "memory");
     }
-    rec = s_rec;
 #pragma unroll
     for (int r = 0; r < SPAN; ++r) rs[r] += s_delta[ly + r];
     // z range of the tile -> keys that order exactly like z (see KeyCode)
@@ -551,13 +607,12 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     }
   }
   __syncthreads();  // (uniform: `staged` is per CTA)
-  const uint32_t zlo = staged ? s_zlo : 0u, zhi = staged ? s_zhi : 0x7fffffffu;
+  KeyCode kc;  // the same code for every pixel of the tile
+  kc.init(s_max, staged ? s_zlo : 0u, staged ? s_zhi : 0x7fffffffu);
 
   int total = 0;
 #pragma unroll
   for (int r = 0; r < SPAN; ++r) total += rl[r];
-  KeyCode kc;
-  kc.init(total, zlo, zhi);
 
   KeyList<KP> q;
   q.init();
@@ -567,10 +622,22 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     const int c0 = rl[0], c01 = rl[0] + rl[1];
     const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
     if (staged) {
-      for (int t = 0; t < total; ++t) {
-        const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-        const float4 a = s_rec[kRecStride * j];
-        q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
+      if (kc.sh == 0) {
+        // exact keys: key = (zb - base) * 2^bits + t as ONE multiply-add (modulo 2^32)
+        const uint32_t mul = 1u << kc.bits;
+        uint32_t tk = 0u - kc.base * mul;
+        for (int t = 0; t < total; ++t, ++tk) {
+          const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
+          const float4 a = s_rec[kRecStride * j];
+          const uint32_t key = __float_as_uint(__fadd_rn(a.z, 0.0f)) * mul + tk;
+          q.push(hit_test<false>(c, a, nullptr, j) ? key : kEmpty);
+        }
+      } else {
+        for (int t = 0; t < total; ++t) {
+          const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
+          const float4 a = s_rec[kRecStride * j];
+          q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
+        }
       }
     } else {
       // software-pipelined global reads: record t+1 is in flight while t is processed
@@ -605,12 +672,18 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
     }
   }
   if (!inside) return;
-  int sl[KP];
-  if (q.ambiguous(p.K, kc)) {
-    rescan_exact<KP, false>(p, c, n, x, y, sl);
-    rec = p.recA;  // the rescan returns global slots
+
+  // ordinal -> record slot (shared-memory slot when staged: rs[] already carries s_delta)
+  Slots<KP> sl;
+  if (HALO == 1) {
+    const int c0 = rl[0], c01 = rl[0] + rl[1];
+    const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      const int o = (int)(q.k[i] & kc.mask);
+      sl.s[i] = (q.k[i] != kEmpty) ? o + (o < c0 ? s0 : (o < c01 ? o1 : o2)) : -1;
+    }
   } else {
-    // ordinal -> record slot (shared-memory slot when staged: rs[] already carries s_delta)
 #pragma unroll
     for (int i = 0; i < KP; ++i) {
       int o = (int)(q.k[i] & kc.mask);
@@ -620,10 +693,18 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? 4 : ((KP <= 16) ? 2 : 1)) k_r
         if (j < 0 && o < rl[r]) j = rs[r] + o;
         o -= rl[r];
       }
-      sl[i] = (q.k[i] != kEmpty) ? j : -1;
+      sl.s[i] = (q.k[i] != kEmpty) ? j : -1;
     }
   }
-  pixel_epilogue<KP>(p, sl, c, n, x, y, rec);
+  const bool amb = (KP <= 32 && p.K == KP) ? q.ambiguous_full(kc) : q.ambiguous(p.K, kc);
+  if (amb || !staged) {
+    finish_global<KP, false>(p, c, n, x, y, sl, amb);
+    return;
+  }
+  if (KP <= 32 && p.K == KP)
+    pixel_epilogue<KP, true>(p, sl, c, n, x, y, s_rec);
+  else
+    pixel_epilogue<KP, false>(p, sl, c, n, x, y, s_rec);
 }
 
 #ifndef PGDVS_RASTER_SMEM_BYTES
@@ -657,7 +738,7 @@ static bool launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, 
 }
 
 template <int KP>
-static int launch_raster(RasterParams& p, cudaStream_t stream) {
+int launch_raster(RasterParams& p, cudaStream_t stream) {
   dim3 block(32, 8);
   dim3 grid((p.W + 31) / 32, (p.H + 7) / 8, p.N);
   bool done = false;
@@ -681,8 +762,33 @@ static int launch_raster(RasterParams& p, cudaStream_t stream) {
   return check_launch();
 }
 
+// The file can be compiled as one translation unit (default) or, to build the K
+// instantiations in parallel, several times with -DPGDVS_RASTER_PART=n (see _build.py):
+// part 0 holds the C entry point, parts 1..6 one group of launch_raster<KP> each.
+#define PGDVS_RASTER_FOR_PART(n, X) PGDVS_RASTER_FOR_PART_I(n, X)
+#define PGDVS_RASTER_FOR_PART_I(n, X) PGDVS_RASTER_FOR_PART_##n(X)
+#define PGDVS_RASTER_FOR_PART_1(X) X(1) X(2) X(3) X(4)
+#define PGDVS_RASTER_FOR_PART_2(X) X(8)
+#define PGDVS_RASTER_FOR_PART_3(X) X(16)
+#define PGDVS_RASTER_FOR_PART_4(X) X(32)
+#define PGDVS_RASTER_FOR_PART_5(X) X(64)
+#define PGDVS_RASTER_FOR_PART_6(X) X(PGDVS_MAX_POINTS_PER_PIXEL)
+#define PGDVS_RASTER_DECLARE(KP) extern template int launch_raster<KP>(RasterParams&, cudaStream_t);
+#define PGDVS_RASTER_DEFINE(KP) template int launch_raster<KP>(RasterParams&, cudaStream_t);
+#if defined(PGDVS_RASTER_PART) && PGDVS_RASTER_PART == 0
+PGDVS_RASTER_FOR_PART(1, PGDVS_RASTER_DECLARE)
+PGDVS_RASTER_FOR_PART(2, PGDVS_RASTER_DECLARE)
+PGDVS_RASTER_FOR_PART(3, PGDVS_RASTER_DECLARE)
+PGDVS_RASTER_FOR_PART(4, PGDVS_RASTER_DECLARE)
+PGDVS_RASTER_FOR_PART(5, PGDVS_RASTER_DECLARE)
+PGDVS_RASTER_FOR_PART(6, PGDVS_RASTER_DECLARE)
+#elif defined(PGDVS_RASTER_PART)
+PGDVS_RASTER_FOR_PART(PGDVS_RASTER_PART, PGDVS_RASTER_DEFINE)
+#endif
+
 }  // namespace pgdvs
 
+#if !defined(PGDVS_RASTER_PART) || PGDVS_RASTER_PART == 0
 using namespace pgdvs;
 
 extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace_bytes, int N,
@@ -725,6 +831,7 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   // fp32 r*r, as `radius2 = radius * radius` upstream; negative selects the per-point path
   p.r2 = per_point_radius ? -1.0f : radius_max * radius_max;
   p.rr_weight = rr_weight;
+  p.inv_rr_weight = 1.0f / rr_weight;
   p.compositor = compositor;
   for (int c = 0; c < 4; ++c) p.bg[c] = (background != nullptr && c < C) ? background[c] : 0.0f;
   p.static_rgb = static_rgb;
@@ -747,3 +854,4 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   if (K <= 64) return launch_raster<64>(p, stream);
   return launch_raster<PGDVS_MAX_POINTS_PER_PIXEL>(p, stream);
 }
+#endif  // part 0 / single translation unit
