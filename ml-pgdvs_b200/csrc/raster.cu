@@ -455,6 +455,9 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   __shared__ int s_max;          // most candidates any pixel of the tile walks
   __shared__ int s_hist[64];
   __shared__ unsigned char s_perm[256];
+  __shared__ float s_xf[kTileW], s_yf[kTileH];  // NDC pixel centres of the tile's columns / rows
+  __shared__ int2 s_runs[SPAN][256];            // per pixel: (start, length) of each window-row run
+  __shared__ __align__(16) uint16_t s_win[256 * KP];  // per pixel: its K winners (staged slots)
 
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -470,6 +473,9 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
     s_max = 0;
   }
   if (tid < 64) s_hist[tid] = 0;
+  // pixel centres once per CTA (each costs an IEEE division); warps 1 and 2, warp 0 is busy below
+  if (tid >= 32 && tid < 32 + kTileW) s_xf[tid - 32] = pixel_center_ndc(p.ax, x0 + tid - 32);
+  if (tid >= 64 && tid < 64 + kTileH) s_yf[tid - 64] = pixel_center_ndc(p.ay, y0 + tid - 64);
   __syncthreads();
 
   // ---- warp 0 first: size the row runs, decide, arm the barrier, issue the bulk copies; they
@@ -519,13 +525,30 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   // ---- balance the warps: hand the tile's pixels to threads in order of their candidate count
   //      (counting sort in shared memory) so that the lanes of a warp walk runs of similar
   //      length; the largest count also sizes the payload field of the keys
+  int rs[SPAN], rl[SPAN];  // start (global record index) and length of each window-row run
+  int mine = tid;          // tile-local index (row * 32 + column) of the pixel this thread walks
   {
+    // coalesced read of the runs of the thread's own (identity) pixel; the thread that ends up
+    // walking the pixel picks them up from shared memory
     int work = 0;
-    if (x < p.W && y < p.H) {
-      const int* __restrict__ c0p = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
 #pragma unroll
-      for (int ry = 0; ry < SPAN; ++ry) work += __ldg(c0p + ry * p.GW + SPAN) - __ldg(c0p + ry * p.GW);
+    for (int r = 0; r < SPAN; ++r) {
+      rs[r] = 0;
+      rl[r] = 0;
     }
+    if (x < p.W && y < p.H) {
+      const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+#pragma unroll
+      for (int r = 0; r < SPAN; ++r) {
+        rs[r] = __ldg(cs + r * p.GW);
+        rl[r] = __ldg(cs + r * p.GW + SPAN) - rs[r];
+        work += rl[r];
+      }
+    }
+#ifndef PGDVS_RASTER_NO_SORT
+#pragma unroll
+    for (int r = 0; r < SPAN; ++r) s_runs[r][tid] = make_int2(rs[r], rl[r]);
+#endif
     const int wmax = __reduce_max_sync(0xffffffffu, work);
     if ((tid & 31) == 0) atomicMax(&s_max, wmax);
     __syncthreads();  // s_max; also s_staged / s_delta of warp 0
@@ -548,33 +571,25 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
     __syncthreads();
     s_perm[s_hist[bin] + my_rank] = (unsigned char)tid;
     __syncthreads();
-    const int mine = s_perm[tid];
+    mine = s_perm[tid];
     x = x0 + (mine & 31);
     y = y0 + (mine >> 5);
+#pragma unroll
+    for (int r = 0; r < SPAN; ++r) {
+      const int2 run = s_runs[r][mine];
+      rs[r] = run.x;
+      rl[r] = run.y;
+    }
 #endif
   }
   const int ly = y - y0;  // local row of this thread's pixel
 
-  // ---- every thread: its pixel constants and window runs
+  // ---- the pixel this thread walks
   const bool inside = (x < p.W) && (y < p.H);
   PixelCtx c;
-  c.xf = pixel_center_ndc(p.ax, x);
-  c.yf = pixel_center_ndc(p.ay, y);
+  c.xf = s_xf[x - x0];
+  c.yf = s_yf[ly];
   c.r2 = p.r2;
-  int rs[SPAN], rl[SPAN];  // start (global record index) and length of each window-row run
-#pragma unroll
-  for (int r = 0; r < SPAN; ++r) {
-    rs[r] = 0;
-    rl[r] = 0;
-  }
-  if (inside) {
-    const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
-#pragma unroll
-    for (int r = 0; r < SPAN; ++r) {
-      rs[r] = __ldg(cs + r * p.GW);
-      rl[r] = __ldg(cs + r * p.GW + SPAN) - rs[r];
-    }
-  }
   const int n_staged = s_staged;
   const bool staged = n_staged != 0;
   if (staged) {
@@ -671,8 +686,6 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
       }
     }
   }
-  if (!inside) return;
-
   // ordinal -> record slot (shared-memory slot when staged: rs[] already carries s_delta)
   Slots<KP> sl;
   if (HALO == 1) {
@@ -696,11 +709,71 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
       sl.s[i] = (q.k[i] != kEmpty) ? j : -1;
     }
   }
-  const bool amb = (KP <= 32 && p.K == KP) ? q.ambiguous_full(kc) : q.ambiguous(p.K, kc);
-  if (amb || !staged) {
-    finish_global<KP, false>(p, c, n, x, y, sl, amb);
+  const bool amb = inside && ((KP <= 32 && p.K == KP) ? q.ambiguous_full(kc) : q.ambiguous(p.K, kc));
+  if (!staged) {  // (uniform) slots are global indices: finish in walk order
+    if (inside) finish_global<KP, false>(p, c, n, x, y, sl, amb);
     return;
   }
+#ifndef PGDVS_RASTER_NO_SORT
+  // ---- hand the winners back to the pixel's own thread: the epilogue then runs in raster order,
+  //      so fragment / image / mask stores and the static-frame loads are coalesced again and
+  //      neighbouring lanes mostly read the same staged records
+  constexpr uint16_t kNone = 0xFFFFu, kDone = 0xFFFEu;  // staged slots are < smem_records < 0xFFFE
+  if (amb) finish_global<KP, false>(p, c, n, x, y, sl, true);  // rare: the walker finishes it
+  {
+    uint16_t* dst = s_win + mine * KP;
+    if (KP % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < KP; i += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const uint32_t lo = (sl.s[i + 2 * h] < 0) ? kNone : (uint32_t)sl.s[i + 2 * h];
+          const uint32_t hi = (sl.s[i + 2 * h + 1] < 0) ? kNone : (uint32_t)sl.s[i + 2 * h + 1];
+          w[h] = lo | (hi << 16);
+        }
+        if (i == 0 && amb) w[0] = (w[0] & 0xFFFF0000u) | kDone;
+        *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KP; ++i) dst[i] = (sl.s[i] < 0) ? kNone : (uint16_t)sl.s[i];
+      if (amb) dst[0] = kDone;
+    }
+  }
+  __syncthreads();
+  x = x0 + threadIdx.x;
+  y = y0 + threadIdx.y;
+  if (x >= p.W || y >= p.H) return;
+  {
+    const uint16_t* src = s_win + tid * KP;
+    if (KP % 8 == 0) {
+#pragma unroll
+      for (int i = 0; i < KP; i += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const uint32_t lo = w[h] & 0xFFFFu, hi = w[h] >> 16;
+          sl.s[i + 2 * h] = (lo >= kDone) ? -1 - (int)(kNone - lo) : (int)lo;  // kNone -> -1, kDone -> -2
+          sl.s[i + 2 * h + 1] = (hi == kNone) ? -1 : (int)hi;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < KP; ++i) sl.s[i] = (src[i] >= kDone) ? -1 - (int)(kNone - src[i]) : (int)src[i];
+    }
+  }
+  if (sl.s[0] == -2) return;  // finished by its walker
+  c.xf = s_xf[threadIdx.x];
+  c.yf = s_yf[threadIdx.y];
+#else
+  if (!inside) return;
+  if (amb) {
+    finish_global<KP, false>(p, c, n, x, y, sl, true);
+    return;
+  }
+#endif
   if (KP <= 32 && p.K == KP)
     pixel_epilogue<KP, true>(p, sl, c, n, x, y, s_rec);
   else
@@ -725,7 +798,7 @@ static bool launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, 
   if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) return false;
   int smem = (int)need;
   if (smem < 24 * 1024) smem = 24 * 1024;
-  smem = (smem + 8191) & ~8191;
+  smem = (smem + 1023) & ~1023;
   if (HALO == 1 && smem < PGDVS_RASTER_SMEM_BYTES) smem = PGDVS_RASTER_SMEM_BYTES;
   p.smem_records = smem / (int)(kRecStride * sizeof(float4));
   static int attr_smem = 0;  // per instantiation: raise the opt-in limit when needed
@@ -743,9 +816,11 @@ int launch_raster(RasterParams& p, cudaStream_t stream) {
   dim3 grid((p.W + 31) / 32, (p.H + 7) / 8, p.N);
   bool done = false;
 #ifndef PGDVS_RASTER_NO_TMA
-  if (p.r2 >= 0.0f && KP <= 32) {
+  if constexpr (KP <= 32) {
     const double density = p.density;
-    if (p.halo == 1)
+    if (p.r2 < 0.0f)
+      done = false;  // per-point radii: generic kernel
+    else if (p.halo == 1)
       done = launch_tile<KP, 1>(p, grid, block, density, stream);
     else if (p.halo == 2)
       done = launch_tile<KP, 2>(p, grid, block, density, stream);
@@ -844,6 +919,10 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   // mean points per pixel of the batch (P is the capacity of the packed cloud: an upper bound)
   p.density = (double)P / ((double)N * (double)H * (double)W);
 
+#ifdef PGDVS_RASTER_EXP_K8  // developer experiments (tools/exp_variants.py): one instantiation
+  if (K > 4 && K <= 8) return launch_raster<8>(p, stream);
+  return PGDVS_E_BADARG;
+#else
   if (K <= 1) return launch_raster<1>(p, stream);
   if (K <= 2) return launch_raster<2>(p, stream);
   if (K <= 3) return launch_raster<3>(p, stream);
@@ -853,5 +932,6 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   if (K <= 32) return launch_raster<32>(p, stream);
   if (K <= 64) return launch_raster<64>(p, stream);
   return launch_raster<PGDVS_MAX_POINTS_PER_PIXEL>(p, stream);
+#endif
 }
 #endif  // part 0 / single translation unit

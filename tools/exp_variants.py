@@ -10,13 +10,17 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 OUT = ROOT / "exp_libs"
+K8 = ["-DPGDVS_RASTER_EXP_K8"]  # only the K=8 instantiation: seconds instead of minutes per variant
 VARIANTS = {
-    "tma": [],
-    "tma_sort": ["-DPGDVS_RASTER_SORT"],
-    "no_tma": ["-DPGDVS_RASTER_NO_TMA"],
-    "tma_64k": ["-DPGDVS_RASTER_SMEM_BYTES=65536"],
-    "tma_24k": ["-DPGDVS_RASTER_SMEM_BYTES=24576"],
+    "base": K8,
+    "no_sort": K8 + ["-DPGDVS_RASTER_NO_SORT"],
+    "mb5": K8 + ["-DPGDVS_TILE_MINBLOCKS_K8=5"],
+    "mb6_33k": K8 + ["-DPGDVS_TILE_MINBLOCKS_K8=6", "-DPGDVS_RASTER_SMEM_BYTES=32768"],
+    "mb5_33k": K8 + ["-DPGDVS_TILE_MINBLOCKS_K8=5", "-DPGDVS_RASTER_SMEM_BYTES=32768"],
+    "mb3": K8 + ["-DPGDVS_TILE_MINBLOCKS_K8=3"],
 }
+if os.environ.get("VARIANTS"):
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ["VARIANTS"].split(",")}
 SRCS = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu"]
 
 
