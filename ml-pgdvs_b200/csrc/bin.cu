@@ -65,14 +65,14 @@ __global__ void __launch_bounds__(256) k_fill(BinParams p) {
     a.y = __ldg(p.points + q * 3 + 1);
     a.z = __ldg(p.points + q * 3 + 2);
     a.w = __int_as_float((int)q);
-    p.recA[kRecStride * pos] = a;
+    p.recA[rec_a(pos)] = a;
     if (p.features != nullptr || p.radius != nullptr) {
       float f[4] = {0.f, 0.f, 0.f, 0.f};
       if (p.features != nullptr) {
         for (int c = 0; c < p.C; ++c) f[c] = __ldg(p.features + q * p.C + c);
       }
       if (p.radius != nullptr) f[3] = __ldg(p.radius + q);
-      p.recB[kRecStride * pos] = make_float4(f[0], f[1], f[2], f[3]);
+      p.recA[rec_b(pos)] = make_float4(f[0], f[1], f[2], f[3]);
     }
   }
 }
@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(256) k_fill_pre(BinParams p) {
 #pragma unroll
   for (int u = 0; u < kFillUnroll; ++u) {
     if (pos[u] >= 0) {
-      p.recA[kRecStride * pos[u]] = a[u];
-      p.recB[kRecStride * pos[u]] = b[u];
+      p.recA[rec_a(pos[u])] = a[u];
+      p.recA[rec_b(pos[u])] = b[u];
     }
   }
 }

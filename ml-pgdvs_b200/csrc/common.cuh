@@ -84,6 +84,19 @@ constexpr int kScanTile = 4096;  // ints per scan tile (1024 threads x int4)
 // 2: recA/recB interleaved as one 32-byte record per point; 1: two separate float4 arrays
 constexpr int kRecStride = PGDVS_REC_STRIDE;
 
+// Record j is 32 bytes: part A (x_ndc, y_ndc, z, packed idx) and part B (features / radius).
+// The two 16-byte halves swap places every 4 records: rec_a / rec_b give the float4 index of a
+// part relative to the record array.  A warp that reads the A parts of arbitrary records with
+// 128-bit shared-memory loads then spreads over all 8 four-bank groups instead of 4 (a plain
+// 32-byte stride would leave the odd groups to the B parts only).  The staging copy keeps
+// (shared slot - global slot) a multiple of 8 so both sides agree on which half is which.
+__host__ __device__ __forceinline__ int rec_a(int j) {
+  const unsigned u = (unsigned)j;  // unsigned: plain shifts, no sign fix-ups
+  return (int)((u << 1) | ((u >> 2) & 1u));
+}
+__host__ __device__ __forceinline__ int rec_b(int j) { return rec_a(j) ^ 1; }
+static_assert(PGDVS_REC_STRIDE == 2, "records are interleaved 32-byte pairs");
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 inline int halo_cells(float radius_max, int H, int W) {

@@ -27,8 +27,8 @@ namespace pgdvs {
 
 struct RasterParams {
   const int* cell_end;  // per-cell END offsets; start(c) = cell_end[c - 1] (cell_end[-1] == 0)
-  const float4* recA;   // records, stride kRecStride float4: (x_ndc, y_ndc, z, packed idx)
-  const float4* recB;   //                                     (f0, f1, f2, f3 | radius)
+  const float4* recA;   // 32-byte records; part A (x_ndc, y_ndc, z, packed idx) at [rec_a(j)],
+                        // part B (f0, f1, f2, f3 | radius) at [rec_b(j)]  (common.cuh)
   int N, H, W, K, C, halo, GW, GH;
   NdcAxis ax, ay;
   float r2;          // scalar radius^2 (fp32 r*r) or < 0: per-point radius in recB.w
@@ -47,14 +47,13 @@ struct RasterParams {
 };
 
 constexpr float kInf = __builtin_huge_valf();
-static_assert(kRecStride == 2, "the rasterizer expects interleaved 32-byte records (A at 2j, B at 2j+1)");
 
 // candidate (z, idx) strictly before list element (ze, slot se)?  Total order (z, idx).
 __device__ __forceinline__ bool cand_less(float z, int idx, float ze, int se,
                                           const float4* __restrict__ recA) {
   bool lt = z < ze;
   if (z == ze) {  // exact fp32 z tie -> smaller packed index first
-    lt = (se < 0) ? true : (idx < __float_as_int(recA[kRecStride * se].w));
+    lt = (se < 0) ? true : (idx < __float_as_int(recA[rec_a(se)].w));
   }
   return lt;
 }
@@ -124,6 +123,26 @@ struct KeyList {
     }
     rej = min(rej, max(c, prev));
   }
+  // Two candidates at once: the i-th smallest of list + {lo, hi} is
+  //   min(k[i], max(k[i-1], lo), max(k[i-2], hi))
+  // i.e. 3 ops per slot per PAIR with the 3-input integer min (VIMNMX3) instead of 2 per
+  // slot per candidate.
+  __device__ __forceinline__ void insert2(uint32_t c1, uint32_t c2) {
+    static_assert(KP >= 2, "insert2 needs two slots");
+    const uint32_t lo = min(c1, c2), hi = max(c1, c2);
+    uint32_t p2 = k[0], p1 = k[1];  // old k[i-2], k[i-1]
+    k[0] = min(p2, lo);
+    k[1] = min(min(p1, max(p2, lo)), hi);
+#pragma unroll
+    for (int i = 2; i < KP; ++i) {
+      const uint32_t cur = k[i];
+      k[i] = min(min(cur, max(p1, lo)), max(p2, hi));
+      p2 = p1;
+      p1 = cur;
+    }
+    // the two that fall off: the smaller of them is the KP-th smallest of the union
+    rej = min(min(rej, max(p1, lo)), max(p2, hi));
+  }
   // small K: always the branch-free chain (a miss is kEmpty and changes nothing);
   // large K: skip the 2*KP-op chain for keys that cannot enter the list
   __device__ __forceinline__ void push(uint32_t c) {
@@ -189,11 +208,11 @@ struct PixelCtx {
 // PPR = per-point radius (recB.w); the scalar-radius instantiation carries no extra load/branch
 template <bool PPR>
 __device__ __forceinline__ bool hit_test(const PixelCtx& c, const float4 a,
-                                         const float4* __restrict__ recB, int j) {
+                                         const float4* __restrict__ rec, int j) {
   const float d2 = dist2_rn(a.x, a.y, c.xf, c.yf);
   float r2 = c.r2;
   if (PPR) {
-    const float r = __ldg(&recB[kRecStride * j].w);
+    const float r = __ldg(&rec[rec_b(j)].w);
     r2 = __fmul_rn(r, r);
   }
   return d2 < r2;
@@ -212,8 +231,8 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
     const int s = __ldg(p.cell_end + cell0 - 1);
     const int e = __ldg(p.cell_end + cell0 + span - 1);
     for (int j = s; j < e; ++j) {
-      const float4 a = __ldg(p.recA + kRecStride * j);
-      if (hit_test<PPR>(c, a, p.recB, j)) q.insert_exact(a.z, __float_as_int(a.w), j, p.recA);
+      const float4 a = __ldg(p.recA + rec_a(j));
+      if (hit_test<PPR>(c, a, p.recA, j)) q.insert_exact(a.z, __float_as_int(a.w), j, p.recA);
     }
   }
 #pragma unroll
@@ -246,9 +265,14 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
     for (int ch = 0; ch < 4; ++ch)
       if (ch < p.C) st[ch] = __ldg(p.static_rgb + pix * p.C + ch);
   }
-  // pass 1: fragments (idx / zbuf / dists) and the PointsRenderer weights
-  float w[KP];
-  float t_alpha = 0.f;
+  // One pass over the K winners: fragments (idx / zbuf / dists, bit-exact), the PointsRenderer
+  // weight 1 - dists/(r*r) (as a multiply by the fp32 reciprocal, like torch's CUDA division by
+  // a scalar) and the K-ordered compositor sums.  Norm-weighted sums are accumulated
+  // unnormalised and scaled once by 1/max(sum w, 1e-4) at the end; images are
+  // tolerance-matched (|delta| <= 1e-5), not bit-matched.
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float wsum = 0.f;       // the same compositor applied to all-ones features (mask render)
+  float cum_alpha = 1.0f;
   constexpr bool vec4 = FULLK && (KP % 4 == 0);  // K*4 B per pixel is a multiple of 16 B
 #pragma unroll
   for (int k0 = 0; k0 < KP; k0 += 4) {
@@ -261,17 +285,26 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
       o_z[kk] = -1.0f;
       o_d[kk] = -1.0f;
       if (k < KP) {
-        w[k] = 0.f;
         const int s = (k < K) ? sl.s[k] : -1;
         if (s >= 0) {
-          const float4 a = rec[kRecStride * s];
+          const float4 a = rec[rec_a(s)];
           o_d[kk] = dist2_rn(a.x, a.y, c.xf, c.yf);
           o_idx[kk] = __float_as_int(a.w);
           o_z[kk] = a.z;
-          // PointsRenderer: 1 - dists/(r*r), applied as a multiply by the fp32 reciprocal
-          // (|delta w| <= 2e-7; images are tolerance-matched, fragments are bit-exact)
-          w[k] = __fsub_rn(1.0f, __fmul_rn(o_d[kk], p.inv_rr_weight));
-          t_alpha = __fadd_rn(t_alpha, w[k]);
+          if (mode != PGDVS_COMPOSITE_NONE) {
+            const float4 f4 = rec[rec_b(s)];
+            const float w = __fsub_rn(1.0f, __fmul_rn(o_d[kk], p.inv_rr_weight));
+            float wk = w;
+            if (mode == PGDVS_COMPOSITE_ALPHA) {
+              wk = __fmul_rn(cum_alpha, w);
+              cum_alpha = __fmul_rn(cum_alpha, __fsub_rn(1.0f, w));
+            }
+            acc[0] = __fadd_rn(acc[0], __fmul_rn(wk, f4.x));
+            acc[1] = __fadd_rn(acc[1], __fmul_rn(wk, f4.y));
+            acc[2] = __fadd_rn(acc[2], __fmul_rn(wk, f4.z));
+            acc[3] = __fadd_rn(acc[3], __fmul_rn(wk, f4.w));
+            wsum = __fadd_rn(wsum, wk);
+          }
         }
       }
     }
@@ -293,46 +326,34 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
     }
   }
   if (mode == PGDVS_COMPOSITE_NONE) return;
-  if (t_alpha < 0.25f && sl.s[0] >= 0) {
-    // ill-conditioned normalisation (every hit sits near the rim of its splat): the 1-ulp
-    // slack of the reciprocal would be amplified by 1/sum(w), so redo these few pixels with
-    // the true division
-    t_alpha = 0.f;
+  float ones_acc = wsum;
+  if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
+    if (wsum < 0.25f && sl.s[0] >= 0) {
+      // ill-conditioned normalisation (every hit sits near the rim of its splat): the 1-ulp
+      // slack of the reciprocal would be amplified by 1/sum(w), so redo these few pixels with
+      // the true division
+      wsum = 0.f;
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      if (k < K && sl.s[k] >= 0) {
-        const float4 a = rec[kRecStride * sl.s[k]];
-        w[k] = __fsub_rn(1.0f, __fdiv_rn(dist2_rn(a.x, a.y, c.xf, c.yf), p.rr_weight));
-        t_alpha = __fadd_rn(t_alpha, w[k]);
+      for (int ch = 0; ch < 4; ++ch) acc[ch] = 0.f;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        const int s = (k < K) ? sl.s[k] : -1;
+        if (s >= 0) {
+          const float4 a = rec[rec_a(s)];
+          const float4 f4 = rec[rec_b(s)];
+          const float w = __fsub_rn(1.0f, __fdiv_rn(dist2_rn(a.x, a.y, c.xf, c.yf), p.rr_weight));
+          acc[0] = __fadd_rn(acc[0], __fmul_rn(w, f4.x));
+          acc[1] = __fadd_rn(acc[1], __fmul_rn(w, f4.y));
+          acc[2] = __fadd_rn(acc[2], __fmul_rn(w, f4.z));
+          acc[3] = __fadd_rn(acc[3], __fmul_rn(w, f4.w));
+          wsum = __fadd_rn(wsum, w);
+        }
       }
     }
-  }
-
-  // pass 2: compositor.  The K-ordered accumulation follows the pytorch3d CPU loops; the
-  // norm-weighted division by max(sum w, 1e-4) is applied as one reciprocal multiply
-  // (images are tolerance-matched, |delta| <= 1e-5; fragments above are bit-exact).
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float ones_acc = 0.f;  // the same compositor applied to all-ones features (mask render)
-  float cum_alpha = 1.0f;
-  const float inv_t = __frcp_rn(fmaxf(t_alpha, 1e-4f));
+    const float inv_t = __frcp_rn(fmaxf(wsum, 1e-4f));
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    if (k < K && sl.s[k] >= 0) {
-      const float4 f4 = rec[kRecStride * sl.s[k] + 1];
-      float wk = w[k];
-      if (mode == PGDVS_COMPOSITE_NORM_WEIGHTED) {
-        wk = __fmul_rn(wk, inv_t);
-      } else if (mode == PGDVS_COMPOSITE_ALPHA) {
-        const float a = wk;
-        wk = __fmul_rn(cum_alpha, a);
-        cum_alpha = __fmul_rn(cum_alpha, __fsub_rn(1.0f, a));
-      }
-      acc[0] = __fadd_rn(acc[0], __fmul_rn(wk, f4.x));
-      acc[1] = __fadd_rn(acc[1], __fmul_rn(wk, f4.y));
-      acc[2] = __fadd_rn(acc[2], __fmul_rn(wk, f4.z));
-      acc[3] = __fadd_rn(acc[3], __fmul_rn(wk, f4.w));
-      ones_acc = __fadd_rn(ones_acc, wk);
-    }
+    for (int ch = 0; ch < 4; ++ch) acc[ch] = __fmul_rn(acc[ch], inv_t);
+    ones_acc = __fmul_rn(wsum, inv_t);
   }
   const bool is_bg = sl.s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
   const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
@@ -381,7 +402,6 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
   c.yf = pixel_center_ndc(p.ay, y);
   c.r2 = p.r2;
   const float4* __restrict__ recA = p.recA;
-  const float4* __restrict__ recB = p.recB;
 
   const int span = 2 * p.halo + 1;
   // cs[c] = start of cell (x + c) of the first window row = cell_end[... - 1]
@@ -399,8 +419,8 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
     const int s = __ldg(cs + (int64_t)ry * p.GW);
     const int e = __ldg(cs + (int64_t)ry * p.GW + span);
     for (int j = s; j < e; ++j, ++t) {
-      const float4 a = __ldg(recA + kRecStride * j);
-      q.push(kc.encode(hit_test<PPR>(c, a, recB, j), a.z, t));
+      const float4 a = __ldg(recA + rec_a(j));
+      q.push(kc.encode(hit_test<PPR>(c, a, recA, j), a.z, t));
     }
   }
   Slots<KP> sl;
@@ -438,7 +458,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 #ifndef PGDVS_TILE_MINBLOCKS_K8
-#define PGDVS_TILE_MINBLOCKS_K8 4
+#define PGDVS_TILE_MINBLOCKS_K8 5
 #endif
 
 template <int KP, int HALO>
@@ -447,17 +467,22 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   constexpr int ROWS = kTileH + 2 * HALO;  // extended-grid rows the tile's pixels can touch
   static_assert(ROWS <= 32, "one lane per tile row");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4* s_rec = reinterpret_cast<float4*>(smem_raw);  // staged records (kRecStride float4 each)
+  float4* s_rec = reinterpret_cast<float4*>(smem_raw);  // staged records (32 bytes each)
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_delta[ROWS];  // smem record index = global record index + s_delta[row]
+  __shared__ int2 s_row[ROWS];   // (first shared slot, records) of every staged row
   __shared__ int s_staged;       // records staged (> 0: the tile's runs fit and are being copied)
   __shared__ uint32_t s_zlo, s_zhi;  // range of the staged z bit patterns (KeyCode)
   __shared__ int s_max;          // most candidates any pixel of the tile walks
   __shared__ int s_hist[64];
   __shared__ unsigned char s_perm[256];
   __shared__ float s_xf[kTileW], s_yf[kTileH];  // NDC pixel centres of the tile's columns / rows
-  __shared__ int2 s_runs[SPAN][256];            // per pixel: (start, length) of each window-row run
-  __shared__ __align__(16) uint16_t s_win[256 * KP];  // per pixel: its K winners (staged slots)
+  // one scratch area, two lives: before the walk, per pixel the (start, length) of each window-row
+  // run; after it (separated by barriers), per pixel its K winners as 16-bit staged slots
+  constexpr int kScratchBytes = (SPAN * 256 * 8 > 256 * KP * 2) ? SPAN * 256 * 8 : 256 * KP * 2;
+  __shared__ __align__(16) unsigned char s_scratch[kScratchBytes];
+  int2(*s_runs)[256] = reinterpret_cast<int2(*)[256]>(s_scratch);
+  uint16_t* s_win = reinterpret_cast<uint16_t*>(s_scratch);
 
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
@@ -492,28 +517,39 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
       ge = __ldg(p.cell_end + rb + xe);
     }
     const int len = ge - gs;
-    int inc = len;  // inclusive prefix over the rows -> smem offsets
+    // Row r is staged at shared slot base_r + (gs & 7), base_r a multiple of 8: shared slot and
+    // global slot of a record then differ by a multiple of 8, so rec_a()/rec_b() pick the same
+    // half of the 32-byte record on both sides.  pad_len = footprint incl. that lead-in, x8.
+    const int pad_len = (len > 0) ? (((gs & 7) + len + 7) & ~7) : 0;
+    int inc = pad_len;  // inclusive prefix over the rows -> smem offsets
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int o = __shfl_up_sync(0xffffffffu, inc, d);
       if (lane >= d) inc += o;
     }
-    const int total = __shfl_sync(0xffffffffu, inc, ROWS - 1);
+    const int total = __shfl_sync(0xffffffffu, inc, ROWS - 1);  // padded footprint of the tile
+    int cnt = len;  // records actually copied
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     const bool fits = total <= p.smem_records;
-    if (lane < ROWS) s_delta[lane] = fits ? (inc - len) - gs : 0;
+    const int dst_slot = (inc - pad_len) + (gs & 7);
+    if (lane < ROWS) {
+      s_delta[lane] = fits ? dst_slot - gs : 0;
+      s_row[lane] = make_int2(dst_slot, len);
+    }
     if (lane == 0) {
-      s_staged = fits ? total : 0;
+      s_staged = fits ? cnt : 0;
       if (fits) {
-        const uint32_t bytes = (uint32_t)total * (uint32_t)(kRecStride * sizeof(float4));
+        const uint32_t bytes = (uint32_t)cnt * 32u;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes)
                      : "memory");
       }
     }
     __syncwarp();
     if (fits && lane < ROWS && len > 0) {
-      const float4* src = p.recA + (int64_t)kRecStride * gs;
-      float4* dst = s_rec + (int64_t)kRecStride * (inc - len);
-      const uint32_t bytes = (uint32_t)len * (uint32_t)(kRecStride * sizeof(float4));
+      const float4* src = p.recA + (int64_t)2 * gs;
+      float4* dst = s_rec + 2 * dst_slot;
+      const uint32_t bytes = (uint32_t)len * 32u;
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
               smem_u32(dst)),
@@ -609,10 +645,13 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
     for (int r = 0; r < SPAN; ++r) rs[r] += s_delta[ly + r];
     // z range of the tile -> keys that order exactly like z (see KeyCode)
     uint32_t lo = 0xFFFFFFFFu, hi = 0u;
-    for (int i = tid; i < n_staged; i += 256) {
-      const uint32_t zb = __float_as_uint(__fadd_rn(s_rec[kRecStride * i].z, 0.0f));
-      lo = min(lo, zb);
-      hi = max(hi, zb);
+    for (int r = threadIdx.y; r < ROWS; r += kTileH) {  // one warp per staged row
+      const int2 row = s_row[r];
+      for (int i = threadIdx.x; i < row.y; i += 32) {
+        const uint32_t zb = __float_as_uint(__fadd_rn(s_rec[rec_a(row.x + i)].z, 0.0f));
+        lo = min(lo, zb);
+        hi = max(hi, zb);
+      }
     }
     lo = __reduce_min_sync(0xffffffffu, lo);
     hi = __reduce_max_sync(0xffffffffu, hi);
@@ -641,28 +680,33 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
         // exact keys: key = (zb - base) * 2^bits + t as ONE multiply-add (modulo 2^32)
         const uint32_t mul = 1u << kc.bits;
         uint32_t tk = 0u - kc.base * mul;
-        for (int t = 0; t < total; ++t, ++tk) {
+        auto key_at = [&](int t, uint32_t tkey) {
           const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-          const float4 a = s_rec[kRecStride * j];
-          const uint32_t key = __float_as_uint(__fadd_rn(a.z, 0.0f)) * mul + tk;
-          q.push(hit_test<false>(c, a, nullptr, j) ? key : kEmpty);
+          const float4 a = s_rec[rec_a(j)];
+          const uint32_t key = __float_as_uint(__fadd_rn(a.z, 0.0f)) * mul + tkey;
+          return hit_test<false>(c, a, nullptr, j) ? key : kEmpty;
+        };
+        int t = 0;
+        if constexpr (KP >= 2 && KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
+          for (; t + 1 < total; t += 2, tk += 2) q.insert2(key_at(t, tk), key_at(t + 1, tk + 1));
         }
+        for (; t < total; ++t, ++tk) q.push(key_at(t, tk));
       } else {
         for (int t = 0; t < total; ++t) {
           const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-          const float4 a = s_rec[kRecStride * j];
+          const float4 a = s_rec[rec_a(j)];
           q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
         }
       }
     } else {
       // software-pipelined global reads: record t+1 is in flight while t is processed
       int j = (0 < c0 ? s0 : (0 < c01 ? o1 : o2));
-      float4 a = (total > 0) ? __ldg(p.recA + kRecStride * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 a = (total > 0) ? __ldg(p.recA + rec_a(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int t = 0; t < total; ++t) {
         const int tn = t + 1;
         const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
         float4 an = a;
-        if (tn < total) an = __ldg(p.recA + kRecStride * jn);
+        if (tn < total) an = __ldg(p.recA + rec_a(jn));
         q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
         a = an;
         j = jn;
@@ -675,12 +719,12 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
       const int s = rs[r], e = rs[r] + rl[r];
       if (staged) {
         for (int j = s; j < e; ++j, ++t) {
-          const float4 a = s_rec[kRecStride * j];
+          const float4 a = s_rec[rec_a(j)];
           q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
         }
       } else {
         for (int j = s; j < e; ++j, ++t) {
-          const float4 a = __ldg(p.recA + kRecStride * j);
+          const float4 a = __ldg(p.recA + rec_a(j));
           q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
         }
       }
@@ -781,7 +825,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
 }
 
 #ifndef PGDVS_RASTER_SMEM_BYTES
-#define PGDVS_RASTER_SMEM_BYTES (40 * 1024)
+#define PGDVS_RASTER_SMEM_BYTES (24 * 1024)
 #endif
 #ifndef PGDVS_RASTER_SMEM_BYTES_WIDE
 #define PGDVS_RASTER_SMEM_BYTES_WIDE (100 * 1024)
@@ -794,13 +838,16 @@ static bool launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, 
   // If even the mean tile would not fit in PGDVS_RASTER_SMEM_BYTES_WIDE, the generic kernel
   // (more resident CTAs, no staging) is the better choice.
   const double tile_cells = (double)(kTileW + 2 * HALO) * (kTileH + 2 * HALO);
-  const double need = 1.5 * density * tile_cells * (double)(kRecStride * sizeof(float4));
+#ifndef PGDVS_RASTER_HEADROOM
+#define PGDVS_RASTER_HEADROOM 1.5
+#endif
+  const double need = PGDVS_RASTER_HEADROOM * density * tile_cells * 32.0;
   if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) return false;
   int smem = (int)need;
   if (smem < 24 * 1024) smem = 24 * 1024;
   smem = (smem + 1023) & ~1023;
   if (HALO == 1 && smem < PGDVS_RASTER_SMEM_BYTES) smem = PGDVS_RASTER_SMEM_BYTES;
-  p.smem_records = smem / (int)(kRecStride * sizeof(float4));
+  p.smem_records = smem / 32;
   static int attr_smem = 0;  // per instantiation: raise the opt-in limit when needed
   if (smem > attr_smem) {
     cudaFuncSetAttribute(k_raster_tile<KP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -892,7 +939,6 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   RasterParams p;
   p.cell_end = reinterpret_cast<const int*>(ws + L.off_cells);
   p.recA = reinterpret_cast<const float4*>(ws + L.off_recA);
-  p.recB = reinterpret_cast<const float4*>(ws + L.off_recB);
   p.N = N;
   p.H = H;
   p.W = W;
