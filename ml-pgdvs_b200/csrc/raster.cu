@@ -245,15 +245,49 @@ __device__ __noinline__ void rescan_exact(const RasterParams& p, const PixelCtx&
 // the staged case compiles to LDS); s[k] < 0 = empty.  FULLK: K == KP (every loop bound is a
 // compile-time constant and fragments are written with 128-bit stores).
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
 template <int KP>
 struct Slots {
   int s[KP];
 };
 
-template <int KP, bool FULLK>
+// Where the epilogue reads the winners' records from.  The shared-memory source addresses the
+// staging buffer with 32-bit shared addresses and three integer ops per access
+// (base + 32 j, then OR in bit 4 = bit 2 of j; the buffer is 32-byte aligned).
+struct GlobalRecords {
+  const float4* p;
+  __device__ __forceinline__ float4 a(int j) const { return p[rec_a(j)]; }
+  __device__ __forceinline__ float4 b(int j) const { return p[rec_b(j)]; }
+};
+struct StagedRecords {
+  uint32_t base;  // shared-state-space address of the staging buffer
+  static __device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+  }
+  __device__ __forceinline__ uint32_t addr_a(int j) const {
+    // spelled in PTX: the C++ form gets "simplified" into twice as many instructions
+    uint32_t addr;
+    asm("{\n\t.reg .b32 t, a;\n\t"
+        "shl.b32 t, %1, 2;\n\t"
+        "mad.lo.u32 a, %1, 32, %2;\n\t"
+        "lop3.b32 %0, a, t, 16, 0xF8;\n\t}"  // a | (t & 16)
+        : "=r"(addr)
+        : "r"(j), "r"(base));
+    return addr;
+  }
+  __device__ __forceinline__ float4 a(int j) const { return lds128(addr_a(j)); }
+  __device__ __forceinline__ float4 b(int j) const { return lds128(addr_a(j) ^ 16u); }
+};
+
+template <int KP, bool FULLK, typename Records>
 __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slots<KP>& sl,
                                                const PixelCtx& c, int n, int x, int y,
-                                               const float4* rec) {
+                                               const Records rec) {
   const int K = FULLK ? KP : p.K;
   const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
   const int mode = p.compositor;
@@ -287,12 +321,12 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
       if (k < KP) {
         const int s = (k < K) ? sl.s[k] : -1;
         if (s >= 0) {
-          const float4 a = rec[rec_a(s)];
+          const float4 a = rec.a(s);
           o_d[kk] = dist2_rn(a.x, a.y, c.xf, c.yf);
           o_idx[kk] = __float_as_int(a.w);
           o_z[kk] = a.z;
           if (mode != PGDVS_COMPOSITE_NONE) {
-            const float4 f4 = rec[rec_b(s)];
+            const float4 f4 = rec.b(s);
             const float w = __fsub_rn(1.0f, __fmul_rn(o_d[kk], p.inv_rr_weight));
             float wk = w;
             if (mode == PGDVS_COMPOSITE_ALPHA) {
@@ -339,8 +373,8 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
       for (int k = 0; k < KP; ++k) {
         const int s = (k < K) ? sl.s[k] : -1;
         if (s >= 0) {
-          const float4 a = rec[rec_a(s)];
-          const float4 f4 = rec[rec_b(s)];
+          const float4 a = rec.a(s);
+          const float4 f4 = rec.b(s);
           const float w = __fsub_rn(1.0f, __fdiv_rn(dist2_rn(a.x, a.y, c.xf, c.yf), p.rr_weight));
           acc[0] = __fadd_rn(acc[0], __fmul_rn(w, f4.x));
           acc[1] = __fadd_rn(acc[1], __fmul_rn(w, f4.y));
@@ -379,9 +413,9 @@ __device__ __noinline__ void finish_global(const RasterParams& p, const PixelCtx
                                            int y, Slots<KP> sl, bool rescan) {
   if (rescan) rescan_exact<KP, PPR>(p, c, n, x, y, sl.s);
   if (KP <= 32 && p.K == KP)
-    pixel_epilogue<KP, true>(p, sl, c, n, x, y, p.recA);
+    pixel_epilogue<KP, true>(p, sl, c, n, x, y, GlobalRecords{p.recA});
   else
-    pixel_epilogue<KP, false>(p, sl, c, n, x, y, p.recA);
+    pixel_epilogue<KP, false>(p, sl, c, n, x, y, GlobalRecords{p.recA});
 }
 
 #ifndef PGDVS_RASTER_MINBLOCKS
@@ -443,19 +477,15 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
     base += len;
   }
   if (KP <= 32 && p.K == KP)
-    pixel_epilogue<KP, true>(p, sl, c, n, x, y, recA);
+    pixel_epilogue<KP, true>(p, sl, c, n, x, y, GlobalRecords{recA});
   else
-    pixel_epilogue<KP, false>(p, sl, c, n, x, y, recA);
+    pixel_epilogue<KP, false>(p, sl, c, n, x, y, GlobalRecords{recA});
 }
 
 // ---------------------------------------------------------------------------------------
 // TMA-staged tile kernel: small halos (compile-time HALO = 1..3), scalar radius.
 // ---------------------------------------------------------------------------------------
 constexpr int kTileW = 32, kTileH = 8;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
 
 #ifndef PGDVS_TILE_MINBLOCKS_K8
 #define PGDVS_TILE_MINBLOCKS_K8 5
@@ -468,6 +498,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   static_assert(ROWS <= 32, "one lane per tile row");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_rec = reinterpret_cast<float4*>(smem_raw);  // staged records (32 bytes each)
+  const StagedRecords staged_rec{smem_u32(smem_raw)};
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ int s_delta[ROWS];  // smem record index = global record index + s_delta[row]
   __shared__ int2 s_row[ROWS];   // (first shared slot, records) of every staged row
@@ -648,7 +679,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
     for (int r = threadIdx.y; r < ROWS; r += kTileH) {  // one warp per staged row
       const int2 row = s_row[r];
       for (int i = threadIdx.x; i < row.y; i += 32) {
-        const uint32_t zb = __float_as_uint(__fadd_rn(s_rec[rec_a(row.x + i)].z, 0.0f));
+        const uint32_t zb = __float_as_uint(__fadd_rn(staged_rec.a(row.x + i).z, 0.0f));
         lo = min(lo, zb);
         hi = max(hi, zb);
       }
@@ -682,8 +713,9 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
         uint32_t tk = 0u - kc.base * mul;
         auto key_at = [&](int t, uint32_t tkey) {
           const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-          const float4 a = s_rec[rec_a(j)];
-          const uint32_t key = __float_as_uint(__fadd_rn(a.z, 0.0f)) * mul + tkey;
+          const float4 a = staged_rec.a(j);
+          uint32_t key;  // one IMAD on the FMA pipe (C++ would turn it into shift + add on the ALU pipe)
+          asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(__float_as_uint(__fadd_rn(a.z, 0.0f))), "r"(mul), "r"(tkey));
           return hit_test<false>(c, a, nullptr, j) ? key : kEmpty;
         };
         int t = 0;
@@ -694,7 +726,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
       } else {
         for (int t = 0; t < total; ++t) {
           const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-          const float4 a = s_rec[rec_a(j)];
+          const float4 a = staged_rec.a(j);
           q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
         }
       }
@@ -719,7 +751,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
       const int s = rs[r], e = rs[r] + rl[r];
       if (staged) {
         for (int j = s; j < e; ++j, ++t) {
-          const float4 a = s_rec[rec_a(j)];
+          const float4 a = staged_rec.a(j);
           q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
         }
       } else {
@@ -819,9 +851,9 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   }
 #endif
   if (KP <= 32 && p.K == KP)
-    pixel_epilogue<KP, true>(p, sl, c, n, x, y, s_rec);
+    pixel_epilogue<KP, true>(p, sl, c, n, x, y, staged_rec);
   else
-    pixel_epilogue<KP, false>(p, sl, c, n, x, y, s_rec);
+    pixel_epilogue<KP, false>(p, sl, c, n, x, y, staged_rec);
 }
 
 #ifndef PGDVS_RASTER_SMEM_BYTES
