@@ -91,8 +91,20 @@ constexpr int kRecStride = PGDVS_REC_STRIDE;
 // 32-byte stride would leave the odd groups to the B parts only).  The staging copy keeps
 // (shared slot - global slot) a multiple of 8 so both sides agree on which half is which.
 __host__ __device__ __forceinline__ int rec_a(int j) {
-  const unsigned u = (unsigned)j;  // unsigned: plain shifts, no sign fix-ups
+#ifdef __CUDA_ARCH__
+  // spelled in PTX (3 instructions): the C++ form below is "simplified" into twice as many
+  unsigned r;
+  asm("{\n\t.reg .b32 t;\n\t"
+      "shr.u32 t, %1, 2;\n\t"
+      "and.b32 t, t, 1;\n\t"
+      "mad.lo.u32 %0, %1, 2, t;\n\t}"
+      : "=r"(r)
+      : "r"(j));
+  return (int)r;
+#else
+  const unsigned u = (unsigned)j;
   return (int)((u << 1) | ((u >> 2) & 1u));
+#endif
 }
 __host__ __device__ __forceinline__ int rec_b(int j) { return rec_a(j) ^ 1; }
 static_assert(PGDVS_REC_STRIDE == 2, "records are interleaved 32-byte pairs");

@@ -171,6 +171,52 @@ struct KeyList {
   }
 };
 
+// General path (long lists, unknown z range): (z, record slot) pairs ordered by z alone with a
+// compare-exchange chain that only runs for candidates nearer than the current last element.
+// Exact fp32 z ties that could change the result are DETECTED, not resolved: `tie` is set when a
+// rejected or evicted candidate had the z of the (then) last kept element — which is implied
+// whenever it ties with the final one — and ambiguous() adds ties between kept neighbours.
+// Flagged pixels are redone by rescan_exact().
+template <int KP>
+struct PairList {
+  float z[KP];
+  int s[KP];
+  bool tie;
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      z[i] = kInf;
+      s[i] = -1;
+    }
+    tie = false;
+  }
+  __device__ __forceinline__ void push(bool hit, float cz, int cs) {
+    if (!hit) return;
+    if (cz < z[KP - 1]) {
+#pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        const bool p = cz < z[i];
+        const float tz = z[i];
+        const int ts = s[i];
+        z[i] = p ? cz : tz;
+        s[i] = p ? cs : ts;
+        cz = p ? tz : cz;
+        cs = p ? ts : cs;
+      }
+      tie = tie | ((cs >= 0) & (cz == z[KP - 1]));  // (cz, cs) is now the evicted element
+    } else {
+      tie = tie | (cz == z[KP - 1]);
+    }
+  }
+  __device__ __forceinline__ bool ambiguous(int K) const {
+    bool amb = (K >= KP) & tie;
+#pragma unroll
+    for (int i = 1; i < KP; ++i)
+      if (i <= K) amb = amb | ((s[i] >= 0) & (z[i] == z[i - 1]));
+    return amb;
+  }
+};
+
 // Exact path: full (z, idx) order, (z, slot) pairs.
 template <int KP>
 struct ExactList {
@@ -440,41 +486,22 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
   const int span = 2 * p.halo + 1;
   // cs[c] = start of cell (x + c) of the first window row = cell_end[... - 1]
   const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
-  int total = 0;
-  for (int ry = 0; ry < span; ++ry)
-    total += __ldg(cs + (int64_t)ry * p.GW + span) - __ldg(cs + (int64_t)ry * p.GW);
-  KeyCode kc;
-  kc.init(total, 0u, 0x7fffffffu);
-
-  KeyList<KP> q;
+  PairList<KP> q;
   q.init();
-  uint32_t t = 0;
   for (int ry = 0; ry < span; ++ry) {
     const int s = __ldg(cs + (int64_t)ry * p.GW);
     const int e = __ldg(cs + (int64_t)ry * p.GW + span);
-    for (int j = s; j < e; ++j, ++t) {
+    for (int j = s; j < e; ++j) {
       const float4 a = __ldg(recA + rec_a(j));
-      q.push(kc.encode(hit_test<PPR>(c, a, recA, j), a.z, t));
+      q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
     }
   }
   Slots<KP> sl;
 #pragma unroll
-  for (int i = 0; i < KP; ++i) sl.s[i] = -1;
-  if (q.ambiguous(p.K, kc)) {
+  for (int i = 0; i < KP; ++i) sl.s[i] = q.s[i];
+  if (q.ambiguous(p.K)) {
     finish_global<KP, PPR>(p, c, n, x, y, sl, true);
     return;
-  }
-  // ordinal -> record slot: walk the window rows once more (cell_end is L1-resident by now)
-  int base = 0;
-  for (int ry = 0; ry < span; ++ry) {
-    const int s = __ldg(cs + (int64_t)ry * p.GW);
-    const int len = __ldg(cs + (int64_t)ry * p.GW + span) - s;
-#pragma unroll
-    for (int i = 0; i < KP; ++i) {
-      const int o = (int)(q.k[i] & kc.mask) - base;
-      if (q.k[i] != kEmpty && o >= 0 && o < len) sl.s[i] = s + o;
-    }
-    base += len;
   }
   if (KP <= 32 && p.K == KP)
     pixel_epilogue<KP, true>(p, sl, c, n, x, y, GlobalRecords{recA});
@@ -486,6 +513,35 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
 // TMA-staged tile kernel: small halos (compile-time HALO = 1..3), scalar radius.
 // ---------------------------------------------------------------------------------------
 constexpr int kTileW = 32, kTileH = 8;
+
+// Same walk with the general (z, slot) list: long lists, unstaged tiles, tiles whose z range does
+// not leave room for exact 32-bit keys.  The payload is the record slot itself.
+template <int KP, int HALO>
+__device__ __forceinline__ bool walk_tile_pairs(const RasterParams& p, const PixelCtx& c,
+                                                const int (&rs)[2 * HALO + 1], const int (&rl)[2 * HALO + 1],
+                                                bool staged, const StagedRecords staged_rec, Slots<KP>& sl) {
+  constexpr int SPAN = 2 * HALO + 1;
+  PairList<KP> q;
+  q.init();
+#pragma unroll
+  for (int r = 0; r < SPAN; ++r) {
+    const int s = rs[r], e = rs[r] + rl[r];
+    if (staged) {
+      for (int j = s; j < e; ++j) {
+        const float4 a = staged_rec.a(j);
+        q.push(hit_test<false>(c, a, nullptr, j), a.z, j);
+      }
+    } else {
+      for (int j = s; j < e; ++j) {
+        const float4 a = __ldg(p.recA + rec_a(j));
+        q.push(hit_test<false>(c, a, nullptr, j), a.z, j);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < KP; ++i) sl.s[i] = q.s[i];
+  return q.ambiguous(p.K);
+}
 
 #ifndef PGDVS_TILE_MINBLOCKS_K8
 #define PGDVS_TILE_MINBLOCKS_K8 5
@@ -692,100 +748,106 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
     }
   }
   __syncthreads();  // (uniform: `staged` is per CTA)
-  KeyCode kc;  // the same code for every pixel of the tile
-  kc.init(s_max, staged ? s_zlo : 0u, staged ? s_zhi : 0x7fffffffu);
+  // short lists: sorted 32-bit keys (KeyList); long lists: the general pair list
+  Slots<KP> sl;
+  bool amb;
+  if constexpr (KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
+    KeyCode kc;  // the same code for every pixel of the tile
+    kc.init(s_max, staged ? s_zlo : 0u, staged ? s_zhi : 0x7fffffffu);
 
-  int total = 0;
-#pragma unroll
-  for (int r = 0; r < SPAN; ++r) total += rl[r];
+    int total = 0;
+  #pragma unroll
+    for (int r = 0; r < SPAN; ++r) total += rl[r];
 
-  KeyList<KP> q;
-  q.init();
-  if (HALO == 1) {
-    // the three row runs are walked by ONE flattened loop so that lanes with uneven rows do not
-    // wait for each other three times; the body is branch-free (see KeyList)
-    const int c0 = rl[0], c01 = rl[0] + rl[1];
-    const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
-    if (staged) {
-      if (kc.sh == 0) {
-        // exact keys: key = (zb - base) * 2^bits + t as ONE multiply-add (modulo 2^32)
-        const uint32_t mul = 1u << kc.bits;
-        uint32_t tk = 0u - kc.base * mul;
-        auto key_at = [&](int t, uint32_t tkey) {
-          const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-          const float4 a = staged_rec.a(j);
-          uint32_t key;  // one IMAD on the FMA pipe (C++ would turn it into shift + add on the ALU pipe)
-          asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(__float_as_uint(__fadd_rn(a.z, 0.0f))), "r"(mul), "r"(tkey));
-          return hit_test<false>(c, a, nullptr, j) ? key : kEmpty;
-        };
-        int t = 0;
-        if constexpr (KP >= 2 && KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
-          for (; t + 1 < total; t += 2, tk += 2) q.insert2(key_at(t, tk), key_at(t + 1, tk + 1));
+    KeyList<KP> q;
+    q.init();
+    if (HALO == 1) {
+      // the three row runs are walked by ONE flattened loop so that lanes with uneven rows do not
+      // wait for each other three times; the body is branch-free (see KeyList)
+      const int c0 = rl[0], c01 = rl[0] + rl[1];
+      const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
+      if (staged) {
+        if (kc.sh == 0) {
+          // exact keys: key = (zb - base) * 2^bits + t as ONE multiply-add (modulo 2^32)
+          const uint32_t mul = 1u << kc.bits;
+          uint32_t tk = 0u - kc.base * mul;
+          auto key_at = [&](int t, uint32_t tkey) {
+            const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
+            const float4 a = staged_rec.a(j);
+            uint32_t key;  // one IMAD on the FMA pipe (C++ would turn it into shift + add on the ALU pipe)
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(__float_as_uint(__fadd_rn(a.z, 0.0f))), "r"(mul), "r"(tkey));
+            return hit_test<false>(c, a, nullptr, j) ? key : kEmpty;
+          };
+          int t = 0;
+          if constexpr (KP >= 2 && KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
+            for (; t + 1 < total; t += 2, tk += 2) q.insert2(key_at(t, tk), key_at(t + 1, tk + 1));
+          }
+          for (; t < total; ++t, ++tk) q.push(key_at(t, tk));
+        } else {
+          for (int t = 0; t < total; ++t) {
+            const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
+            const float4 a = staged_rec.a(j);
+            q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
+          }
         }
-        for (; t < total; ++t, ++tk) q.push(key_at(t, tk));
       } else {
+        // software-pipelined global reads: record t+1 is in flight while t is processed
+        int j = (0 < c0 ? s0 : (0 < c01 ? o1 : o2));
+        float4 a = (total > 0) ? __ldg(p.recA + rec_a(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < total; ++t) {
-          const int j = t + (t < c0 ? s0 : (t < c01 ? o1 : o2));
-          const float4 a = staged_rec.a(j);
+          const int tn = t + 1;
+          const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
+          float4 an = a;
+          if (tn < total) an = __ldg(p.recA + rec_a(jn));
           q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
+          a = an;
+          j = jn;
         }
       }
     } else {
-      // software-pipelined global reads: record t+1 is in flight while t is processed
-      int j = (0 < c0 ? s0 : (0 < c01 ? o1 : o2));
-      float4 a = (total > 0) ? __ldg(p.recA + rec_a(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int t = 0; t < total; ++t) {
-        const int tn = t + 1;
-        const int jn = tn + (tn < c0 ? s0 : (tn < c01 ? o1 : o2));
-        float4 an = a;
-        if (tn < total) an = __ldg(p.recA + rec_a(jn));
-        q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t));
-        a = an;
-        j = jn;
-      }
-    }
-  } else {
-    uint32_t t = 0;
-#pragma unroll
-    for (int r = 0; r < SPAN; ++r) {
-      const int s = rs[r], e = rs[r] + rl[r];
-      if (staged) {
-        for (int j = s; j < e; ++j, ++t) {
-          const float4 a = staged_rec.a(j);
-          q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
-        }
-      } else {
-        for (int j = s; j < e; ++j, ++t) {
-          const float4 a = __ldg(p.recA + rec_a(j));
-          q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
-        }
-      }
-    }
-  }
-  // ordinal -> record slot (shared-memory slot when staged: rs[] already carries s_delta)
-  Slots<KP> sl;
-  if (HALO == 1) {
-    const int c0 = rl[0], c01 = rl[0] + rl[1];
-    const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
-#pragma unroll
-    for (int i = 0; i < KP; ++i) {
-      const int o = (int)(q.k[i] & kc.mask);
-      sl.s[i] = (q.k[i] != kEmpty) ? o + (o < c0 ? s0 : (o < c01 ? o1 : o2)) : -1;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < KP; ++i) {
-      int o = (int)(q.k[i] & kc.mask);
-      int j = -1;
-#pragma unroll
+      uint32_t t = 0;
+  #pragma unroll
       for (int r = 0; r < SPAN; ++r) {
-        if (j < 0 && o < rl[r]) j = rs[r] + o;
-        o -= rl[r];
+        const int s = rs[r], e = rs[r] + rl[r];
+        if (staged) {
+          for (int j = s; j < e; ++j, ++t) {
+            const float4 a = staged_rec.a(j);
+            q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
+          }
+        } else {
+          for (int j = s; j < e; ++j, ++t) {
+            const float4 a = __ldg(p.recA + rec_a(j));
+            q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
+          }
+        }
       }
-      sl.s[i] = (q.k[i] != kEmpty) ? j : -1;
     }
+    // ordinal -> record slot (shared-memory slot when staged: rs[] already carries s_delta)
+    if (HALO == 1) {
+      const int c0 = rl[0], c01 = rl[0] + rl[1];
+      const int s0 = rs[0], o1 = rs[1] - c0, o2 = rs[2] - c01;
+  #pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        const int o = (int)(q.k[i] & kc.mask);
+        sl.s[i] = (q.k[i] != kEmpty) ? o + (o < c0 ? s0 : (o < c01 ? o1 : o2)) : -1;
+      }
+    } else {
+  #pragma unroll
+      for (int i = 0; i < KP; ++i) {
+        int o = (int)(q.k[i] & kc.mask);
+        int j = -1;
+  #pragma unroll
+        for (int r = 0; r < SPAN; ++r) {
+          if (j < 0 && o < rl[r]) j = rs[r] + o;
+          o -= rl[r];
+        }
+        sl.s[i] = (q.k[i] != kEmpty) ? j : -1;
+      }
+    }
+    amb = inside && ((KP <= 32 && p.K == KP) ? q.ambiguous_full(kc) : q.ambiguous(p.K, kc));
+  } else {
+    amb = walk_tile_pairs<KP, HALO>(p, c, rs, rl, staged, staged_rec, sl) && inside;
   }
-  const bool amb = inside && ((KP <= 32 && p.K == KP) ? q.ambiguous_full(kc) : q.ambiguous(p.K, kc));
   if (!staged) {  // (uniform) slots are global indices: finish in walk order
     if (inside) finish_global<KP, false>(p, c, n, x, y, sl, amb);
     return;

@@ -13,10 +13,9 @@ OUT = ROOT / "exp_libs"
 K8 = ["-DPGDVS_RASTER_EXP_K8"]  # only the K=8 instantiation: seconds instead of minutes per variant
 VARIANTS = {
     "base": K8,
-    "mb4": K8 + ["-DPGDVS_TILE_MINBLOCKS_K8=4"],
-    "mb6_28k": K8 + ["-DPGDVS_TILE_MINBLOCKS_K8=6", "-DPGDVS_RASTER_HEADROOM=1.25"],
-    "no_sort": K8 + ["-DPGDVS_RASTER_NO_SORT"],
 }
+if os.environ.get("PREBUILT"):  # time prebuilt exp_libs/lib_<name>.so files
+    VARIANTS = {k: [] for k in os.environ["PREBUILT"].split(",")}
 if os.environ.get("VARIANTS"):
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ["VARIANTS"].split(",")}
 SRCS = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu"]
