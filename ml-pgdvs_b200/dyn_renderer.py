@@ -62,6 +62,31 @@ def opencv_to_p3d_camera(K44, c2w44, H, W):
     return R_p3d.reshape(9), T_p3d, focal.astype(np.float32), p0.astype(np.float32)
 
 
+def opencv_to_p3d_cameras(Ks, c2ws, H, W) -> np.ndarray:
+    """opencv_to_p3d_camera for a batch: [N,4,4] x2 -> float32 [N,16] rows laid out like PgdvsCamera
+    (R[9], T[3], focal[2], p0[2]).  One batched LAPACK inverse instead of N Python round trips;
+    the per-matrix arithmetic is the same."""
+    Ks = np.asarray(Ks, np.float32).reshape(-1, 4, 4)
+    c2ws = np.asarray(c2ws, np.float32).reshape(-1, 4, 4)
+    n = Ks.shape[0]
+    out = np.empty((n, 16), np.float32)
+    if n == 0:
+        return out
+    w2c = np.linalg.inv(c2ws).astype(np.float32)
+    s = np.float32(min(H, W)) / np.float32(2.0)
+    R_p3d = np.ascontiguousarray(np.transpose(w2c[:, :3, :3], (0, 2, 1)))
+    R_p3d[:, :, :2] *= -1
+    T_p3d = w2c[:, :3, 3].copy()
+    T_p3d[:, :2] *= -1
+    out[:, 0:9] = R_p3d.reshape(n, 9)
+    out[:, 9:12] = T_p3d
+    out[:, 12] = Ks[:, 0, 0] / s
+    out[:, 13] = Ks[:, 1, 1] / s
+    c0 = np.array([W, H], np.float32) / np.float32(2.0)
+    out[:, 14:16] = -(Ks[:, :2, 2] - c0) / s
+    return out
+
+
 def _fill(arr, vals):
     for i, v in enumerate(np.asarray(vals, dtype=np.float32).reshape(-1)):
         arr[i] = float(v)
@@ -105,7 +130,20 @@ class SourcePair:
             self.w2 = (tt - t1) / (t2 - t1)
 
     def group_key(self):
-        """Everything of a job except the target camera / view index."""
+        """Everything of a job except the target camera / view index (cached)."""
+        if getattr(self, "_gkey", None) is None:
+            self._gkey = self._group_key()
+        return self._gkey
+
+    def record(self) -> np.ndarray:
+        """The job descriptor as raw bytes (uint8[sizeof(PgdvsUwpJob)]), built once; only the
+        packed frame-2 pointer is patched in per PreparedViews."""
+        if getattr(self, "_rec", None) is None:
+            j = self.to_struct()
+            self._rec = np.frombuffer(bytes(j), dtype=np.uint8).copy()
+        return self._rec
+
+    def _group_key(self):
         ptr = lambda t: t.data_ptr() if t is not None else 0  # noqa: E731
         return (ptr(self.depth_1), ptr(self.rgb_1), ptr(self.mask_1), ptr(self.flow_12), ptr(self.occ_12),
                 ptr(self.depth_2), ptr(self.rgb_2), ptr(self.keep), self.M1.tobytes(),
@@ -150,37 +188,42 @@ class PreparedViews:
         self.device = torch.device(device)
         assert all(pairs[i].view <= pairs[i + 1].view for i in range(self.n_jobs - 1)), \
             "jobs must be sorted by view"
-        cam_structs = []
-        for (R, T, f, p0) in cams_p3d:
-            c = _cabi.PgdvsCamera()
-            _fill(c.R, R)
-            _fill(c.T, T)
-            _fill(c.focal, f)
-            _fill(c.p0, p0)
-            cam_structs.append(c)
+        # cameras: float32 [N,16] rows = PgdvsCamera (R[9], T[3], focal[2], p0[2])
+        if isinstance(cams_p3d, np.ndarray):
+            cam_arr = np.ascontiguousarray(cams_p3d, np.float32).reshape(-1, 16)
+        else:
+            cam_arr = np.empty((self.n_views, 16), np.float32)
+            for i, (R, T, f, p0) in enumerate(cams_p3d):
+                cam_arr[i, 0:9] = np.asarray(R, np.float32).reshape(9)
+                cam_arr[i, 9:12] = np.asarray(T, np.float32).reshape(3)
+                cam_arr[i, 12:14] = np.asarray(f, np.float32).reshape(2)
+                cam_arr[i, 14:16] = np.asarray(p0, np.float32).reshape(2)
+        assert ctypes.sizeof(_cabi.PgdvsCamera) == 64
         # frame-2 planes are shared by many jobs (every source frame feeds several target views):
         # pack each distinct (rgb, depth) pair once per render as an (r,g,b,depth) float4 plane
         self.n_frames = 0
         self.frames_dev = None
+        rgbd_ptr = np.zeros(max(self.n_jobs, 1), np.uint64)
         if pack_frames:
             uniq = {}
-            for p in pairs:
+            frame_of = [-1] * self.n_jobs
+            for j, p in enumerate(pairs):
                 if p.same_time:
                     continue
                 key = (p.rgb_2.data_ptr(), p.depth_2.data_ptr())
-                if key not in uniq:
-                    uniq[key] = (len(uniq), p.rgb_2, p.depth_2)
+                slot = uniq.get(key)
+                if slot is None:
+                    slot = uniq[key] = len(uniq)
+                frame_of[j] = slot
             if uniq:
                 self.rgbd = torch.empty((len(uniq), H, W, 4), dtype=torch.float32, device=device)
-                packs = [None] * len(uniq)
-                for key, (i, rgb, depth) in uniq.items():
-                    fp = _cabi.PgdvsFramePack()
-                    fp.rgb, fp.depth, fp.rgbd = rgb.data_ptr(), depth.data_ptr(), self.rgbd[i].data_ptr()
-                    packs[i] = fp
-                for p in pairs:
-                    if not p.same_time:
-                        p.rgbd_2 = self.rgbd[uniq[(p.rgb_2.data_ptr(), p.depth_2.data_ptr())][0]]
-                self.frames_dev = _upload_structs(packs, _cabi.PgdvsFramePack, device)
+                base, stride = self.rgbd.data_ptr(), H * W * 16
+                packs = np.empty((len(uniq), 3), np.uint64)  # PgdvsFramePack {rgb, depth, rgbd}
+                for (rgb_ptr, depth_ptr), i in uniq.items():
+                    packs[i] = (rgb_ptr, depth_ptr, base + i * stride)
+                fo = np.asarray(frame_of, np.int64)
+                rgbd_ptr[:self.n_jobs] = np.where(fo >= 0, base + np.maximum(fo, 0) * stride, 0).astype(np.uint64)
+                self.frames_dev = torch.from_numpy(packs.view(np.uint8).reshape(-1)).to(device)
                 self.n_frames = len(uniq)
         # job groups: jobs that differ only in the target camera share validity, gathers and the
         # world point (e.g. the 12 cameras per time step of the NVIDIA benchmark)
@@ -196,10 +239,21 @@ class PreparedViews:
                     members += idxs
                     first.append(len(members))
                 self.n_groups = len(groups)
-                self.group_first_dev = torch.tensor(first, dtype=torch.int32).to(device)
-                self.group_members_dev = torch.tensor(members, dtype=torch.int32).to(device)
-        self.jobs_dev = _upload_structs([p.to_struct() for p in pairs], _cabi.PgdvsUwpJob, device)
-        self.cams_dev = _upload_structs(cam_structs, _cabi.PgdvsCamera, device)
+                gm = np.asarray(first + members, np.int32)  # one upload for both arrays
+                gm_dev = torch.from_numpy(gm).to(device)
+                self.group_first_dev = gm_dev[:len(first)]
+                self.group_members_dev = gm_dev[len(first):]
+        # job descriptors: cached per SourcePair, only the packed frame-2 pointer is patched in
+        size = ctypes.sizeof(_cabi.PgdvsUwpJob)
+        if self.n_jobs:
+            recs = np.stack([p.record() for p in pairs])
+            off = _cabi.PgdvsUwpJob.rgbd2.offset
+            recs[:, off:off + 8] = rgbd_ptr[:self.n_jobs].view(np.uint8).reshape(-1, 8)
+        else:
+            recs = np.zeros((1, size), np.uint8)
+        self.jobs_dev = torch.from_numpy(recs.reshape(-1)).to(device)
+        self.cams_dev = torch.from_numpy(cam_arr.view(np.uint8).reshape(-1).copy()
+                                         if cam_arr.size else np.zeros(64, np.uint8)).to(device)
         self._keepalive = list(pairs)
         self.h2d_bytes = self.jobs_dev.numel() + self.cams_dev.numel() + \
             (self.frames_dev.numel() if self.frames_dev is not None else 0)
@@ -221,8 +275,12 @@ class PreparedViews:
 def prepare_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, device,
                   group_jobs: bool = True) -> PreparedViews:
     """tgt_cams: per view (K44, c2w44) in OpenCV convention (flat_cam[2:18], flat_cam[18:34])."""
-    cams = [opencv_to_p3d_camera(K, c2w, H, W) for (K, c2w) in tgt_cams]
-    return PreparedViews(pairs, cams, H, W, device, group_jobs=group_jobs)
+    if len(tgt_cams):
+        Ks = np.stack([_np44(K) for (K, _) in tgt_cams])
+        c2ws = np.stack([_np44(c) for (_, c) in tgt_cams])
+    else:
+        Ks = c2ws = np.zeros((0, 4, 4), np.float32)
+    return PreparedViews(pairs, opencv_to_p3d_cameras(Ks, c2ws, H, W), H, W, device, group_jobs=group_jobs)
 
 
 def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=None,
