@@ -227,3 +227,51 @@ def test_argument_errors():
         pgdvs_b200.rasterize_points_packed(pts, fi, npc, (8, 0), 0.1, 2)
     with pytest.raises(RuntimeError):
         pgdvs_b200.rasterize_points_packed(pts.cpu(), fi, npc, (8, 8), 0.1, 2)  # no CPU fallback
+
+
+# ---------------------------------------------------------------------------------------------
+# The TMA-staged tile kernel (halo 1..3, scalar radius) and its rare paths.  r_px ~ 1.4 at 96x128.
+# ---------------------------------------------------------------------------------------------
+def _tile_case(rng, H, W, P, z_mode, cluster=0.0):
+    s = min(H, W) / 2
+    x = rng.uniform(-W / 2 / s, W / 2 / s, P)
+    y = rng.uniform(-H / 2 / s, H / 2 / s, P)
+    if cluster > 0:  # a dense blob: its tiles overflow the staging buffer (sized from the MEAN density)
+        n = int(P * cluster)
+        x[:n] = rng.uniform(0.10, 0.10 + 16 / s, n)
+        y[:n] = rng.uniform(-0.20, -0.20 + 16 / s, n)
+    if z_mode == "wide":      # depth ratio 1e9 inside every tile: no room for exact 32-bit keys
+        z = 10.0 ** rng.uniform(-3, 6, P)
+    elif z_mode == "ties":    # four depth planes: almost every pixel has exact z ties
+        z = rng.integers(1, 5, P).astype(np.float64)
+    elif z_mode == "zero":    # +0.0 / -0.0 / denormals next to ordinary depths
+        z = rng.uniform(0.5, 4.0, P)
+        z[::7] = 0.0
+        z[3::7] = -0.0
+        z[5::7] = 1e-42
+    else:
+        z = rng.uniform(1.0, 10.0, P)
+    return np.stack([x, y, z], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("z_mode,cluster,K,P", [
+    ("smooth", 0.0, 8, 30000),   # the fast path: exact 32-bit keys
+    ("wide", 0.0, 8, 30000),     # truncated keys + ambiguity rescan
+    ("ties", 0.0, 8, 30000),     # exact ties everywhere -> rescan_exact on most pixels
+    ("zero", 0.0, 4, 20000),     # signed zeros and denormal depths
+    ("smooth", 0.6, 8, 40000),   # overflowing tiles: unstaged walk in the same launch
+    ("ties", 0.5, 5, 30000),     # both at once, K not a template size
+    ("smooth", 0.0, 16, 30000),  # long lists inside the tile kernel (pair list)
+    ("wide", 0.3, 32, 30000),
+])
+def test_tile_kernel_paths_bit_exact(z_mode, cluster, K, P):
+    rng = np.random.default_rng(sum(map(ord, z_mode)) * 1000 + K * 10 + int(cluster * 10))
+    H, W, r = 96, 128, 0.029
+    pts = _tile_case(rng, H, W, P, z_mode, cluster)
+    feats = rng.uniform(0, 1, (P, 3)).astype(np.float32)
+    fi = np.array([0, P // 3], np.int64)
+    npc = np.array([P // 3, P - P // 3], np.int64)
+    out = _run(pts, feats, fi, npc, H, W, r, K, "norm")
+    img, frags = oracle.render_points(pts, fi, npc, feats, (H, W), r, K, "norm", background=(0, 0, 0), n_threads=4)
+    _assert_frags(out, frags)
+    np.testing.assert_allclose(out["image"], img, atol=IMG_ATOL, rtol=0)
