@@ -543,6 +543,11 @@ __device__ __forceinline__ bool walk_tile_pairs(const RasterParams& p, const Pix
   return q.ambiguous(p.K);
 }
 
+// tile kernel: lists up to this length use sorted 32-bit keys (branch-free up to
+// PGDVS_RASTER_BRANCHFREE_MAXK, with a "can it enter?" pre-test above), longer ones the pair list
+#ifndef PGDVS_TILE_KEYS_MAXK
+#define PGDVS_TILE_KEYS_MAXK 32
+#endif
 #ifndef PGDVS_TILE_MINBLOCKS_K8
 #define PGDVS_TILE_MINBLOCKS_K8 5
 #endif
@@ -751,7 +756,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   // short lists: sorted 32-bit keys (KeyList); long lists: the general pair list
   Slots<KP> sl;
   bool amb;
-  if constexpr (KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
+  if constexpr (KP <= PGDVS_TILE_KEYS_MAXK) {
     KeyCode kc;  // the same code for every pixel of the tile
     kc.init(s_max, staged ? s_zlo : 0u, staged ? s_zhi : 0x7fffffffu);
 
@@ -935,8 +940,16 @@ static bool launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, 
 #ifndef PGDVS_RASTER_HEADROOM
 #define PGDVS_RASTER_HEADROOM 1.5
 #endif
-  const double need = PGDVS_RASTER_HEADROOM * density * tile_cells * 32.0;
-  if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) return false;
+#ifndef PGDVS_RASTER_HEADROOM_DENSE
+#define PGDVS_RASTER_HEADROOM_DENSE 1.15
+#endif
+  double need = PGDVS_RASTER_HEADROOM * density * tile_cells * 32.0;
+  if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) {
+    // dense clouds: trade head-room for staging at all (tiles that still overflow walk the
+    // global records inside the kernel)
+    need = PGDVS_RASTER_HEADROOM_DENSE * density * tile_cells * 32.0;
+    if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) return false;
+  }
   int smem = (int)need;
   if (smem < 24 * 1024) smem = 24 * 1024;
   smem = (smem + 1023) & ~1023;
