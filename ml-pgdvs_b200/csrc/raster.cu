@@ -809,21 +809,38 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
           j = jn;
         }
       }
+    } else if (staged) {
+      // wider windows: the same flattened walk, the run of ordinal t found with SPAN-1 selects
+      int cum[SPAN], off[SPAN];  // cum[r] = candidates in rows 0..r, off[r] = rs[r] - cum[r-1]
+      int acc = 0;
+  #pragma unroll
+      for (int r = 0; r < SPAN; ++r) {
+        off[r] = rs[r] - acc;
+        acc += rl[r];
+        cum[r] = acc;
+      }
+      auto key_at = [&](int t) {
+        int o = off[SPAN - 1];
+  #pragma unroll
+        for (int r = SPAN - 2; r >= 0; --r) o = (t < cum[r]) ? off[r] : o;
+        const int j = t + o;
+        const float4 a = staged_rec.a(j);
+        return kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t);
+      };
+      int t = 0;
+      if constexpr (KP >= 2 && KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
+        for (; t + 1 < total; t += 2) q.insert2(key_at(t), key_at(t + 1));
+      }
+      for (; t < total; ++t) q.push(key_at(t));
     } else {
+      // unstaged tile with a wide window: row by row over the global records
       uint32_t t = 0;
   #pragma unroll
       for (int r = 0; r < SPAN; ++r) {
         const int s = rs[r], e = rs[r] + rl[r];
-        if (staged) {
-          for (int j = s; j < e; ++j, ++t) {
-            const float4 a = staged_rec.a(j);
-            q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
-          }
-        } else {
-          for (int j = s; j < e; ++j, ++t) {
-            const float4 a = __ldg(p.recA + rec_a(j));
-            q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
-          }
+        for (int j = s; j < e; ++j, ++t) {
+          const float4 a = __ldg(p.recA + rec_a(j));
+          q.push(kc.encode(hit_test<false>(c, a, nullptr, j), a.z, t));
         }
       }
     }
