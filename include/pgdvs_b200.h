@@ -257,6 +257,31 @@ int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* ref, int64_t
 int pgdvs_knn_points(const float* query, int64_t Q, const float* ref, int64_t R, int K,
                      float* dists_out, int64_t* idx_out, void* stream);
 
+/* --------------------------------------------------------------------------------------
+ * 7. Softmax splatting ("next" row 3 of the scope table; the reference's default
+ *    dyn_render_type).
+ *    pgdvs_softsplat_forward replaces `softsplat_func.forward` (pgdvs/utils/softsplat.py:342-427,
+ *    a cupy-compiled kernel upstream): tenIn f32 [N,C,H,W], tenFlow f32 [N,2,H,W] ->
+ *    tenOut f32 [N,C,H,W]; every source pixel is added to the four pixels around
+ *    (x + flow_x, y + flow_y) with bilinear weights; non-finite targets are skipped.
+ *    pgdvs_softsplat_dyn fuses the whole dynamic branch of PGDVSDynamicRenderer.forward
+ *    (pgdvs_renderer_dyn.py:157-209 with PGDVSBaseRenderer.softsplat_img,
+ *    pgdvs_renderer_base.py:59-138): static regions of frame 1 replaced by `noise` (NULL = 0),
+ *    back-warp of frame 2 along flow_12 (grid_sample bilinear/zeros/align_corners=True),
+ *    metric = mean_c |rgb1 - warp|, weight exp(clip(-alpha*metric, -alpha, alpha)), "soft" splat
+ *    of rgb and of the mask along flow_1_to_tgt, division by (sum + 1e-7), mask > 1e-3,
+ *    rgb * mask.  Inputs channels-last f32 (rgb1/rgb2/noise [B,H,W,3], mask1 [B,H,W,1], flows
+ *    [B,H,W,2]); outputs as upstream: out_rgb [B,3,H,W], out_mask [B,1,H,W], out_metric
+ *    [B,1,H,W] (nullable).  workspace: pgdvs_softsplat_workspace_bytes, 32-byte aligned.
+ * ------------------------------------------------------------------------------------ */
+int pgdvs_softsplat_forward(const float* ten_in, const float* ten_flow, int N, int C, int H, int W,
+                            float* ten_out, void* stream);
+int pgdvs_softsplat_workspace_bytes(int B, int H, int W, size_t* bytes);
+int pgdvs_softsplat_dyn(const float* rgb1, const float* mask1, const float* noise, const float* rgb2,
+                        const float* flow_1_to_tgt, const float* flow_12, float alpha, int B, int H,
+                        int W, float* out_rgb, float* out_mask, float* out_metric, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = (
     "pgdvs_uwp_bin_workspace_bytes", "pgdvs_uwp_bin", "pgdvs_pack_rgbd",
     "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist", "pgdvs_knn_points",
     "pgdvs_track_workspace_bytes", "pgdvs_track_points", "pgdvs_quantize_u8",
+    "pgdvs_softsplat_forward", "pgdvs_softsplat_workspace_bytes", "pgdvs_softsplat_dyn",
 )
 
 
@@ -117,6 +118,14 @@ def lib():
                                      c_void_p, c_void_p, c_size_t, c_void_p]
     L.pgdvs_quantize_u8.restype = c_int
     L.pgdvs_quantize_u8.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    L.pgdvs_softsplat_forward.restype = c_int
+    L.pgdvs_softsplat_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.pgdvs_softsplat_workspace_bytes.restype = c_int
+    L.pgdvs_softsplat_workspace_bytes.argtypes = [c_int, c_int, c_int, POINTER(c_size_t)]
+    L.pgdvs_softsplat_dyn.restype = c_int
+    L.pgdvs_softsplat_dyn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                      c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]
     L.pgdvs_knn_points.restype = c_int
     L.pgdvs_knn_points.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     if L.pgdvs_abi_version() != 1:

@@ -392,6 +392,7 @@ class PGDVSDynamicRenderer(torch.nn.Module):
         super().__init__()
         self.cfg = cfg
         self.proj_func = proj_func
+        self.softsplat_metric_abs_alpha = float(softsplat_metric_abs_alpha)
         self.use_tracker = use_tracker
         if use_tracker:
             raise NotImplementedError(
@@ -495,12 +496,51 @@ class PGDVSDynamicRenderer(torch.nn.Module):
             raise ValueError(_cfg(render_cfg, "dyn_render_type"))
         return flow_1_to_tgt, valid_mask, info
 
-    # ---- pgdvs_renderer_dyn.py:63-257 (pcl branch, no tracker)
+    # ---- pgdvs_renderer_dyn.py:157-209: flow frame 1 -> target from the projected cloud (:470-503),
+    #      then the fused softmax splat (softsplat.softsplat_dyn)
+    def _forward_softsplat(self, data, pairs, cams, H, W, dev, noise=None):
+        from . import softsplat as _softsplat
+        n_b = len(pairs)
+        if n_b:
+            Ks = np.stack([_np44(K) for (K, _) in cams])
+            c2ws = np.stack([_np44(c) for (_, c) in cams])
+        else:
+            Ks = c2ws = np.zeros((0, 4, 4), np.float32)
+        prep = PreparedViews(pairs, opencv_to_p3d_cameras(Ks, c2ws, H, W), H, W, dev)
+        cloud = unproject_warp_project(prep, want_src_pix=True)
+        first, num = cloud["first_idx"].tolist(), cloud["num_points"].tolist()  # one sync per batch
+        flow_t = torch.zeros((n_b, H * W, 2), dtype=torch.float32, device=dev)
+        valid = torch.zeros((n_b, H * W, 1), dtype=torch.float32, device=dev)
+        s = min(H, W) / 2.0
+        for b in range(n_b):
+            if num[b] == 0:
+                continue  # empty mask: zero flow, zero mask (pgdvs_renderer_dyn.py:131-141)
+            seg = slice(first[b], first[b] + num[b])
+            sp = cloud["src_pix"][seg].long()
+            ndc = cloud["xyz_ndc"][seg]
+            uv_t = torch.stack([W / 2.0 - ndc[:, 0] * s, H / 2.0 - ndc[:, 1] * s], dim=1)
+            uv1 = torch.stack([(sp % W).float(), (sp // W).float()], dim=1)
+            flow_t[b, sp] = uv_t - uv1
+            valid[b, sp] = 1.0
+        rgb_1 = data["rgb_src_temporal"][:, 0]
+        rgb_2 = data["rgb_src_temporal"][:, 1]
+        if noise is None:
+            noise = torch.clamp(torch.randn_like(rgb_1), 0.0, 1.0)  # pgdvs_renderer_dyn.py:183-185
+        # (views with an empty dynamic mask have an all-zero valid mask: their splatted mask, hence
+        #  their output, is zero whatever the colours are — as upstream, :131-141 and :203-205)
+        return _softsplat.softsplat_dyn(
+            rgb_1=rgb_1, dyn_mask_1=valid.view(n_b, H, W, 1), rgb_2=rgb_2,
+            flow_1_to_tgt=flow_t.view(n_b, H, W, 2), flow_12=data["flow_fwd"],
+            alpha=self.softsplat_metric_abs_alpha, noise=noise)
+
+    # ---- pgdvs_renderer_dyn.py:63-257 (pcl / softsplat branches, no tracker)
     def forward(self, data: Dict[str, torch.Tensor], ray_batch=None, render_cfg=None, for_debug=False,
-                disable_tqdm=False, static_rgb: Optional[torch.Tensor] = None):
+                disable_tqdm=False, static_rgb: Optional[torch.Tensor] = None,
+                softsplat_noise: Optional[torch.Tensor] = None):
         render_cfg = render_cfg if render_cfg is not None else DEFAULT_RENDER_CFG
-        if _cfg(render_cfg, "dyn_render_type") != "pcl":
-            raise NotImplementedError("only dyn_render_type='pcl' is on the B200 hot path")
+        render_type = _cfg(render_cfg, "dyn_render_type")
+        if render_type not in ("pcl", "softsplat"):
+            raise NotImplementedError("dyn_render_type must be 'pcl' or 'softsplat' (mesh mode is not built)")
         n_b, _, H, W, _ = data["rgb_src_temporal"].shape
         dev = data["rgb_src_temporal"].device
         use_occ = bool(_cfg(render_cfg, "dyn_render_use_flow_consistency"))
@@ -535,10 +575,13 @@ class PGDVSDynamicRenderer(torch.nn.Module):
                     thres = torch.median(avg) + torch.std(avg) * float(_cfg(render_cfg, "dyn_pcl_outlier_std_thres"))
                     keep[cloud["src_pix"][first[b]:first[b] + num[b]].long()] = (avg < thres).to(torch.uint8)
                 pairs[b].keep = keep
-        out = render_views(pairs, cams, H, W, radius=radius, points_per_pixel=K,
-                           compositor=_cfg(render_cfg, "dyn_render_compositor"))
-        dyn_rgb = out["image"].permute(0, 3, 1, 2).contiguous()
-        dyn_mask = out["mask"].permute(0, 3, 1, 2).contiguous()
+        if render_type == "softsplat":
+            dyn_rgb, dyn_mask = self._forward_softsplat(data, pairs, cams, H, W, dev, softsplat_noise)
+        else:
+            out = render_views(pairs, cams, H, W, radius=radius, points_per_pixel=K,
+                               compositor=_cfg(render_cfg, "dyn_render_compositor"))
+            dyn_rgb = out["image"].permute(0, 3, 1, 2).contiguous()
+            dyn_mask = out["mask"].permute(0, 3, 1, 2).contiguous()
         rgb_final, mask_final, combined = ops.merge_blend(dyn_rgb, dyn_mask, None, None, static_rgb)
         info = {
             "temporal_closest_rgb": dyn_rgb, "temporal_closest_mask": dyn_mask,

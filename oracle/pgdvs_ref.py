@@ -276,3 +276,102 @@ def compute_pcl_for_tgt(*, tracks, visibles, rgbs, depths, flat_cams, times, tim
     ratio = (time_tgt - t_use[:, :1]) / (t_use[:, 1:2] - t_use[:, :1] + 1e-8)
     pcl = pts[:, 0, :] + (pts[:, 1, :] - pts[:, 0, :]) * ratio
     return pcl, rgb, torch.nonzero(flag_valid)[:, 0]
+
+
+# ----------------------------------------------------------------------------- softmax splatting
+# /root/reference/pgdvs/utils/softsplat.py:280-427 (the forward kernel is a cupy-compiled CUDA
+# string upstream and asserts on CPU tensors, so it cannot be executed here: PARITY UNPINNED for
+# softsplat_forward, restated from the in-tree kernel text) and
+# /root/reference/pgdvs/renderers/pgdvs_renderer_base.py:59-138 (pure torch: pinned by
+# tests/golden/softsplat_metric.npz, generated from the real module).
+def softsplat_forward(ten_in, ten_flow):
+    """softsplat_func.forward (softsplat.py:342-420): tenIn [N,C,H,W], tenFlow [N,2,H,W]."""
+    ten_in = np.asarray(ten_in, np.float32)
+    ten_flow = np.asarray(ten_flow, np.float32)
+    N, C, H, W = ten_in.shape
+    out = np.zeros_like(ten_in)
+    ys, xs = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    for n in range(N):
+        fx = (xs + ten_flow[n, 0]).astype(np.float32)
+        fy = (ys + ten_flow[n, 1]).astype(np.float32)
+        ok = np.isfinite(fx) & np.isfinite(fy)
+        fx0, fy0 = np.where(ok, fx, 0).astype(np.float32), np.where(ok, fy, 0).astype(np.float32)
+        nwx, nwy = np.floor(fx0), np.floor(fy0)
+        sex, sey = nwx + 1, nwy + 1
+        taps = [
+            (nwx, nwy, (sex - fx0) * (sey - fy0)),   # north-west
+            (sex, nwy, (fx0 - nwx) * (sey - fy0)),   # north-east
+            (nwx, sey, (sex - fx0) * (fy0 - nwy)),   # south-west
+            (sex, sey, (fx0 - nwx) * (fy0 - nwy)),   # south-east
+        ]
+        for tx, ty, w in taps:
+            m = ok & (tx >= 0) & (tx < W) & (ty >= 0) & (ty < H)
+            txi, tyi = tx[m].astype(np.int64), ty[m].astype(np.int64)
+            wv = w[m].astype(np.float32)
+            for c in range(C):
+                np.add.at(out[n, c], (tyi, txi), (ten_in[n, c][m] * wv).astype(np.float32))
+    return out
+
+
+def softsplat(ten_in, ten_flow, ten_metric, mode):
+    """softsplat.softsplat (softsplat.py:280-334) on torch CPU tensors."""
+    base = mode.split("-")[0]
+    assert base in ("sum", "avg", "linear", "soft")
+    if base == "avg":
+        ten_in = torch.cat([ten_in, ten_in.new_ones([ten_in.shape[0], 1, ten_in.shape[2], ten_in.shape[3]])], 1)
+    elif base == "linear":
+        ten_in = torch.cat([ten_in * ten_metric, ten_metric], 1)
+    elif base == "soft":
+        ten_in = torch.cat([ten_in * ten_metric.exp(), ten_metric.exp()], 1)
+    out = torch.from_numpy(softsplat_forward(ten_in.numpy(), ten_flow.numpy()))
+    if base in ("avg", "linear", "soft"):
+        norm = out[:, -1:, :, :]
+        parts = mode.split("-")
+        if len(parts) == 1 or parts[1] == "addeps":
+            norm = norm + 0.0000001
+        elif parts[1] == "zeroeps":
+            norm = norm.clone()
+            norm[norm == 0.0] = 1.0
+        elif parts[1] == "clipeps":
+            norm = norm.clip(0.0000001, None)
+        out = out[:, :-1, :, :] / norm
+    return out
+
+
+def backwarp_for_softsplat_metric(ten_in, ten_flow):
+    """pgdvs_renderer_base.py:100-138."""
+    H, W = ten_flow.shape[2], ten_flow.shape[3]
+    hor = torch.linspace(-1.0, 1.0, W, dtype=ten_flow.dtype).view(1, 1, 1, -1).repeat(1, 1, H, 1)
+    ver = torch.linspace(-1.0, 1.0, H, dtype=ten_flow.dtype).view(1, 1, -1, 1).repeat(1, 1, 1, W)
+    grid = torch.cat([hor, ver], 1)
+    flow = torch.cat([ten_flow[:, 0:1] / ((ten_in.shape[3] - 1.0) / 2.0),
+                      ten_flow[:, 1:2] / ((ten_in.shape[2] - 1.0) / 2.0)], 1)
+    return torch.nn.functional.grid_sample(input=ten_in, grid=(grid + flow).permute(0, 2, 3, 1), mode="bilinear",
+                                           padding_mode="zeros", align_corners=True)
+
+
+def softsplat_img(*, rgb_src1, flow_src1_to_tgt, rgb_src2=None, flow_src1_to_src2=None, metric=None, alpha=100.0):
+    """PGDVSBaseRenderer.softsplat_img (pgdvs_renderer_base.py:59-98)."""
+    if metric is None:
+        warp = backwarp_for_softsplat_metric(rgb_src2, flow_src1_to_src2)
+        metric = torch.nn.functional.l1_loss(input=rgb_src1, target=warp, reduction="none").mean(dim=1, keepdim=True)
+    out = softsplat(rgb_src1, flow_src1_to_tgt, (-alpha * metric).clip(-alpha, alpha), "soft")
+    return out, metric
+
+
+def softsplat_dyn_render(*, rgb_1, dyn_mask_1, rgb_2, flow_1_to_tgt, flow_12, noise=None, alpha=100.0):
+    """The softsplat branch of PGDVSDynamicRenderer.forward (pgdvs_renderer_dyn.py:157-209).
+    Channels-last inputs [B,H,W,C]; `noise` stands for clamp(randn_like(rgb), 0, 1) (zeros if None).
+    Returns (render_dyn_rgb [B,3,H,W], render_dyn_mask [B,1,H,W], metric [B,1,H,W])."""
+    m = dyn_mask_1.permute(0, 3, 1, 2)
+    f_t = flow_1_to_tgt.permute(0, 3, 1, 2)
+    r2 = rgb_2.permute(0, 3, 1, 2)
+    f12 = flow_12.permute(0, 3, 1, 2)
+    r1 = rgb_1.permute(0, 3, 1, 2)
+    nz = noise.permute(0, 3, 1, 2) if noise is not None else torch.zeros_like(r1)
+    r1 = r1 * m + nz * (1 - m)
+    splat, metric = softsplat_img(rgb_src1=r1, flow_src1_to_tgt=f_t, rgb_src2=r2, flow_src1_to_src2=f12, alpha=alpha)
+    mask, _ = softsplat_img(rgb_src1=m, flow_src1_to_tgt=f_t, rgb_src2=r2, flow_src1_to_src2=f12, metric=metric,
+                            alpha=alpha)
+    mask = (mask > 1e-3).float()
+    return splat * mask, mask, metric

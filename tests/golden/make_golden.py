@@ -324,6 +324,18 @@ def main():
                         flat_cams=_np(sc["flat_cam_src"]), times=_np(times), time_tgt=_np(time_tgt),
                         idx_temporal_closest=np.array(idx_closest), idx_real_track=np.array([0, 1, 4, 5]),
                         out_pcl=_np(pcl_t), out_rgb=_np(rgb_t))
+    # ---- 6. softsplat importance metric (pgdvs_renderer_base.py:59-138).  The splat kernel itself
+    #         is cupy-compiled CUDA and asserts on CPU tensors, so only the pure-torch part
+    #         (back-warp + L1 metric) can be recorded from the real module.
+    g = torch.Generator().manual_seed(11)
+    Bs, Hs, Ws = 2, 14, 22
+    rgb1 = torch.rand(Bs, 3, Hs, Ws, generator=g)
+    rgb2 = torch.rand(Bs, 3, Hs, Ws, generator=g)
+    flow12 = torch.randn(Bs, 2, Hs, Ws, generator=g) * 3.0
+    warp = base.backwarp_for_softsplat_metric(tenIn=rgb2, tenFlow=flow12)
+    metric = torch.nn.functional.l1_loss(input=rgb1, target=warp, reduction="none").mean(dim=1, keepdim=True)
+    np.savez_compressed(OUT_DIR / "softsplat_metric.npz", rgb1=_np(rgb1), rgb2=_np(rgb2), flow12=_np(flow12),
+                        warp=_np(warp), metric=_np(metric))
     print("wrote", sorted(p.name for p in OUT_DIR.glob("*.npz")))
 
 

@@ -104,3 +104,14 @@ def test_track_pcl_matches_reference(golden_dir):
     assert pcl.shape[0] == g["out_pcl"].shape[0] and pcl.shape[0] > 0
     np.testing.assert_allclose(pcl.numpy(), g["out_pcl"], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(rgb.numpy(), g["out_rgb"], rtol=1e-6, atol=1e-6)
+
+
+def test_softsplat_metric_matches_reference(golden_dir):
+    """back-warp + L1 importance metric (pgdvs_renderer_base.py:59-138) recorded from the real module."""
+    g = np.load(golden_dir / "softsplat_metric.npz")
+    rgb1, rgb2, flow12 = (torch.from_numpy(g[k]) for k in ("rgb1", "rgb2", "flow12"))
+    warp = ref.backwarp_for_softsplat_metric(rgb2, flow12)
+    assert np.array_equal(warp.numpy(), g["warp"])
+    _, metric = ref.softsplat_img(rgb_src1=rgb1, flow_src1_to_tgt=torch.zeros_like(flow12), rgb_src2=rgb2,
+                                  flow_src1_to_src2=flow12)
+    assert np.array_equal(metric.numpy(), g["metric"])

@@ -135,3 +135,25 @@ def test_render_points_mask_semantics():
     assert mask.sum() == 1 and mask[2, 1]
     np.testing.assert_allclose(img[0, 2, 1], col[0], rtol=1e-6)
     assert np.all(img[0][~mask] == 0)
+
+
+def test_softsplat_forward_known_answers():
+    """softsplat.py:355-393 by hand: one pixel moved by (0.25, 0.5) lands on four pixels with the
+    bilinear weights; non-finite or out-of-image targets contribute nothing."""
+    from oracle import pgdvs_ref as ref
+    x = np.zeros((1, 1, 4, 4), np.float32)
+    x[0, 0, 1, 1] = 2.0
+    flow = np.zeros((1, 2, 4, 4), np.float32)
+    flow[0, 0, 1, 1], flow[0, 1, 1, 1] = 0.25, 0.5
+    out = ref.softsplat_forward(x, flow)
+    assert out[0, 0, 1, 1] == np.float32(2.0 * 0.75 * 0.5) and out[0, 0, 1, 2] == np.float32(2.0 * 0.25 * 0.5)
+    assert out[0, 0, 2, 1] == np.float32(2.0 * 0.75 * 0.5) and out[0, 0, 2, 2] == np.float32(2.0 * 0.25 * 0.5)
+    assert np.isclose(out.sum(), 2.0)
+    flow[0, 0, 1, 1] = np.nan
+    assert ref.softsplat_forward(x, flow).sum() == 0
+    flow[0, 0, 1, 1] = -10.0
+    assert ref.softsplat_forward(x, flow).sum() == 0
+    # target exactly on the last column: the east taps fall outside and are dropped
+    flow[0, 0, 1, 1], flow[0, 1, 1, 1] = 2.0, 0.0
+    out = ref.softsplat_forward(x, flow)
+    assert out[0, 0, 1, 3] == 2.0 and out.sum() == 2.0
