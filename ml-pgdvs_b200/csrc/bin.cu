@@ -94,9 +94,12 @@ __global__ void __launch_bounds__(256) k_fill_pre(BinParams p) {
     const int64_t q = base + (int64_t)u * blockDim.x;
     cell[u] = -1;
     if (q < total) {
-      cell[u] = __ldg(p.cell_of + q);
+      // packed-order record of the uwp kernel: (x, y, z, cell) + (r, g, b)
       a[u] = __ldg(p.preA + q);
-      b[u] = __ldg(p.preB + q);
+      const float* pb = reinterpret_cast<const float*>(p.preB) + q * 3;
+      b[u] = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), 0.0f);
+      cell[u] = __float_as_int(a[u].w);
+      a[u].w = __int_as_float((int)q);  // the packed index is the position itself
     }
   }
   int pos[kFillUnroll];

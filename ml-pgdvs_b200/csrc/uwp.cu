@@ -292,9 +292,12 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
       if (FUSED) {
         const int cell = point_cell(p.g, view, ndc.x, ndc.y, ndc.z);
         if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
-        p.cell_of[out] = cell;
-        p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float((int)out));
-        p.preB[out] = make_float4(cr[k], cg[k], cb[k], 0.0f);
+        // packed-order record: (x, y, z, cell) + (r, g, b); the packed index is the position itself
+        p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float(cell));
+        float* pb = reinterpret_cast<float*>(p.preB) + out * 3;
+        pb[0] = cr[k];
+        pb[1] = cg[k];
+        pb[2] = cb[k];
       }
       if (p.xyz_ndc) {
         p.xyz_ndc[out * 3 + 0] = ndc.x;
