@@ -101,25 +101,36 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(const float* __restrict__ q
   }
 }
 
+// knn_grid.cu
+size_t knn_grid_workspace_bytes(int64_t R);
+int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t R, int K, int skip,
+                       float* mean_out, void* workspace, cudaStream_t stream);
+constexpr int64_t kKnnGridMinPoints = 4096;  // below this the brute-force kernel is faster
+
 }  // namespace pgdvs
 
 using namespace pgdvs;
 
 extern "C" int pgdvs_knn_workspace_bytes(int64_t Q, int64_t R, size_t* bytes) {
   if (!bytes || Q < 0 || R < 0) return PGDVS_E_BADARG;
-  *bytes = 256;  // brute-force version needs no scratch; kept for ABI stability
+  // scratch of the uniform-grid search (knn_grid.cu); small clouds use the brute-force kernel,
+  // which needs none
+  *bytes = (R >= kKnnGridMinPoints) ? knn_grid_workspace_bytes(R) : 256;
   return PGDVS_OK;
 }
 
 extern "C" int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* ref, int64_t R, int K,
                                    int skip_first, float* mean_out, void* workspace,
                                    size_t workspace_bytes, void* stream) {
-  (void)workspace;
-  (void)workspace_bytes;
   if (Q < 0 || R < 0 || K < 1 || skip_first < 0) return PGDVS_E_BADARG;
   if (K > kKnnMaxK) return PGDVS_E_K_TOO_LARGE;
   if (Q == 0) return PGDVS_OK;
   if (!query || !mean_out || (R > 0 && !ref)) return PGDVS_E_BADARG;
+  // exact uniform-grid search when the caller provides the scratch (pgdvs_knn_workspace_bytes);
+  // without it, or for small clouds, the brute-force kernel below gives the same answer
+  if (R >= kKnnGridMinPoints && R >= K && R < (int64_t)INT32_MAX && workspace != nullptr &&
+      (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && workspace_bytes >= knn_grid_workspace_bytes(R))
+    return knn_grid_mean_dist(query, Q, ref, R, K, skip_first, mean_out, workspace, (cudaStream_t)stream);
   const unsigned grid = (unsigned)((Q + kKnnThreads - 1) / kKnnThreads);
   k_knn<false><<<grid, kKnnThreads, 0, (cudaStream_t)stream>>>(query, Q, ref, R, K, skip_first, mean_out,
                                                                nullptr, nullptr);

@@ -1,0 +1,388 @@
+// Uniform-grid K nearest neighbours for the statistical outlier filter (exact).
+//
+// The reference calls `pytorch3d.ops.knn_points(pcl, pcl, K=51)` — brute force, O(P^2) — on every
+// source pair with the filter enabled (pgdvs_renderer_dyn.py:405-427; ON in every published
+// benchmark).  At P = 156 672 (one 288x544 frame) the brute-force kernel of
+// knn.cu needs 58 ms on a B200, 2 000x the rest of the per-view path.  This file answers the
+// same question with a counting-sorted uniform grid:
+//
+//   k_knn_bbox   bounding box of the reference cloud (warp shuffles + ordered-int atomics)
+//   k_knn_setup  one thread: cell size from the cloud's footprint (depth-map clouds are
+//                surfaces: ~4 points per occupied cell), grid dims capped at 4 M cells
+//   k_knn_count  cell of every reference point + per-cell counts (RED)
+//   k_scan       (bin.cu) exclusive scan of the counters
+//   k_knn_fill   points scattered into cell order as float4 (x, y, z, original index)
+//   k_knn_query  one thread per query walks cubic shells of cells around its own cell — each
+//                (dz, dy) row of a shell face is ONE contiguous run of the sorted array — keeps
+//                the K smallest squared distances sorted in registers, and stops as soon as the
+//                K-th is no farther than the nearest unvisited cell can be.  Exact, not
+//                approximate: the stopping bound is the true distance to the shell boundary
+//                (sides that coincide with the grid boundary are unbounded).
+//
+// Everything stays on the device (the grid geometry is a device struct), no host sync.
+#include "common.cuh"
+
+namespace pgdvs {
+
+int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state, int* ticket,
+                           cudaStream_t stream);
+
+__host__ __device__ __forceinline__ float kInfF() {
+#ifdef __CUDA_ARCH__
+  return __int_as_float(0x7f800000);
+#else
+  return __builtin_huge_valf();
+#endif
+}
+
+constexpr int kGridMaxCells = 1 << 22;
+constexpr int kGridMaxK = 64;
+constexpr float kGridTargetPerCell = 4.0f;
+constexpr int kGridSamples = 128;  // sample queries that calibrate the cell size
+
+struct KnnGrid {
+  float lo[3];
+  float h, inv_h;
+  int n[3];
+};
+
+struct KnnGridLayout {
+  size_t off_grid, off_bbox, off_est, off_cells, off_state, off_ticket, off_zero_end, off_cell_of, off_sorted, total;
+  int64_t scan_tiles;
+};
+
+static inline KnnGridLayout make_knn_grid_layout(int64_t R) {
+  KnnGridLayout L;
+  size_t o = 0;
+  L.off_grid = o;
+  o += 256;
+  L.off_bbox = o;
+  o += 256;
+  L.off_est = o;
+  o += sizeof(float) * kGridSamples;
+  o = align256(o);
+  o += 256;  // zero pad in front of the cells: cells[-1] == 0
+  L.off_cells = o;
+  L.scan_tiles = ((int64_t)kGridMaxCells + 1 + kScanTile - 1) / kScanTile;
+  o = align256(o + sizeof(int) * (size_t)(L.scan_tiles * kScanTile));
+  L.off_state = o;
+  o = align256(o + sizeof(unsigned long long) * (size_t)L.scan_tiles);
+  L.off_ticket = o;
+  o = align256(o + 256);
+  L.off_zero_end = o;
+  L.off_cell_of = o;
+  o = align256(o + sizeof(int) * (size_t)(R > 0 ? R : 1));
+  L.off_sorted = o;
+  o = align256(o + sizeof(float4) * (size_t)(R > 0 ? R : 1));
+  L.total = o;
+  return L;
+}
+
+// order-preserving float <-> int encoding for atomicMin/Max
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int i = __float_as_int(f);
+  return (i >= 0) ? i : (i ^ 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float((i >= 0) ? i : (i ^ 0x7fffffff)); }
+
+__global__ void __launch_bounds__(256) k_fill_f32(float* out, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = v;
+}
+
+__global__ void k_knn_bbox_init(int* bbox) {
+  if (threadIdx.x < 3) bbox[threadIdx.x] = 0x7fffffff;        // mins
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = (int)0x80000000;  // maxs
+}
+
+__global__ void __launch_bounds__(256) k_knn_bbox(const float* __restrict__ ref, int64_t R, int* bbox) {
+  float lo[3] = {kInfF(), kInfF(), kInfF()}, hi[3] = {-kInfF(), -kInfF(), -kInfF()};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = __ldg(ref + i * 3 + a);
+      if (v == v && fabsf(v) < 1e30f) {  // NaN / inf points do not stretch the grid
+        lo[a] = fminf(lo[a], v);
+        hi[a] = fmaxf(hi[a], v);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(bbox + a, float_to_ordered(lo[a]));
+      atomicMax(bbox + 3 + a, float_to_ordered(hi[a]));
+    }
+  }
+}
+
+// Calibration: for 128 sample points, a histogram of log2(squared distance) to ALL reference
+// points gives the radius that holds K + 1 of them (within a factor sqrt(2)).  The median of
+// those radii becomes the cell size, so a typical query is done after the first or second shell
+// whatever the local shape of the cloud (thin surface, rough surface, volume).
+__global__ void __launch_bounds__(256) k_knn_sample(const float* __restrict__ ref, int64_t R, int K,
+                                                    float* __restrict__ est) {
+  __shared__ int s_hist[256];  // bin = biased exponent of d2 (0..255)
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t si = (int64_t)blockIdx.x * R / kGridSamples;
+  const float qx = __ldg(ref + si * 3), qy = __ldg(ref + si * 3 + 1), qz = __ldg(ref + si * 3 + 2);
+  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) {
+    const float dx = qx - __ldg(ref + i * 3), dy = qy - __ldg(ref + i * 3 + 1), dz = qz - __ldg(ref + i * 3 + 2);
+    const float d = dx * dx + dy * dy + dz * dz;
+    if (d == d) atomicAdd(&s_hist[(__float_as_uint(d) >> 23) & 255], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cum = 0, bin = 255;
+    for (int b = 0; b < 256; ++b) {
+      cum += s_hist[b];
+      if (cum >= K + 1) {
+        bin = b;
+        break;
+      }
+    }
+    // upper edge of the bin: d2 < 2^(bin - 126)
+    est[blockIdx.x] = (bin >= 254 || !(qx == qx && qy == qy && qz == qz)) ? 0.0f
+                                                                           : sqrtf(__uint_as_float((unsigned)(bin + 1) << 23));
+  }
+}
+
+__global__ void k_knn_setup(const int* bbox, int64_t R, const float* est, KnnGrid* g) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float lo[3], e[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = ordered_to_float(bbox[a]);
+    const float hi = ordered_to_float(bbox[3 + a]);
+    e[a] = (hi >= lo[a]) ? (hi - lo[a]) : 0.0f;
+    if (!(lo[a] == lo[a]) || fabsf(lo[a]) > 1e30f) {  // empty / degenerate cloud
+      lo[a] = 0.0f;
+      e[a] = 0.0f;
+    }
+  }
+  // footprint = the largest face of the box (depth-map clouds are height fields over it)
+  const float emax = fmaxf(e[0], fmaxf(e[1], e[2]));
+  const float emin = fminf(e[0], fminf(e[1], e[2]));
+  const float emid = e[0] + e[1] + e[2] - emax - emin;
+  float area = emax * emid;
+  if (!(area > 0.0f)) area = emax * emax;
+  float h = sqrtf(kGridTargetPerCell * area / (float)(R > 0 ? R : 1));  // fallback: thin-surface model
+  if (!(h > 0.0f)) h = 1.0f;
+  {
+    // median of the calibrated K-neighbourhood radii (zeros = unusable samples)
+    float v[kGridSamples];
+    int m = 0;
+    for (int i = 0; i < kGridSamples; ++i)
+      if (est[i] > 0.0f) v[m++] = est[i];
+    for (int i = 1; i < m; ++i) {  // insertion sort, 128 values
+      const float x = v[i];
+      int j = i - 1;
+      while (j >= 0 && v[j] > x) {
+        v[j + 1] = v[j];
+        --j;
+      }
+      v[j + 1] = x;
+    }
+    if (m > 0 && v[m / 2] > 0.0f) h = v[m / 2];
+  }
+  int n[3];
+  for (int it = 0; it < 64; ++it) {
+    double cells = 1.0;
+    for (int a = 0; a < 3; ++a) {
+      const float f = floorf(e[a] / h) + 1.0f;
+      n[a] = (int)fminf(f, 4096.0f);
+      cells *= (double)n[a];
+    }
+    if (cells <= (double)kGridMaxCells && n[0] < 4096 && n[1] < 4096 && n[2] < 4096) break;
+    h *= 1.2599f;
+  }
+  for (int a = 0; a < 3; ++a) {
+    g->lo[a] = lo[a];
+    g->n[a] = n[a];
+  }
+  g->h = h;
+  g->inv_h = 1.0f / h;
+}
+
+__device__ __forceinline__ int3 grid_coord(const KnnGrid& g, float x, float y, float z) {
+  int3 c;
+  c.x = min(max((int)floorf((x - g.lo[0]) * g.inv_h), 0), g.n[0] - 1);
+  c.y = min(max((int)floorf((y - g.lo[1]) * g.inv_h), 0), g.n[1] - 1);
+  c.z = min(max((int)floorf((z - g.lo[2]) * g.inv_h), 0), g.n[2] - 1);
+  return c;
+}
+__device__ __forceinline__ int grid_cell(const KnnGrid& g, int3 c) { return (c.z * g.n[1] + c.y) * g.n[0] + c.x; }
+
+__global__ void __launch_bounds__(256) k_knn_count(const float* __restrict__ ref, int64_t R,
+                                                   const KnnGrid* __restrict__ gp, int* cells, int* cell_of) {
+  const KnnGrid g = *gp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __ldg(ref + i * 3), y = __ldg(ref + i * 3 + 1), z = __ldg(ref + i * 3 + 2);
+    int cell = -1;
+    if (x == x && y == y && z == z) {  // NaN points are never anybody's neighbour (d2 = NaN fails `<`)
+      cell = grid_cell(g, grid_coord(g, x, y, z));
+      atomicAdd(cells + cell, 1);
+    }
+    cell_of[i] = cell;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_knn_fill(const float* __restrict__ ref, int64_t R, int* cells,
+                                                  const int* __restrict__ cell_of, float4* sorted) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < R; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cell = cell_of[i];
+    if (cell < 0) continue;
+    const int pos = atomicAdd(cells + cell, 1);  // starts -> ends
+    sorted[pos] = make_float4(__ldg(ref + i * 3), __ldg(ref + i * 3 + 1), __ldg(ref + i * 3 + 2),
+                              __int_as_float((int)i));
+  }
+}
+
+// SELF: queries are the reference points themselves, processed in cell order (coherent warps)
+template <bool SELF>
+__global__ void __launch_bounds__(128) k_knn_query(const float* __restrict__ query, int64_t Q,
+                                                   const KnnGrid* __restrict__ gp, const int* __restrict__ cell_end,
+                                                   const float4* __restrict__ sorted, int64_t R_sorted_hint,
+                                                   int K, int skip, float* __restrict__ mean_out) {
+  const KnnGrid g = *gp;
+  const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= Q) return;
+  float qx, qy, qz;
+  int64_t out_i = qi;
+  if (SELF) {
+    // sorted holds only the finite points: the tail of an array with NaN points is unused
+    const int total_sorted = __ldg(cell_end + (int64_t)g.n[0] * g.n[1] * g.n[2] - 1);
+    if (qi >= total_sorted) return;
+    const float4 p = __ldg(sorted + qi);
+    qx = p.x;
+    qy = p.y;
+    qz = p.z;
+    out_i = __float_as_int(p.w);
+  } else {
+    qx = __ldg(query + qi * 3);
+    qy = __ldg(query + qi * 3 + 1);
+    qz = __ldg(query + qi * 3 + 2);
+  }
+  (void)R_sorted_hint;
+  float best[kGridMaxK];
+#pragma unroll
+  for (int i = 0; i < kGridMaxK; ++i) best[i] = kInfF();
+  float kth = kInfF();
+  const int3 c = grid_coord(g, qx, qy, qz);
+  const int rmax = max(g.n[0], max(g.n[1], g.n[2]));
+  for (int r = 0; r <= rmax; ++r) {
+    const int z0 = max(c.z - r, 0), z1 = min(c.z + r, g.n[2] - 1);
+    const int y0 = max(c.y - r, 0), y1 = min(c.y + r, g.n[1] - 1);
+    const int x0 = max(c.x - r, 0), x1 = min(c.x + r, g.n[0] - 1);
+    for (int z = z0; z <= z1; ++z) {
+      const bool zface = (z == c.z - r) || (z == c.z + r);
+      for (int y = y0; y <= y1; ++y) {
+        const bool face = zface || (y == c.y - r) || (y == c.y + r);
+        const int row = (z * g.n[1] + y) * g.n[0];
+        // a face row of the shell: the whole x-run; an interior row: only its two end cells
+        for (int part = 0; part < (face ? 1 : 2); ++part) {
+          int xa, xb;
+          if (face) {
+            xa = x0;
+            xb = x1;
+          } else {
+            xa = xb = (part == 0) ? c.x - r : c.x + r;
+            if (xa < 0 || xa >= g.n[0] || (part == 1 && r == 0)) continue;
+          }
+          const int s = __ldg(cell_end + row + xa - 1);
+          const int e = __ldg(cell_end + row + xb);
+          for (int j = s; j < e; ++j) {
+            const float4 p = __ldg(sorted + j);
+            const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+            const float d = dx * dx + dy * dy + dz * dz;
+            if (d < kth) {
+              float cd = d;
+#pragma unroll
+              for (int t = 0; t < kGridMaxK; ++t) {
+                if (t < K) {
+                  const float b = best[t];
+                  const bool lt = cd < b;
+                  best[t] = lt ? cd : b;
+                  cd = lt ? b : cd;
+                }
+              }
+              float k2 = best[0];
+#pragma unroll
+              for (int t = 1; t < kGridMaxK; ++t)
+                if (t == K - 1) k2 = best[t];
+              kth = k2;
+            }
+          }
+        }
+      }
+    }
+    // every unvisited point lies outside the cube of cells [c - r, c + r]; sides of the cube that
+    // reach the grid boundary have nothing behind them
+    float bound = kInfF();
+    const float q[3] = {qx, qy, qz};
+    const int cc[3] = {c.x, c.y, c.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (cc[a] - r > 0) bound = fminf(bound, q[a] - (g.lo[a] + (float)(cc[a] - r) * g.h));
+      if (cc[a] + r < g.n[a] - 1) bound = fminf(bound, (g.lo[a] + (float)(cc[a] + r + 1) * g.h) - q[a]);
+    }
+    if (bound == kInfF()) break;                 // the cube covers the whole grid
+    bound = fmaxf(bound - 1e-4f * g.h, 0.0f);    // slack for the rounding of the cell assignment
+    if (kth <= bound * bound) break;
+  }
+  const int kk = K;  // (the caller guarantees R >= K on this path)
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < kGridMaxK; ++t)
+    if (t >= skip && t < kk && best[t] < kInfF()) sum += best[t];
+  int cnt = 0;
+#pragma unroll
+  for (int t = 0; t < kGridMaxK; ++t)
+    if (t >= skip && t < kk && best[t] < kInfF()) ++cnt;
+  mean_out[out_i] = cnt > 0 ? sum / (float)cnt : 0.f;
+}
+
+// Host driver used by pgdvs_knn_mean_dist (knn.cu) when the caller provides the workspace.
+size_t knn_grid_workspace_bytes(int64_t R) { return make_knn_grid_layout(R).total; }
+
+int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t R, int K, int skip,
+                       float* mean_out, void* workspace, cudaStream_t stream) {
+  const KnnGridLayout L = make_knn_grid_layout(R);
+  char* ws = static_cast<char*>(workspace);
+  KnnGrid* grid = reinterpret_cast<KnnGrid*>(ws + L.off_grid);
+  int* bbox = reinterpret_cast<int*>(ws + L.off_bbox);
+  int* cells = reinterpret_cast<int*>(ws + L.off_cells);
+  int* cell_of = reinterpret_cast<int*>(ws + L.off_cell_of);
+  float4* sorted = reinterpret_cast<float4*>(ws + L.off_sorted);
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.off_zero_end, stream);
+  if (e != cudaSuccess) return (int)e;
+  const int blocks = (int)((R + 255) / 256 < 148 * 8 ? (R + 255) / 256 : 148 * 8);
+  k_knn_bbox_init<<<1, 32, 0, stream>>>(bbox);
+  k_knn_bbox<<<blocks, 256, 0, stream>>>(ref, R, bbox);
+  float* est = reinterpret_cast<float*>(ws + L.off_est);
+  k_knn_sample<<<kGridSamples, 256, 0, stream>>>(ref, R, K, est);
+  k_knn_setup<<<1, 32, 0, stream>>>(bbox, R, est, grid);
+  k_knn_count<<<blocks, 256, 0, stream>>>(ref, R, grid, cells, cell_of);
+  if (int rc = check_launch()) return rc;
+  if (int rc = scan_exclusive_inplace(cells, L.scan_tiles, reinterpret_cast<unsigned long long*>(ws + L.off_state),
+                                      reinterpret_cast<int*>(ws + L.off_ticket), stream))
+    return rc;
+  k_knn_fill<<<blocks, 256, 0, stream>>>(ref, R, cells, cell_of, sorted);
+  const unsigned qb = (unsigned)((Q + 127) / 128);
+  if (query == ref && Q == R) {
+    // points with NaN coordinates are not in the sorted array: like the brute-force kernel they
+    // get +inf (no finite neighbour distance)
+    k_fill_f32<<<blocks, 256, 0, stream>>>(mean_out, Q, kInfF());
+    k_knn_query<true><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
+  } else {
+    k_knn_query<false><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
+  }
+  return check_launch();
+}
+
+}  // namespace pgdvs

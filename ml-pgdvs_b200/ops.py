@@ -283,10 +283,15 @@ def knn_mean_dist(query: torch.Tensor, ref: torch.Tensor, K: int, skip_first: in
     q = _f32c(query).reshape(-1, 3)
     r = _f32c(ref.to(dev)).reshape(-1, 3)
     out = torch.empty((q.shape[0],), dtype=torch.float32, device=dev)
+    L = _cabi.lib()
+    nbytes = ctypes.c_size_t(0)
+    _cabi.check(L.pgdvs_knn_workspace_bytes(q.shape[0], r.shape[0], ctypes.byref(nbytes)), "pgdvs_knn_workspace_bytes")
+    ws = _WS.get(dev, nbytes.value, tag="knn")  # uniform-grid scratch (large clouds)
     with torch.cuda.device(dev):
-        _cabi.check(_cabi.lib().pgdvs_knn_mean_dist(q.data_ptr(), q.shape[0], r.data_ptr(), r.shape[0],
-                                                    int(K), int(skip_first), out.data_ptr(), None, 0,
-                                                    _stream_ptr(dev)), "pgdvs_knn_mean_dist")
+        _cabi.check(L.pgdvs_knn_mean_dist(q.data_ptr(), q.shape[0], r.data_ptr(), r.shape[0],
+                                          int(K), int(skip_first), out.data_ptr(), _aligned_ptr(ws), nbytes.value,
+                                          _stream_ptr(dev)), "pgdvs_knn_mean_dist")
+    LAUNCHES["count"] += 1
     return out
 
 

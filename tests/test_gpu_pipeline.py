@@ -492,3 +492,45 @@ def test_pytorch3d_facade_generic_equals_fused():
         assert fused.shape == (1, H, W, 3)
         np.testing.assert_allclose(fused.cpu().numpy(), two_step.cpu().numpy(), atol=IMG_ATOL, rtol=0)
         assert float((frags.idx >= 0).float().mean()) > 0.05
+
+
+def _knn_brute(q, r, K, skip):
+    """the brute-force kernel (no workspace -> never the grid path)"""
+    import pgdvs_b200
+    from pgdvs_b200 import _cabi, ops
+    out = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
+    _cabi.check(_cabi.lib().pgdvs_knn_mean_dist(q.data_ptr(), q.shape[0], r.data_ptr(), r.shape[0], K, skip,
+                                                out.data_ptr(), None, 0, ops._stream_ptr(q.device)), "knn")
+    return out
+
+
+@pytest.mark.parametrize("kind", ["surface", "volume", "clustered", "planar_dups"])
+def test_knn_grid_equals_brute_force(kind):
+    """The uniform-grid search (large clouds) is exact: same K-nearest statistics as brute force."""
+    import pgdvs_b200
+    g = torch.Generator().manual_seed(17)
+    P = 30000
+    if kind == "surface":  # a depth-map-like height field
+        uv = torch.rand(P, 2, generator=g) * torch.tensor([8.0, 5.0])
+        z = 4 + torch.sin(uv[:, :1] * 1.3) + 0.02 * torch.randn(P, 1, generator=g)
+        pts = torch.cat([uv, z], 1)
+    elif kind == "volume":
+        pts = torch.rand(P, 3, generator=g) * torch.tensor([3.0, 2.0, 4.0])
+    elif kind == "clustered":
+        centres = torch.randn(12, 3, generator=g) * 3
+        pts = centres[torch.randint(0, 12, (P,), generator=g)] + 0.05 * torch.randn(P, 3, generator=g)
+        pts[:200] = torch.randn(200, 3, generator=g) * 30  # far outliers stretch the box
+    else:  # a plane with many exact duplicates
+        pts = torch.cat([torch.rand(P, 2, generator=g), torch.zeros(P, 1)], 1)
+        pts[1000:2000] = pts[:1000]
+    d = _dev()
+    pts = pts.float().contiguous().to(d)
+    for K, skip in ((51, 1), (7, 0)):
+        fast = pgdvs_b200.ops.knn_mean_dist(pts, pts, K, skip_first=skip)
+        slow = _knn_brute(pts, pts, K, skip)
+        np.testing.assert_allclose(fast.cpu().numpy(), slow.cpu().numpy(), rtol=1e-5, atol=1e-9)
+    # cross search: queries that lie (far) outside the reference cloud's box
+    q = (pts[:5000] * 1.7 + torch.tensor([0.5, -2.0, 9.0], device=d)).contiguous()
+    fast = pgdvs_b200.ops.knn_mean_dist(q, pts, 51, skip_first=0)
+    slow = _knn_brute(q, pts, 51, 0)
+    np.testing.assert_allclose(fast.cpu().numpy(), slow.cpu().numpy(), rtol=1e-5, atol=1e-9)
