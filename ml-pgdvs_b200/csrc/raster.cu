@@ -4,23 +4,27 @@
 // pgdvs_renderer_dyn.py:690-717 with bin_size=0), PointsRenderer's weight computation,
 // the NormWeighted/Alpha compositors, the background fill and PGDVS's second all-ones
 // render for the mask (pgdvs_renderer_dyn.py:719-722) with ONE pass:
-//   * each thread owns one pixel and keeps its K nearest hits as a z-sorted list of
-//     (z, record slot) pairs in registers;
+//   * each thread walks one pixel and keeps its K nearest hits sorted in registers — as ONE
+//     32-bit key per slot (z pattern + candidate ordinal, see KeyList) in the tile kernel, as
+//     (z, slot) pairs (PairList) in the generic kernel;
 //   * candidates are only the records filed under cells within `halo` of the pixel — for
 //     every window row that is one contiguous run of the cell-sorted record array;
 //   * the hit test reproduces the reference arithmetic bit for bit (dist2_rn, strict <);
-//   * the common-case insertion is a branch-free compare-exchange chain on z alone; exact
-//     fp32 z ties (which the CPU rasterizer's (z, idx, dist2) priority queue orders by the
-//     smaller packed index) are DETECTED in the fast path and the few affected pixels are
-//     redone by a tie-aware slow path, so idx/zbuf/dists stay deterministic and bit-exact.
+//   * insertion is a min/max chain without payload moves (tile kernel: branch-free, two
+//     candidates per step); exact fp32 z ties (which the CPU rasterizer's (z, idx, dist2)
+//     priority queue orders by the smaller packed index) and keys that agree on their whole z
+//     part are DETECTED and the few affected pixels are redone by an exact (z, idx) rescan, so
+//     idx/zbuf/dists stay deterministic and bit-exact.
 //
 // Two kernels share that logic:
-//   k_raster_tile  (3x3 windows, scalar radius — every PGDVS configuration with r_px < 1.5):
-//                  a 32x8-pixel CTA fetches the 10 row runs its pixels can touch into shared
-//                  memory with 1-D TMA bulk copies (cp.async.bulk + mbarrier; the runs ARE
-//                  contiguous because records are sorted by cell), then every lookup of the
-//                  candidate loop and of the epilogue is a shared-memory read.
-//   k_raster_cells (any halo, per-point radii): candidates are read through L1.
+//   k_raster_tile  (halo 1..3, scalar radius, K <= 32 — the PGDVS configurations): a 32x8-pixel
+//                  CTA fetches the 8 + 2*halo row runs its pixels can touch into shared memory
+//                  with 1-D TMA bulk copies (cp.async.bulk + mbarrier; the runs ARE contiguous
+//                  because records are sorted by cell), re-assigns its pixels to threads in
+//                  order of candidate count, walks them with shared-memory reads only, hands the
+//                  winners back to each pixel's own thread and runs the epilogue in raster order.
+//   k_raster_cells (any halo, per-point radii, K <= 150): candidates are read through L1.
+// DESIGN.md 4.1 walks through the tile kernel step by step.
 #include "common.cuh"
 
 namespace pgdvs {
@@ -514,37 +518,8 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
 // ---------------------------------------------------------------------------------------
 constexpr int kTileW = 32, kTileH = 8;
 
-// Same walk with the general (z, slot) list: long lists, unstaged tiles, tiles whose z range does
-// not leave room for exact 32-bit keys.  The payload is the record slot itself.
-template <int KP, int HALO>
-__device__ __forceinline__ bool walk_tile_pairs(const RasterParams& p, const PixelCtx& c,
-                                                const int (&rs)[2 * HALO + 1], const int (&rl)[2 * HALO + 1],
-                                                bool staged, const StagedRecords staged_rec, Slots<KP>& sl) {
-  constexpr int SPAN = 2 * HALO + 1;
-  PairList<KP> q;
-  q.init();
-#pragma unroll
-  for (int r = 0; r < SPAN; ++r) {
-    const int s = rs[r], e = rs[r] + rl[r];
-    if (staged) {
-      for (int j = s; j < e; ++j) {
-        const float4 a = staged_rec.a(j);
-        q.push(hit_test<false>(c, a, nullptr, j), a.z, j);
-      }
-    } else {
-      for (int j = s; j < e; ++j) {
-        const float4 a = __ldg(p.recA + rec_a(j));
-        q.push(hit_test<false>(c, a, nullptr, j), a.z, j);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < KP; ++i) sl.s[i] = q.s[i];
-  return q.ambiguous(p.K);
-}
-
-// tile kernel: lists up to this length use sorted 32-bit keys (branch-free up to
-// PGDVS_RASTER_BRANCHFREE_MAXK, with a "can it enter?" pre-test above), longer ones the pair list
+// tile kernel: its lists (K <= 32) are sorted 32-bit keys, branch-free up to
+// PGDVS_RASTER_BRANCHFREE_MAXK and with a "can it enter?" pre-test above that
 #ifndef PGDVS_TILE_KEYS_MAXK
 #define PGDVS_TILE_KEYS_MAXK 32
 #endif
@@ -868,7 +843,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
     }
     amb = inside && ((KP <= 32 && p.K == KP) ? q.ambiguous_full(kc) : q.ambiguous(p.K, kc));
   } else {
-    amb = walk_tile_pairs<KP, HALO>(p, c, rs, rl, staged, staged_rec, sl) && inside;
+    static_assert(KP <= PGDVS_TILE_KEYS_MAXK, "longer lists use k_raster_cells");
   }
   if (!staged) {  // (uniform) slots are global indices: finish in walk order
     if (inside) finish_global<KP, false>(p, c, n, x, y, sl, amb);
