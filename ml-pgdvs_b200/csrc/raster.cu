@@ -497,7 +497,9 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
     const int e = __ldg(cs + (int64_t)ry * p.GW + span);
     for (int j = s; j < e; ++j) {
       const float4 a = __ldg(recA + rec_a(j));
-      q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
+      // depth first: once the list is full most candidates lie behind its last element and
+      // need no distance test at all (equal z still goes through: it may be a tie)
+      if (a.z <= q.z[KP - 1]) q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
     }
   }
   Slots<KP> sl;
