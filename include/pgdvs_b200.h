@@ -282,6 +282,24 @@ int pgdvs_softsplat_dyn(const float* rgb1, const float* mask1, const float* nois
                         int W, float* out_rgb, float* out_mask, float* out_metric, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* --------------------------------------------------------------------------------------
+ * 8. Mesh mode ("next" row 4 of the scope table; dyn_render_type = mesh).
+ *    Replaces pytorch3d MeshRasterizer (blur_radius = 0, faces_per_pixel = 1, bin_size = 0,
+ *    cull_backfaces = False, clip_barycentric_coords = False) + the reference's SimpleShader
+ *    (pgdvs/utils/pytorch3d_utils.py:50-67) + the second all-ones render for the mask, as called
+ *    by PGDVSDynamicRenderer.render_dyn_mesh (pgdvs_renderer_dyn.py:606-655), for ONE mesh.
+ *    verts_ndc f32 [V,3] (x_ndc, y_ndc, z_view: pgdvs_project_points), faces i32 [F,3],
+ *    vert_rgb f32 [V,3] (nullable when image == NULL).  Outputs (each nullable):
+ *    pix_to_face i32 [H,W] (-1 = background), zbuf f32 [H,W], bary f32 [H,W,3] (-1 filled),
+ *    image f32 [H,W,3] (black background), mask f32 [H,W,1].
+ *    workspace: pgdvs_mesh_workspace_bytes, 8-byte aligned.
+ * ------------------------------------------------------------------------------------ */
+int pgdvs_mesh_workspace_bytes(int H, int W, size_t* bytes);
+int pgdvs_rasterize_mesh(const float* verts_ndc, int64_t V, const int32_t* faces, int64_t F, int H,
+                         int W, int perspective_correct, const float* vert_rgb, int32_t* pix_to_face,
+                         float* zbuf, float* bary, float* image, float* mask, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,5 +17,5 @@ from .renderer import (AlphaCompositor, NormWeightedCompositor, PerspectiveCamer
                        PointFragments, PointsRasterizationSettings, PointsRasterizer, PointsRenderer,
                        cameras_from_opencv_projection, rasterize_points)
 from .dyn_renderer import PGDVSDynamicRenderer, SourcePair, render_views  # noqa: F401
-from . import track, softsplat  # noqa: F401
+from . import track, softsplat, mesh  # noqa: F401
 from .track import StaticGeoPointRenderer  # noqa: F401

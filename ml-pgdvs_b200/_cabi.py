@@ -24,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist", "pgdvs_knn_points",
     "pgdvs_track_workspace_bytes", "pgdvs_track_points", "pgdvs_quantize_u8",
     "pgdvs_softsplat_forward", "pgdvs_softsplat_workspace_bytes", "pgdvs_softsplat_dyn",
+    "pgdvs_mesh_workspace_bytes", "pgdvs_rasterize_mesh",
 )
 
 
@@ -126,6 +127,12 @@ def lib():
     L.pgdvs_softsplat_dyn.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]
+    L.pgdvs_mesh_workspace_bytes.restype = c_int
+    L.pgdvs_mesh_workspace_bytes.argtypes = [c_int, c_int, POINTER(c_size_t)]
+    L.pgdvs_rasterize_mesh.restype = c_int
+    L.pgdvs_rasterize_mesh.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]
     L.pgdvs_knn_points.restype = c_int
     L.pgdvs_knn_points.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
     if L.pgdvs_abi_version() != 1:

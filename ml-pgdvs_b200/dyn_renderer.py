@@ -489,12 +489,50 @@ class PGDVSDynamicRenderer(torch.nn.Module):
                     compositor=_cfg(render_cfg, "dyn_render_compositor"), background=(0.0, 0.0, 0.0),
                     return_fragments=False)
                 info["rgb"], info["mask"] = out["image"][0], out["mask"][0]
+        elif _cfg(render_cfg, "dyn_render_type") == "mesh":
+            # pgdvs_renderer_dyn.py:512-521: grid-topology triangles over the valid pixels
+            from . import mesh as _mesh
+            info["rgb"], info["mask"] = _mesh.render_dyn_mesh(
+                rows=src_pix // W, cols=src_pix % W, dyn_mask=valid_mask, dyn_pcl=pcl, rgbs=rgb,
+                flat_cam=flat_cam_tgt, for_debug=for_debug)
         elif _cfg(render_cfg, "dyn_render_type") == "softsplat":
             info["rgb"] = torch.zeros_like(rgb_1)
             info["mask"] = torch.zeros_like(dyn_mask_1)
         else:
             raise ValueError(_cfg(render_cfg, "dyn_render_type"))
         return flow_1_to_tgt, valid_mask, info
+
+    # ---- mesh mode: one compute_dyn_pcl call per view like upstream (:77-155); this mode keeps the
+    #      reference's per-view loop (face lists are built per view), it is not the batched hot path
+    def _forward_mesh(self, data, render_cfg, static_rgb, for_debug):
+        n_b, _, H, W, _ = data["rgb_src_temporal"].shape
+        dev = data["rgb_src_temporal"].device
+        rgbs, masks = [], []
+        for b in range(n_b):
+            fs = data["flat_cam_src_temporal"][b]
+            if float(data["dyn_mask_src_temporal"][b, 0].sum()) > 0:  # (:104)
+                _, _, info = self.compute_dyn_pcl(
+                    dyn_mask_1=data["dyn_mask_src_temporal"][b, 0], rgb_1=data["rgb_src_temporal"][b, 0],
+                    depth_1=data["depth_src_temporal"][b, 0], flow_12=data["flow_fwd"][b],
+                    flow_12_occ_mask=data["flow_fwd_occ_mask"][b], rgb_2=data["rgb_src_temporal"][b, 1],
+                    depth_2=data["depth_src_temporal"][b, 1], K_1=fs[0, 2:18].reshape(4, 4),
+                    c2w_1=fs[0, 18:34].reshape(4, 4), K_2=fs[1, 2:18].reshape(4, 4), c2w_2=fs[1, 18:34].reshape(4, 4),
+                    flat_cam_tgt=data["flat_cam_tgt"][b], time_1=data["time_src_temporal"][b, 0],
+                    time_2=data["time_src_temporal"][b, 1], time_tgt=data["time_tgt"][b, 0], render_cfg=render_cfg,
+                    for_debug=for_debug)
+                rgbs.append(info["rgb"])
+                masks.append(info["mask"])
+            else:
+                rgbs.append(torch.zeros(H, W, 3, device=dev))
+                masks.append(torch.zeros(H, W, 1, device=dev))
+        dyn_rgb = torch.stack(rgbs, 0).permute(0, 3, 1, 2).contiguous()
+        dyn_mask = torch.stack(masks, 0).permute(0, 3, 1, 2).contiguous()
+        rgb_final, mask_final, combined = ops.merge_blend(dyn_rgb, dyn_mask, None, None, static_rgb)
+        info = {"temporal_closest_rgb": dyn_rgb, "temporal_closest_mask": dyn_mask,
+                "temporal_track_rgb": torch.zeros_like(dyn_rgb), "temporal_track_mask": torch.zeros_like(dyn_mask)}
+        if combined is not None:
+            info["combined_rgb"] = combined
+        return rgb_final, mask_final, info
 
     # ---- pgdvs_renderer_dyn.py:157-209: flow frame 1 -> target from the projected cloud (:470-503),
     #      then the fused softmax splat (softsplat.softsplat_dyn)
@@ -539,8 +577,10 @@ class PGDVSDynamicRenderer(torch.nn.Module):
                 softsplat_noise: Optional[torch.Tensor] = None):
         render_cfg = render_cfg if render_cfg is not None else DEFAULT_RENDER_CFG
         render_type = _cfg(render_cfg, "dyn_render_type")
-        if render_type not in ("pcl", "softsplat"):
-            raise NotImplementedError("dyn_render_type must be 'pcl' or 'softsplat' (mesh mode is not built)")
+        if render_type not in ("pcl", "softsplat", "mesh"):
+            raise ValueError(render_type)
+        if render_type == "mesh":
+            return self._forward_mesh(data, render_cfg, static_rgb, for_debug)
         n_b, _, H, W, _ = data["rgb_src_temporal"].shape
         dev = data["rgb_src_temporal"].device
         use_occ = bool(_cfg(render_cfg, "dyn_render_use_flow_consistency"))

@@ -375,3 +375,46 @@ def softsplat_dyn_render(*, rgb_1, dyn_mask_1, rgb_2, flow_1_to_tgt, flow_12, no
                             alpha=alpha)
     mask = (mask > 1e-3).float()
     return splat * mask, mask, metric
+
+
+# ----------------------------------------------------------------------------- mesh mode
+def mesh_faces_from_mask(rows, cols, H, W):
+    """Grid-topology faces of render_dyn_mesh (pgdvs_renderer_dyn.py:549-604): every valid pixel
+    (row, col) spawns (r,c),(r+1,c),(r+1,c+1) and (r,c),(r+1,c+1),(r,c+1); a face survives if its
+    three corners are in bounds and carry a vertex index > 0 (sic: vertex 0 never gets a face)."""
+    vert_idx = -torch.ones((H, W), dtype=torch.long)
+    vert_idx[rows, cols] = torch.arange(rows.shape[0])
+    c1 = torch.stack([torch.stack((rows, cols), 1), torch.stack((rows + 1, cols), 1),
+                      torch.stack((rows + 1, cols + 1), 1)], 1)
+    c2 = torch.stack([torch.stack((rows, cols), 1), torch.stack((rows + 1, cols + 1), 1),
+                      torch.stack((rows, cols + 1), 1)], 1)
+    cand = torch.cat((c1, c2), 0)
+    inb = torch.all((cand[..., 0] >= 0) & (cand[..., 0] < H) & (cand[..., 1] >= 0) & (cand[..., 1] < W), dim=1)
+    cand = cand[inb]
+    fv = vert_idx[cand[..., 0], cand[..., 1]]
+    return fv[torch.all(fv > 0, dim=1)]
+
+
+def render_dyn_mesh(*, rows, cols, dyn_mask, dyn_pcl, rgbs, flat_cam):
+    """PGDVSDynamicRenderer.render_dyn_mesh (pgdvs_renderer_dyn.py:542-669): MeshRasterizer
+    (blur 0, 1 face per pixel, naive) + SimpleShader (vertex colours interpolated with the
+    perspective-correct barycentrics, hard blend on a black background); the mask is the same
+    render with all-ones vertex colours, > 0.  Returns (img [H,W,3], mask [H,W,1], fragments)."""
+    H, W, _ = dyn_mask.shape
+    faces = mesh_faces_from_mask(rows, cols, H, W)
+    if faces.shape[0] == 0:
+        return torch.zeros(H, W, 3), torch.zeros(H, W, 1), None
+    ndc = world_to_ndc(dyn_pcl, camera_from_flat_cam(flat_cam))
+    fv = ndc[faces]  # [F,3,3]
+    p2f, zbuf, bary, _ = _raster.rasterize_meshes(fv.numpy(), (H, W), 1, 0.0, True)
+    p2f_t = torch.from_numpy(p2f[..., 0]).long()
+    bary_t = torch.from_numpy(bary[..., 0, :])
+    hit = p2f_t >= 0
+    fcol = rgbs[faces]  # [F,3,3] colours of the face corners
+    idx = p2f_t.clamp(min=0)
+    # interpolate_face_attributes: sum_i bary_i * attr_i ; background pixels -> 0
+    img = (bary_t[..., :, None] * fcol[idx]).sum(dim=-2)
+    ones = bary_t.sum(dim=-1, keepdim=True)
+    img = torch.where(hit[..., None], img, torch.zeros_like(img))
+    mask = (torch.where(hit[..., None], ones, torch.zeros_like(ones)) > 0.0).float()
+    return img, mask, (p2f[..., 0], zbuf[..., 0], bary[..., 0, :], faces)

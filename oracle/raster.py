@@ -51,6 +51,9 @@ def _load():
         lib.oracle_composite.restype = ctypes.c_int
         lib.oracle_composite.argtypes = [lp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, fp]
+        lib.oracle_rasterize_meshes_naive.restype = ctypes.c_int
+        lib.oracle_rasterize_meshes_naive.argtypes = [fp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                      ctypes.c_float, ctypes.c_int, ip, fp, fp, fp]
         for name in ("oracle_pixel_center_x", "oracle_pixel_center_y"):
             fn = getattr(lib, name)
             fn.restype = ctypes.c_float
@@ -174,3 +177,24 @@ def render_points(points, first_idx, num_pts, features_pc, image_size, radius, K
         img[mask] = bg[: img.shape[-1]]
         return img, (idx, zbuf, dists)
     return np.transpose(img, (0, 2, 3, 1)).copy(), (idx, zbuf, dists)
+
+
+def rasterize_meshes(face_verts, image_size, faces_per_pixel=1, blur_radius=0.0, perspective_correct=True):
+    """pytorch3d `rasterize_meshes(..., bin_size=0)` for ONE mesh on CPU (naive algorithm).
+    face_verts [F,3,3] f32 (x_ndc, y_ndc, z_view).  Returns (pix_to_face i32 [H,W,K], zbuf f32 [H,W,K],
+    bary f32 [H,W,K,3], dists f32 [H,W,K]), -1 filled."""
+    lib = _load()
+    fv = np.ascontiguousarray(face_verts, dtype=np.float32).reshape(-1, 3, 3)
+    H, W = int(image_size[0]), int(image_size[1])
+    K = int(faces_per_pixel)
+    p2f = np.empty((H, W, K), np.int32)
+    zbuf = np.empty((H, W, K), np.float32)
+    bary = np.empty((H, W, K, 3), np.float32)
+    dists = np.empty((H, W, K), np.float32)
+    rc = lib.oracle_rasterize_meshes_naive(_ptr(fv, ctypes.c_float), fv.shape[0], H, W, K, float(blur_radius),
+                                           1 if perspective_correct else 0, _ptr(p2f, ctypes.c_int32),
+                                           _ptr(zbuf, ctypes.c_float), _ptr(bary, ctypes.c_float),
+                                           _ptr(dists, ctypes.c_float))
+    if rc != 0:
+        raise RuntimeError(f"oracle rasterize_meshes failed rc={rc}")
+    return p2f, zbuf, bary, dists

@@ -361,3 +361,102 @@ int oracle_composite(const int64_t* idx, const float* alphas, const float* featu
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Mesh rasterization, faces_per_pixel = 1 semantics generalised to K (PARITY UNPINNED:
+// restated from the published pytorch3d 0.7.4 algorithm, csrc/rasterize_meshes/
+// rasterize_meshes_cpu.cpp `RasterizeMeshesNaiveCpu` and csrc/utils/geometry_utils.h).
+// Reached from PGDVSDynamicRenderer.render_dyn_mesh (pgdvs_renderer_dyn.py:542-669) through
+// MeshRasterizer with blur_radius = 0, bin_size = 0, cull_backfaces = False,
+// clip_barycentric_coords = False, perspective_correct = True (PerspectiveCameras).
+//   face_verts f32 [F,3,3] (x_ndc, y_ndc, z_view); one mesh.
+//   outputs -1 filled: pix_to_face i32 [H,W,K], zbuf f32 [H,W,K], bary f32 [H,W,K,3],
+//   dists f32 [H,W,K] (signed squared distance to the nearest edge; negative inside).
+// ---------------------------------------------------------------------------------------
+namespace {
+constexpr float kMeshEps = 1e-8f;
+
+inline float EdgeFunction(float px, float py, float ax, float ay, float bx, float by) {
+  return (px - ax) * (by - ay) - (py - ay) * (bx - ax);
+}
+
+inline float PointLineDist2(float px, float py, float ax, float ay, float bx, float by) {
+  // squared distance from p to segment ab (geometry_utils.h PointLineDistanceForward)
+  const float abx = bx - ax, aby = by - ay;
+  const float l2 = abx * abx + aby * aby;
+  if (l2 <= kMeshEps) return (px - bx) * (px - bx) + (py - by) * (py - by);
+  float t = (abx * (px - ax) + aby * (py - ay)) / l2;
+  t = std::min(std::max(t, 0.0f), 1.0f);
+  const float qx = ax + t * abx, qy = ay + t * aby;
+  return (px - qx) * (px - qx) + (py - qy) * (py - qy);
+}
+
+struct FaceHit {
+  float z;
+  int f;
+  float dist, b0, b1, b2;
+};
+inline bool face_less(const FaceHit& a, const FaceHit& b) {
+  return std::make_tuple(a.z, a.f, a.dist, a.b0, a.b1, a.b2) < std::make_tuple(b.z, b.f, b.dist, b.b0, b.b1, b.b2);
+}
+}  // namespace
+
+extern "C" int oracle_rasterize_meshes_naive(const float* face_verts, int64_t F, int H, int W, int K,
+                                             float blur_radius, int perspective_correct, int32_t* pix_to_face,
+                                             float* zbuf, float* bary, float* dists) {
+  if (H <= 0 || W <= 0 || K < 1 || F < 0) return 1;
+  const float blur = std::sqrt(blur_radius);
+  for (int yi = 0; yi < H; ++yi) {
+    const float yf = PixToNonSquareNdc(H - 1 - yi, H, W);
+    for (int xi = 0; xi < W; ++xi) {
+      const float xf = PixToNonSquareNdc(W - 1 - xi, W, H);
+      std::vector<FaceHit> q;  // kept sorted ascending, at most K entries (== the priority queue)
+      for (int64_t f = 0; f < F; ++f) {
+        const float* v = face_verts + f * 9;
+        const float x0 = v[0], y0 = v[1], z0 = v[2], x1 = v[3], y1 = v[4], z1 = v[5], x2 = v[6], y2 = v[7], z2 = v[8];
+        const float xmin = std::min(x0, std::min(x1, x2)), xmax = std::max(x0, std::max(x1, x2));
+        const float ymin = std::min(y0, std::min(y1, y2)), ymax = std::max(y0, std::max(y1, y2));
+        const float zmax = std::max(z0, std::max(z1, z2));
+        // CheckPointOutsideBoundingBox (+ faces entirely behind the camera)
+        if (xf < xmin - blur || xf > xmax + blur || yf < ymin - blur || yf > ymax + blur || zmax < kMeshEps) continue;
+        const float face_area = EdgeFunction(x2, y2, x0, y0, x1, y1);
+        if (face_area <= kMeshEps && face_area >= -kMeshEps) continue;  // degenerate
+        const float area = face_area + kMeshEps;
+        const float w0 = EdgeFunction(xf, yf, x1, y1, x2, y2) / area;
+        const float w1 = EdgeFunction(xf, yf, x2, y2, x0, y0) / area;
+        const float w2 = EdgeFunction(xf, yf, x0, y0, x1, y1) / area;
+        float b0 = w0, b1 = w1, b2 = w2;
+        if (perspective_correct) {
+          const float t0 = w0 * z1 * z2, t1 = z0 * w1 * z2, t2 = z0 * z1 * w2;
+          const float denom = std::max(t0 + t1 + t2, kMeshEps);
+          b0 = t0 / denom;
+          b1 = t1 / denom;
+          b2 = t2 / denom;
+        }
+        const float pz = b0 * z0 + b1 * z1 + b2 * z2;
+        if (pz < 0) continue;
+        const float e0 = PointLineDist2(xf, yf, x0, y0, x1, y1);
+        const float e1 = PointLineDist2(xf, yf, x0, y0, x2, y2);
+        const float e2 = PointLineDist2(xf, yf, x1, y1, x2, y2);
+        const float dist = std::min(e0, std::min(e1, e2));
+        const bool inside = w0 > 0.0f && w1 > 0.0f && w2 > 0.0f;
+        if (!inside && dist >= blur_radius) continue;
+        FaceHit h{pz, (int)f, inside ? -dist : dist, b0, b1, b2};
+        auto it = std::upper_bound(q.begin(), q.end(), h, face_less);
+        q.insert(it, h);
+        if ((int)q.size() > K) q.pop_back();
+      }
+      const int64_t base = ((int64_t)yi * W + xi) * K;
+      for (int k = 0; k < K; ++k) {
+        const bool has = k < (int)q.size();
+        pix_to_face[base + k] = has ? q[k].f : -1;
+        zbuf[base + k] = has ? q[k].z : -1.0f;
+        dists[base + k] = has ? q[k].dist : -1.0f;
+        bary[(base + k) * 3 + 0] = has ? q[k].b0 : -1.0f;
+        bary[(base + k) * 3 + 1] = has ? q[k].b1 : -1.0f;
+        bary[(base + k) * 3 + 2] = has ? q[k].b2 : -1.0f;
+      }
+    }
+  }
+  return 0;
+}

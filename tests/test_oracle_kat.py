@@ -157,3 +157,29 @@ def test_softsplat_forward_known_answers():
     flow[0, 0, 1, 1], flow[0, 1, 1, 1] = 2.0, 0.0
     out = ref.softsplat_forward(x, flow)
     assert out[0, 0, 1, 3] == 2.0 and out.sum() == 2.0
+
+
+def test_mesh_rasterizer_known_answers():
+    """RasterizeMeshesNaiveCpu restatement by hand: coverage is 'all barycentrics > 0', depth is the
+    perspective-correct interpolation, nearer face wins, z ties go to the smaller face index,
+    degenerate / behind-the-camera faces are skipped."""
+    # a big triangle (z 2..4) and a small nearer one (z = 1) over the centre of a 4x4 image
+    big = [[0.9, 0.9, 2.0], [-0.9, 0.9, 2.0], [0.0, -0.9, 4.0]]
+    small = [[0.4, 0.4, 1.0], [-0.4, 0.4, 1.0], [0.0, -0.4, 1.0]]
+    fv = np.array([big, small], np.float32)
+    p2f, z, b, d = raster.rasterize_meshes(fv, (4, 4))
+    assert p2f[0, 1, 0] == 0 and p2f[3, 0, 0] == -1
+    assert p2f[1, 1, 0] == 1 and np.isclose(z[1, 1, 0], 1.0)  # pixel centre (0.25, 0.25) is inside the small face
+    assert np.isclose(b[1, 1, 0].sum(), 1.0) and np.all(b[1, 1, 0] > 0) and d[1, 1, 0] < 0
+    # perspective-correct depth: 1/z is what interpolates linearly
+    w = raster.rasterize_meshes(fv[:1], (4, 4), perspective_correct=False)[2][1, 1, 0]
+    zc = 1.0 / (w[0] / 2.0 + w[1] / 2.0 + w[2] / 4.0)
+    assert np.isclose(raster.rasterize_meshes(fv[:1], (4, 4))[1][1, 1, 0], zc, rtol=1e-6)
+    # exact tie: two copies of the same face -> the smaller index
+    assert raster.rasterize_meshes(np.stack([fv[1], fv[1]]), (4, 4))[0][1, 1, 0] == 0
+    # degenerate and behind-the-camera faces never cover anything
+    deg = np.array([[[0.5, 0.5, 1.0], [0.5, 0.5, 1.0], [-0.5, -0.5, 1.0]]], np.float32)
+    assert (raster.rasterize_meshes(deg, (4, 4))[0] >= 0).sum() == 0
+    behind = fv[1:].copy()
+    behind[..., 2] = -1.0
+    assert (raster.rasterize_meshes(behind, (4, 4))[0] >= 0).sum() == 0
