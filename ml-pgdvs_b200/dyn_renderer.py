@@ -129,6 +129,17 @@ class SourcePair:
             self.w1 = (t2 - tt) / (t2 - t1)  # pgdvs_renderer_dyn.py:385-386 (fp32 like torch)
             self.w2 = (tt - t1) / (t2 - t1)
 
+    @property
+    def keep(self):
+        """optional uint8 [H*W] survivor mask (the statistical outlier filter's verdict)"""
+        return self._keep
+
+    @keep.setter
+    def keep(self, value):
+        self._keep = value
+        self._rec = None   # the cached descriptor and group key embed the pointer
+        self._gkey = None
+
     def group_key(self):
         """Everything of a job except the target camera / view index (cached)."""
         if getattr(self, "_gkey", None) is None:
@@ -607,8 +618,14 @@ class PGDVSDynamicRenderer(torch.nn.Module):
             first = cloud["first_idx"].tolist()
             num = cloud["num_points"].tolist()
             knn = int(_cfg(render_cfg, "dyn_pcl_outlier_knn"))
-            for b in range(n_b):
+            keep_of_group = {}  # the filter lives in world space: views that share the source pair
+            for b in range(n_b):  # and the target time (e.g. the 12 cameras of a time step) share it
+                gk = pairs[b].group_key()
+                if gk in keep_of_group:
+                    pairs[b].keep = keep_of_group[gk]
+                    continue
                 keep = torch.zeros(H * W, dtype=torch.uint8, device=dev)
+                keep_of_group[gk] = keep
                 if num[b] > 0:
                     pw = cloud["xyz_world"][first[b]:first[b] + num[b]]
                     avg = ops.knn_mean_dist(pw, pw, knn + 1, skip_first=1)
