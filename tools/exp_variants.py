@@ -13,12 +13,16 @@ OUT = ROOT / "exp_libs"
 K8 = ["-DPGDVS_RASTER_EXP_K8"]  # only the K=8 instantiation: seconds instead of minutes per variant
 VARIANTS = {
     "base": K8,
+    "fill8": K8 + ["-DPGDVS_FILL_UNROLL=8"],
+    "fill2": K8 + ["-DPGDVS_FILL_UNROLL=2"],
+    "uwp_mb2": K8 + ["-DPGDVS_UWP_MINBLOCKS=2"],
+    "uwp_mb4": K8 + ["-DPGDVS_UWP_MINBLOCKS=4"],
 }
 if os.environ.get("PREBUILT"):  # time prebuilt exp_libs/lib_<name>.so files
     VARIANTS = {k: [] for k in os.environ["PREBUILT"].split(",")}
 if os.environ.get("VARIANTS"):
     VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ["VARIANTS"].split(",")}
-SRCS = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu"]
+SRCS = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu", "knn_grid.cu"]
 
 
 def build():
