@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(256) k_fill(BinParams p) {
   }
 }
 
-// Fused path: the uwp kernel already produced the cell of every point and the packed-order
-// records.  Each thread moves kFillUnroll points with all loads, then all atomics, then all
-// stores issued back to back.
+// Fused path: the uwp kernel already produced the packed-order records, cell id included.
+// Each thread moves kFillUnroll points with all loads, then all atomics, then all stores issued
+// back to back.
 #ifndef PGDVS_FILL_UNROLL
 #define PGDVS_FILL_UNROLL 4
 #endif

@@ -71,9 +71,10 @@ struct BinLayout {
   size_t off_state;   // uint64 [n_tiles]    decoupled look-back state
   size_t off_ticket;  // int32 [4]           scan ticket counter (+pad)
   size_t off_zero_end;  // everything in [0, off_zero_end) is zeroed before each binning
-  size_t off_cell_of; // int32  [P]          cell of every packed point (-1 = never rasterized)
-  size_t off_recA;    // float4 [P] stride kRecStride: (x_ndc, y_ndc, z, packed idx as int bits)
-  size_t off_recB;    // float4 [P] stride kRecStride: features (C<=4) or (f0,f1,f2,radius)
+  size_t off_cell_of; // int32  [P]          cell of every packed point (-1 = never rasterized);
+                      //                     staged path only (the fused path carries it in its records)
+  size_t off_recA;    // 32-byte records [P], cell-sorted: part A (x_ndc, y_ndc, z, packed idx as
+  size_t off_recB;    // int bits) and part B (features C<=4, or f0,f1,f2,radius) at rec_a(j) / rec_b(j)
   size_t total;
 };
 
@@ -146,8 +147,8 @@ inline BinLayout make_bin_layout(int N, int H, int W, int64_t P, float radius_ma
 // The fused path (uwp kernel counts cells itself) parks its not-yet-sorted records behind
 // the regular layout, so the rasterizer sees the same front part in both modes.
 struct FusedTail {
-  size_t off_preA;  // float4 [P]  (x_ndc, y_ndc, z, packed idx) in packed (reference) order
-  size_t off_preB;  // float4 [P]  (r, g, b, 0)
+  size_t off_preA;  // float4 [P]  (x_ndc, y_ndc, z, cell id) in packed (reference) order
+  size_t off_preB;  // 3 floats per point (r, g, b), unpadded (the area is sized for float4)
   size_t total;
 };
 

@@ -19,7 +19,8 @@
 // float4 plane when the caller provides one: the nearest pixel is always one of the four
 // bilinear taps, so 4 x 128-bit loads replace 13 scalar ones.  In the fused mode
 // (pgdvs_uwp_bin) the kernel also files every point under its raster cell (one RED atomic),
-// which removes the separate counting pass over the cloud.
+// which removes the separate counting pass over the cloud, and leaves a 28-byte packed-order
+// record (x, y, z, cell | r, g, b) per point for k_fill_pre to scatter into cell order.
 #include "common.cuh"
 
 namespace pgdvs {
@@ -49,9 +50,8 @@ struct UwpParams {
   // fused binning (all null/0 in the plain mode)
   CellGrid g;
   int* cell_count;
-  int* cell_of;
-  float4* preA;
-  float4* preB;
+  float4* preA;      // [cap] (x_ndc, y_ndc, z, cell id)  in packed (reference) order
+  float4* preB;      // [cap * 3 floats] (r, g, b), unpadded
 };
 
 // torch grid_sample(align_corners=False) source index of pixel coordinate c on an axis of
@@ -376,7 +376,7 @@ static inline UwpLayout make_uwp_layout(int n_jobs, int H, int W) {
 static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras, int n_views, int H,
                    int W, float* xyz_ndc, float* rgb, float* xyz_world, int32_t* src_pix,
                    int64_t* first_idx, int64_t* num_points, int64_t* total_points, char* ws,
-                   const UwpLayout& L, const CellGrid* grid, int* cell_count, int* cell_of, float4* preA,
+                   const UwpLayout& L, const CellGrid* grid, int* cell_count, float4* preA,
                    float4* preB, const int32_t* group_first, const int32_t* group_members, int n_groups,
                    cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(ws, 0, L.off_zero_end, stream);
@@ -409,7 +409,6 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
     if (grid != nullptr) {
       p.g = *grid;
       p.cell_count = cell_count;
-      p.cell_of = cell_of;
       p.preA = preA;
       p.preB = preB;
       k_uwp<true><<<grid_blocks, kUwpThreads, 0, stream>>>(p);
@@ -452,7 +451,7 @@ extern "C" int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs,
   if (n_jobs > 0 && (!jobs || !cameras || !xyz_ndc || !rgb)) return PGDVS_E_BADARG;
   return run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, xyz_world, src_pix, first_idx,
                  num_points, total_points, static_cast<char*>(workspace), L, nullptr, nullptr, nullptr,
-                 nullptr, nullptr, group_first, group_members, n_groups, (cudaStream_t)stream_);
+                 nullptr, group_first, group_members, n_groups, (cudaStream_t)stream_);
 }
 
 extern "C" int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int W, float radius,
@@ -494,7 +493,7 @@ extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCam
   const CellGrid g = make_cell_grid(H, W, B.halo);
   int rc = run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, nullptr, nullptr, first_idx,
                    num_points, total_points, ws + T.total, U, &g,
-                   reinterpret_cast<int*>(ws + B.off_cells), reinterpret_cast<int*>(ws + B.off_cell_of),
+                   reinterpret_cast<int*>(ws + B.off_cells),
                    reinterpret_cast<float4*>(ws + T.off_preA), reinterpret_cast<float4*>(ws + T.off_preB),
                    group_first, group_members, n_groups, stream);
   if (rc) return rc;

@@ -129,3 +129,61 @@ def test_synthetic_workload_shapes(name, P):
     assert wl.n_views == 5 and len(wl.view_pairs[0]) == 2 and wl.static_rgb.shape == (5, 24, 40, 3)
     pairs, cams = wl.jobs([4, 1])
     assert [p.view for p in pairs] == [0, 0, 1, 1] and len(cams) == 2
+
+
+def test_batched_camera_conversion_matches_single():
+    """prepare_views converts all target cameras with one batched inverse: same bits as one by one."""
+    from pgdvs_b200.dyn_renderer import opencv_to_p3d_camera, opencv_to_p3d_cameras
+    rng = np.random.default_rng(2)
+    n, H, W = 7, 288, 544
+    Ks = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
+    Ks[:, 0, 0] = 480 + rng.random(n).astype(np.float32) * 40
+    Ks[:, 1, 1] = 470
+    Ks[:, 0, 2], Ks[:, 1, 2] = W / 2 + 3, H / 2 - 2
+    c2w = np.tile(np.eye(4, dtype=np.float32), (n, 1, 1))
+    ang = rng.random(n).astype(np.float32) * 0.3
+    c2w[:, 0, 0], c2w[:, 0, 2], c2w[:, 2, 0], c2w[:, 2, 2] = np.cos(ang), np.sin(ang), -np.sin(ang), np.cos(ang)
+    c2w[:, :3, 3] = rng.random((n, 3)).astype(np.float32)
+    batch = opencv_to_p3d_cameras(Ks, c2w, H, W)
+    assert batch.shape == (n, 16) and batch.dtype == np.float32
+    for i in range(n):
+        one = np.concatenate(opencv_to_p3d_camera(Ks[i], c2w[i], H, W))
+        assert np.array_equal(one.view(np.int32), batch[i].view(np.int32))
+
+
+def test_job_descriptor_cache_is_invalidated_by_keep():
+    """SourcePair caches its C descriptor; attaching an outlier mask must rebuild it."""
+    import ctypes
+    from pgdvs_b200 import _cabi
+    from pgdvs_b200.dyn_renderer import SourcePair
+    H, W = 4, 6
+    z = torch.zeros
+    p = SourcePair(depth_1=z(H, W, 1), rgb_1=z(H, W, 3), mask_1=z(H, W, 1), flow_12=z(H, W, 2), depth_2=z(H, W, 1),
+                   rgb_2=z(H, W, 3), K_1=torch.eye(4), c2w_1=torch.eye(4), K_2=torch.eye(4), c2w_2=torch.eye(4),
+                   time_1=0.0, time_2=1.0, time_tgt=0.5, view=3)
+    rec0, key0 = p.record().copy(), p.group_key()
+    assert rec0.shape == (ctypes.sizeof(_cabi.PgdvsUwpJob),)
+    off = _cabi.PgdvsUwpJob.keep.offset
+    assert int(rec0[off:off + 8].view(np.uint64)[0]) == 0
+    keep = torch.ones(H * W, dtype=torch.uint8)
+    p.keep = keep
+    rec1 = p.record()
+    assert int(rec1[off:off + 8].view(np.uint64)[0]) == keep.data_ptr()
+    assert p.group_key() != key0
+    voff = _cabi.PgdvsUwpJob.view.offset
+    assert int(rec1[voff:voff + 4].view(np.int32)[0]) == 3
+
+
+def test_mesh_faces_match_oracle_construction():
+    """Grid-topology faces of mesh mode: same list, same order, same vertex-0 quirk as the oracle's
+    restatement of pgdvs_renderer_dyn.py:549-604 (index plumbing, runs on any device)."""
+    from oracle import pgdvs_ref as ref
+    from pgdvs_b200.mesh import mesh_faces_from_mask
+    g = torch.Generator().manual_seed(6)
+    H, W = 9, 13
+    mask = torch.rand(H, W, generator=g) < 0.7
+    rows, cols = torch.nonzero(mask, as_tuple=True)
+    a = mesh_faces_from_mask(rows, cols, H, W)
+    b = ref.mesh_faces_from_mask(rows, cols, H, W)
+    assert a.dtype == torch.int32 and torch.equal(a.long(), b) and b.shape[0] > 10
+    assert int((a == 0).sum()) == 0  # vertex 0 never appears in a face (upstream uses `> 0`)
