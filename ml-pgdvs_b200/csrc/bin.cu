@@ -233,6 +233,7 @@ extern "C" int pgdvs_bin_workspace_bytes(int N, int H, int W, int64_t P, float r
                                          size_t* bytes) {
   if (bytes == nullptr || N < 0 || H <= 0 || W <= 0 || P < 0 || !(radius_max >= 0.0f))
     return PGDVS_E_BADARG;
+  if (P >= kMaxRecords) return PGDVS_E_BADARG;
   BinLayout L = make_bin_layout(N, H, W, P, radius_max);
   if (L.cells + kScanTile >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
   *bytes = L.total;
@@ -246,7 +247,7 @@ extern "C" int pgdvs_bin_points(const float* points, const float* features, int 
   cudaStream_t stream = (cudaStream_t)stream_;
   if (N < 0 || H <= 0 || W <= 0 || P < 0 || !(radius_max >= 0.0f) || workspace == nullptr)
     return PGDVS_E_BADARG;
-  if (P >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  if (P >= kMaxRecords) return PGDVS_E_BADARG;  // record float4 indices (2 per record) are int32
   if (features != nullptr && (C < 1 || C > PGDVS_MAX_FUSED_CHANNELS)) return PGDVS_E_CHANNELS;
   if (features != nullptr && radius != nullptr && C > 3) return PGDVS_E_CHANNELS;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;

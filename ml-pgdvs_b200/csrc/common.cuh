@@ -109,6 +109,7 @@ __host__ __device__ __forceinline__ int rec_a(int j) {
 }
 __host__ __device__ __forceinline__ int rec_b(int j) { return rec_a(j) ^ 1; }
 static_assert(PGDVS_REC_STRIDE == 2, "records are interleaved 32-byte pairs");
+constexpr int64_t kMaxRecords = (int64_t)1 << 30;  // rec_a / rec_b return int32 float4 indices
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 

@@ -1025,6 +1025,7 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
       !(radius_max >= 0.0f))
     return PGDVS_E_BADARG;
   if (K > PGDVS_MAX_POINTS_PER_PIXEL) return PGDVS_E_K_TOO_LARGE;
+  if (P >= kMaxRecords) return PGDVS_E_BADARG;
   if (compositor < PGDVS_COMPOSITE_NONE || compositor > PGDVS_COMPOSITE_WEIGHTED_SUM)
     return PGDVS_E_BADARG;
   if (compositor != PGDVS_COMPOSITE_NONE) {

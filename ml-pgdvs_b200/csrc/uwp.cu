@@ -459,7 +459,7 @@ extern "C" int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int
   if (!bytes || n_jobs < 0 || n_views < 0 || H <= 0 || W <= 0 || !(radius >= 0.0f))
     return PGDVS_E_BADARG;
   const int64_t cap = (int64_t)n_jobs * H * W;
-  if (cap >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  if (cap >= kMaxRecords) return PGDVS_E_BADARG;  // record float4 indices (2 per record) are int32
   BinLayout B = make_bin_layout(n_views, H, W, cap, radius);
   if (B.cells + kScanTile >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
   FusedTail T = make_fused_tail(B, cap);
@@ -478,7 +478,7 @@ extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCam
     return PGDVS_E_BADARG;
   if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;
   const int64_t cap = (int64_t)n_jobs * H * W;
-  if (cap >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
+  if (cap >= kMaxRecords) return PGDVS_E_BADARG;  // record float4 indices (2 per record) are int32
   BinLayout B = make_bin_layout(n_views, H, W, cap, radius);
   if (B.cells + kScanTile >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
   FusedTail T = make_fused_tail(B, cap);

@@ -52,6 +52,19 @@ def test_error_strings_and_host_side_validation(lib):
     assert lib.pgdvs_rasterize_composite(dummy, 16, 1, 0, 8, 8, 4, 0.1, 0, 0, 0, 1.0, None, None, None,
                                          None, None, None, None, None) == -3
     assert lib.pgdvs_knn_mean_dist(None, 5, None, 5, 65, 0, None, None, 0, None) == -2
+    # more records than int32 float4 indices can address are refused up front
+    assert lib.pgdvs_bin_workspace_bytes(1, 8, 8, 1 << 30, 0.1, ctypes.byref(n)) == -1
+    assert lib.pgdvs_rasterize_composite(dummy, 1 << 40, 1, 1 << 30, 8, 8, 4, 0.1, 0, 0, 0, 1.0, None, None,
+                                         None, None, None, None, None, None) == -1
+    # softsplat / mesh / knn-grid entry points validate before touching the device
+    assert lib.pgdvs_softsplat_workspace_bytes(2, 8, 8, ctypes.byref(n)) == 0 and n.value == 2 * 8 * 8 * 8 * 4
+    assert lib.pgdvs_softsplat_dyn(None, None, None, None, None, None, 100.0, 1, 8, 8, None, None, None,
+                                   None, 0, None) == -1
+    assert lib.pgdvs_mesh_workspace_bytes(8, 12, ctypes.byref(n)) == 0 and n.value == 8 * 12 * 8
+    assert lib.pgdvs_rasterize_mesh(None, 3, None, 1, 8, 8, 1, None, None, None, None, None, None, None, 0,
+                                    None) == -1
+    assert lib.pgdvs_knn_workspace_bytes(100, 100, ctypes.byref(n)) == 0 and n.value == 256
+    assert lib.pgdvs_knn_workspace_bytes(100000, 100000, ctypes.byref(n)) == 0 and n.value > 16 << 20
 
 
 def test_struct_layout_matches_library(lib):
