@@ -174,10 +174,13 @@ def run_reference(args):
         return
     n_threads = os.cpu_count() or 1
     wl = make_cpu_workload(args.workload, n_views=max(1, min(args.steps + args.warmup, 16)))
+    # bounded sample: the timed row band of every step is sized so that the whole run (warm-up
+    # included) stays around two minutes whatever --steps is
+    budget = min(args.ref_step_seconds, 120.0 / max(1, args.steps + args.warmup))
     rows = None
     times = []
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_view(wl, i % wl.n_views, n_threads, rows_budget_s=args.ref_step_seconds, rows=rows)
+        r = cpu_reference_view(wl, i % wl.n_views, n_threads, rows_budget_s=budget, rows=rows)
         rows = r["rows"]
         if i >= args.warmup:
             times.append(r["t_view_s"])
