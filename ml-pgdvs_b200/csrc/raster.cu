@@ -558,6 +558,33 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   const int n = blockIdx.z;
   int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
 
+  // ---- every global read of the prologue is issued first; the set-up work below (mbarrier, pixel
+  //      centre tables, first barrier) runs under their latency
+  int rs[SPAN], rl[SPAN];  // start (global record index) and length of each window-row run
+#pragma unroll
+  for (int r = 0; r < SPAN; ++r) {
+    rs[r] = 0;
+    rl[r] = 0;
+  }
+  if (x < p.W && y < p.H) {
+    // coalesced read of the runs of the thread's own (identity) pixel; the thread that ends up
+    // walking the pixel picks them up from shared memory
+    const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+#pragma unroll
+    for (int r = 0; r < SPAN; ++r) {
+      rs[r] = __ldg(cs + r * p.GW);
+      rl[r] = __ldg(cs + r * p.GW + SPAN);  // end of the run for now
+    }
+  }
+  int row_gs = 0, row_ge = 0;  // warp 0, lane r: bounds of staged row r
+  if (threadIdx.y == 0 && threadIdx.x < ROWS && y0 + (int)threadIdx.x < p.GH) {
+    // extended-grid row (y0 + lane) holds image row y0 + lane - HALO; cells x0 .. x0+31+2*HALO
+    const int64_t rb = ((int64_t)n * p.GH + y0 + threadIdx.x) * p.GW;
+    const int xe = min(x0 + kTileW - 1 + 2 * HALO, p.GW - 1);
+    row_gs = __ldg(p.cell_end + rb + x0 - 1);
+    row_ge = __ldg(p.cell_end + rb + xe);
+  }
+
   if (tid == 0) {
     // one arrival (the expect_tx below); the copies complete the transaction count
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
@@ -576,15 +603,7 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   //      are in flight while the CTA sorts its pixels below
   if (threadIdx.y == 0) {
     const int lane = threadIdx.x;
-    // extended-grid row (y0 + lane) holds image row y0 + lane - HALO; cells x0 .. x0+31+2*HALO
-    const int row = y0 + lane;
-    int gs = 0, ge = 0;
-    if (lane < ROWS && row < p.GH) {
-      const int64_t rb = ((int64_t)n * p.GH + row) * p.GW;
-      const int xe = min(x0 + kTileW - 1 + 2 * HALO, p.GW - 1);
-      gs = __ldg(p.cell_end + rb + x0 - 1);
-      ge = __ldg(p.cell_end + rb + xe);
-    }
+    const int gs = row_gs, ge = row_ge;
     const int len = ge - gs;
     // Row r is staged at shared slot base_r + (gs & 7), base_r a multiple of 8: shared slot and
     // global slot of a record then differ by a multiple of 8, so rec_a()/rec_b() pick the same
@@ -630,25 +649,13 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
   // ---- balance the warps: hand the tile's pixels to threads in order of their candidate count
   //      (counting sort in shared memory) so that the lanes of a warp walk runs of similar
   //      length; the largest count also sizes the payload field of the keys
-  int rs[SPAN], rl[SPAN];  // start (global record index) and length of each window-row run
   int mine = tid;          // tile-local index (row * 32 + column) of the pixel this thread walks
   {
-    // coalesced read of the runs of the thread's own (identity) pixel; the thread that ends up
-    // walking the pixel picks them up from shared memory
     int work = 0;
 #pragma unroll
     for (int r = 0; r < SPAN; ++r) {
-      rs[r] = 0;
-      rl[r] = 0;
-    }
-    if (x < p.W && y < p.H) {
-      const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
-#pragma unroll
-      for (int r = 0; r < SPAN; ++r) {
-        rs[r] = __ldg(cs + r * p.GW);
-        rl[r] = __ldg(cs + r * p.GW + SPAN) - rs[r];
-        work += rl[r];
-      }
+      rl[r] -= rs[r];  // end -> length
+      work += rl[r];
     }
 #ifndef PGDVS_RASTER_NO_SORT
 #pragma unroll
