@@ -94,8 +94,13 @@ int pgdvs_bin_points(const float* points, const float* features, int C, const in
  *                features is > 0
  *  static_rgb    f32 [N,H,W,C] or NULL.  If given (with image and mask non-NULL) `image`
  *                receives the blend (1-mask)*static + mask*dyn of pgdvs_renderer.py:169-172.
+ *  workspace     read, and possibly REORDERED in place: when a pixel's window holds many more
+ *                records than K, the records inside each small cell are put in ascending z
+ *                order first so that the walk can leave a cell early.  The order of records
+ *                within a cell never affects the result, so the workspace stays valid for
+ *                further calls (on the same stream).
  * ------------------------------------------------------------------------------------ */
-int pgdvs_rasterize_composite(const void* workspace, size_t workspace_bytes, int N, int64_t P,
+int pgdvs_rasterize_composite(void* workspace, size_t workspace_bytes, int N, int64_t P,
                               int H, int W, int K, float radius_max, int per_point_radius, int C,
                               int compositor,
                               float rr_weight, const float* background, const float* static_rgb,

@@ -27,6 +27,8 @@
 // DESIGN.md 4.1 walks through the tile kernel step by step.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace pgdvs {
 
 struct RasterParams {
@@ -48,7 +50,14 @@ struct RasterParams {
   float* mask;
   int smem_records;  // capacity of the staging buffer of k_raster_tile, in records
   double density;    // host-side hint: mean points per pixel (sizes the staging buffer)
+  int cells_sorted;  // 1: every cell of at most kSortCap records is in ascending z order (k_sort_cells)
+  int force_generic; // developer switch (PGDVS_RASTER_FORCE_GENERIC): skip the tile kernel
 };
+
+// Cells holding up to kSortCap records can be put in ascending z order (k_sort_cells, run by the
+// generic path when a pixel sees many more candidates than it keeps): the walk then leaves a cell
+// at the first record that lies behind the K-th hit so far, because the rest of the cell does too.
+constexpr int kSortCap = 16;
 
 constexpr float kInf = __builtin_huge_valf();
 
@@ -334,20 +343,23 @@ struct StagedRecords {
   __device__ __forceinline__ float4 b(int j) const { return lds128(addr_a(j) ^ 16u); }
 };
 
-template <int KP, bool FULLK, typename Records>
+// SPEC: the PGDVS configuration (NormWeightedCompositor over rgb) with compositor and channel
+// count as compile-time constants — no per-winner mode branches, accumulators stay in registers.
+template <int KP, bool FULLK, typename Records, bool SPEC = false>
 __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slots<KP>& sl,
                                                const PixelCtx& c, int n, int x, int y,
                                                const Records rec) {
   const int K = FULLK ? KP : p.K;
   const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-  const int mode = p.compositor;
+  const int mode = SPEC ? (int)PGDVS_COMPOSITE_NORM_WEIGHTED : p.compositor;
+  const int nch = SPEC ? 3 : p.C;
   // the static frame is only needed at the very end: fetch it now, use it after the K loop
   float st[4] = {0.f, 0.f, 0.f, 0.f};
   const bool blend = (p.static_rgb != nullptr) && (p.image != nullptr) && (mode != PGDVS_COMPOSITE_NONE);
   if (blend) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
-      if (ch < p.C) st[ch] = __ldg(p.static_rgb + pix * p.C + ch);
+      if (ch < nch) st[ch] = __ldg(p.static_rgb + pix * nch + ch);
   }
   // One pass over the K winners: fragments (idx / zbuf / dists, bit-exact), the PointsRenderer
   // weight 1 - dists/(r*r) (as a multiply by the fp32 reciprocal, like torch's CUDA division by
@@ -445,11 +457,11 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
   if (p.image) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-      if (ch < p.C) {
+      if (ch < nch) {
         float v = is_bg ? p.bg[ch] : acc[ch];
         // combined = (1 - mask) * static + mask * dyn   (pgdvs_renderer.py:169-172)
         if (blend) v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st[ch]), __fmul_rn(m, v));
-        p.image[pix * p.C + ch] = v;
+        p.image[pix * nch + ch] = v;
       }
     }
   }
@@ -492,14 +504,35 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
   const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
   PairList<KP> q;
   q.init();
-  for (int ry = 0; ry < span; ++ry) {
-    const int s = __ldg(cs + (int64_t)ry * p.GW);
-    const int e = __ldg(cs + (int64_t)ry * p.GW + span);
-    for (int j = s; j < e; ++j) {
-      const float4 a = __ldg(recA + rec_a(j));
-      // depth first: once the list is full most candidates lie behind its last element and
-      // need no distance test at all (equal z still goes through: it may be a tie)
-      if (a.z <= q.z[KP - 1]) q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
+  if (p.cells_sorted) {
+    // z-sorted cells: cell by cell, leaving a (sorted) cell at the first record behind the list's
+    // last element — with a window of hundreds of candidates most cells cost one record
+    for (int ry = 0; ry < span; ++ry) {
+      const int* __restrict__ row = cs + (int64_t)ry * p.GW;
+      int s = __ldg(row);
+      for (int cx = 1; cx <= span; ++cx) {
+        const int e = __ldg(row + cx);
+        const bool sorted = (e - s) <= kSortCap;
+        for (int j = s; j < e; ++j) {
+          const float4 a = __ldg(recA + rec_a(j));
+          if (a.z <= q.z[KP - 1])
+            q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
+          else if (sorted)
+            break;
+        }
+        s = e;
+      }
+    }
+  } else {
+    for (int ry = 0; ry < span; ++ry) {
+      const int s = __ldg(cs + (int64_t)ry * p.GW);
+      const int e = __ldg(cs + (int64_t)ry * p.GW + span);
+      for (int j = s; j < e; ++j) {
+        const float4 a = __ldg(recA + rec_a(j));
+        // depth first: once the list is full most candidates lie behind its last element and
+        // need no distance test at all (equal z still goes through: it may be a tie)
+        if (a.z <= q.z[KP - 1]) q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
+      }
     }
   }
   Slots<KP> sl;
@@ -918,11 +951,79 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
     return;
   }
 #endif
-  if (KP <= 32 && p.K == KP)
-    pixel_epilogue<KP, true>(p, sl, c, n, x, y, staged_rec);
-  else
+  if (KP <= 32 && p.K == KP) {
+#ifndef PGDVS_RASTER_NO_SPEC
+    if (KP >= 8 && KP <= 16 && p.compositor == PGDVS_COMPOSITE_NORM_WEIGHTED && p.C == 3)
+      pixel_epilogue<KP, true, StagedRecords, true>(p, sl, c, n, x, y, staged_rec);
+    else
+#endif
+      pixel_epilogue<KP, true>(p, sl, c, n, x, y, staged_rec);
+  } else {
     pixel_epilogue<KP, false>(p, sl, c, n, x, y, staged_rec);
+  }
 }
+
+// ---------------------------------------------------------------------------------------
+// In-place z-sort of the small cells (generic path only).  One thread per cell: the cell's
+// records are read into registers, ranked by their z bit pattern (z >= 0, so the pattern orders
+// like the value; NaN patterns sort last; equal z keep their order) and written back to their
+// ranks.  Cells are disjoint, so no thread touches another's records.  Any order of the records
+// of a cell gives the same fragments (ties are resolved by packed index, not by position), so a
+// sorted workspace is as good as an unsorted one for every other consumer.
+// ---------------------------------------------------------------------------------------
+int maybe_sort_cells(RasterParams& p, int KP, cudaStream_t stream);
+
+#if !defined(PGDVS_RASTER_PART) || PGDVS_RASTER_PART == 0
+__global__ void __launch_bounds__(128) k_sort_cells(const int* __restrict__ cell_end, float4* rec,
+                                                    int64_t n_cells) {
+  const int64_t cell = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (cell >= n_cells) return;
+  const int s = __ldg(cell_end + cell - 1), e = __ldg(cell_end + cell);
+  const int n = e - s;
+  if (n < 2 || n > kSortCap) return;
+  float4 a[kSortCap], b[kSortCap];
+  uint32_t key[kSortCap];
+#pragma unroll
+  for (int i = 0; i < kSortCap; ++i) {
+    key[i] = 0xFFFFFFFFu;
+    if (i < n) {
+      a[i] = rec[rec_a(s + i)];
+      b[i] = rec[rec_b(s + i)];
+      key[i] = __float_as_uint(__fadd_rn(a[i].z, 0.0f));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSortCap; ++i) {
+    if (i < n) {
+      int r = 0;  // records strictly before record i in (z pattern, position) order
+#pragma unroll
+      for (int j = 0; j < kSortCap; ++j) {
+        if (j < i) r += (key[j] <= key[i]) ? 1 : 0;
+        if (j > i) r += (j < n && key[j] < key[i]) ? 1 : 0;
+      }
+      if (r != i) {
+        rec[rec_a(s + r)] = a[i];
+        rec[rec_b(s + r)] = b[i];
+      }
+    }
+  }
+}
+
+int maybe_sort_cells(RasterParams& p, int KP, cudaStream_t stream) {
+  const double span = 2.0 * p.halo + 1.0;
+  const double candidates = span * span * p.density;  // mean candidates per pixel
+  bool sort = candidates >= 64.0 && candidates >= 4.0 * KP;
+  if (const char* env = getenv("PGDVS_SORT_CELLS")) sort = env[0] == '1';  // developer switch
+  p.cells_sorted = 0;
+  if (!sort) return 0;
+  const int64_t n_cells = (int64_t)p.N * p.GH * p.GW;
+  const int64_t blocks = (n_cells + 127) / 128;
+  k_sort_cells<<<(unsigned)blocks, 128, 0, stream>>>(p.cell_end, const_cast<float4*>(p.recA), n_cells);
+  if (int rc = check_launch()) return rc;
+  p.cells_sorted = 1;
+  return 0;
+}
+#endif
 
 #ifndef PGDVS_RASTER_SMEM_BYTES
 #define PGDVS_RASTER_SMEM_BYTES (24 * 1024)
@@ -973,7 +1074,7 @@ int launch_raster(RasterParams& p, cudaStream_t stream) {
 #ifndef PGDVS_RASTER_NO_TMA
   if constexpr (KP <= 32) {
     const double density = p.density;
-    if (p.r2 < 0.0f)
+    if (p.r2 < 0.0f || p.force_generic)
       done = false;  // per-point radii: generic kernel
     else if (p.halo == 1)
       done = launch_tile<KP, 1>(p, grid, block, density, stream);
@@ -984,6 +1085,8 @@ int launch_raster(RasterParams& p, cudaStream_t stream) {
   }
 #endif
   if (!done) {
+    // many more candidates per pixel than kept hits: z-sort the cells first (see kSortCap)
+    if (int rc = maybe_sort_cells(p, KP, stream)) return rc;
     if (p.r2 < 0.0f)
       k_raster_cells<KP, true><<<grid, block, 0, stream>>>(p);
     else
@@ -1021,7 +1124,7 @@ PGDVS_RASTER_FOR_PART(PGDVS_RASTER_PART, PGDVS_RASTER_DEFINE)
 #if !defined(PGDVS_RASTER_PART) || PGDVS_RASTER_PART == 0
 using namespace pgdvs;
 
-extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace_bytes, int N,
+extern "C" int pgdvs_rasterize_composite(void* workspace, size_t workspace_bytes, int N,
                                          int64_t P, int H, int W, int K, float radius_max,
                                          int per_point_radius, int C, int compositor,
                                          float rr_weight, const float* background,
@@ -1071,6 +1174,11 @@ extern "C" int pgdvs_rasterize_composite(const void* workspace, size_t workspace
   p.image = image;
   p.mask = mask;
   p.smem_records = 0;
+  p.cells_sorted = 0;
+  {
+    const char* env = getenv("PGDVS_RASTER_FORCE_GENERIC");  // developer switch
+    p.force_generic = (env != nullptr && env[0] == '1') ? 1 : 0;
+  }
   // mean points per pixel of the batch (P is the capacity of the packed cloud: an upper bound)
   p.density = (double)P / ((double)N * (double)H * (double)W);
 
