@@ -57,6 +57,8 @@ struct RasterParams {
 // Cells holding up to kSortCap records can be put in ascending z order (k_sort_cells, run by the
 // generic path when a pixel sees many more candidates than it keeps): the walk then leaves a cell
 // at the first record that lies behind the K-th hit so far, because the rest of the cell does too.
+// Measured on C5 (1080p, 8 points per pixel): K = 8, r = 0.01 (121-cell window) 21.7 -> 11.1 ms per
+// 4 views, K = 32, r = 0.02 (529 cells) 144 -> 71 ms per 2 views, the sort itself 0.9 / 0.5 ms.
 constexpr int kSortCap = 16;
 
 constexpr float kInf = __builtin_huge_valf();
@@ -505,22 +507,32 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
   PairList<KP> q;
   q.init();
   if (p.cells_sorted) {
-    // z-sorted cells: cell by cell, leaving a (sorted) cell at the first record behind the list's
-    // last element — with a window of hundreds of candidates most cells cost one record
-    for (int ry = 0; ry < span; ++ry) {
-      const int* __restrict__ row = cs + (int64_t)ry * p.GW;
-      int s = __ldg(row);
-      for (int cx = 1; cx <= span; ++cx) {
-        const int e = __ldg(row + cx);
-        const bool sorted = (e - s) <= kSortCap;
-        for (int j = s; j < e; ++j) {
-          const float4 a = __ldg(recA + rec_a(j));
-          if (a.z <= q.z[KP - 1])
-            q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
-          else if (sorted)
-            break;
+    // z-sorted cells, one flattened loop: every lane keeps its own cursor (window row, cell,
+    // record) and leaves a sorted cell at the first record behind its list's last element, so a
+    // warp runs for as long as its busiest lane has records to look at — not for the longest
+    // cell of every step, which is what a per-cell loop nest costs once lanes exit early
+    const int* __restrict__ row = cs;  // boundaries of the cells of window row ry: row[0 .. span]
+    int ry = 0, cx = 0;
+    int j = __ldg(row), e = j;         // nothing open yet: the first trip opens cell 1
+    bool sorted = false;
+    for (;;) {
+      if (j >= e) {  // open the next cell (j == start of it: the cells of a row are contiguous)
+        if (++cx > span) {
+          if (++ry >= span) break;
+          row += p.GW;
+          cx = 1;
+          j = __ldg(row);
         }
-        s = e;
+        e = __ldg(row + cx);
+        sorted = (e - j) <= kSortCap;
+      }
+      if (j < e) {
+        const float4 a = __ldg(recA + rec_a(j));
+        const int slot = j++;
+        if (a.z <= q.z[KP - 1])
+          q.push(hit_test<PPR>(c, a, recA, slot), a.z, slot);
+        else if (sorted)
+          j = e;
       }
     }
   } else {

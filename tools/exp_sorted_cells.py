@@ -78,6 +78,14 @@ def main():
                 same = "yes" if all(torch.equal(ref[k], out[k]) for k in keys) else \
                     "NO: " + ",".join(k for k in keys if not torch.equal(ref[k], out[k]))
             print(f"| {label} ({wl.n_views} views) | {mode} | {r_ms:.3f} | {s_ms:.3f} | {same} |", flush=True)
+            if os.environ.get("PROFILE") and mode == "default":
+                # per-kernel device times of one step (CUPTI through torch.profiler; not a bench number)
+                from torch.profiler import ProfilerActivity, profile
+                with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                    step()
+                    torch.cuda.synchronize()
+                for evt in sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:8]:
+                    print(f"|  | kernel {evt.key[:60]} | {evt.device_time_total / 1e3:.3f} | x{evt.count} | |", flush=True)
             del out
         del ref, prep, wl
         torch.cuda.empty_cache()
