@@ -482,8 +482,13 @@ __device__ __noinline__ void finish_global(const RasterParams& p, const PixelCtx
     pixel_epilogue<KP, false>(p, sl, c, n, x, y, GlobalRecords{p.recA});
 }
 
+// Resident CTAs per SM the generic kernel is compiled for.  Its walk is a chain of dependent
+// loads, so it wants warps more than registers (the K-list itself takes 2*KP of them): 48 / 64 /
+// 128 registers for KP <= 8 / 16 / 32 instead of the 72 / 96 / 168 ptxas takes when left alone
+// (3 / 2 / 1 CTAs).  Measured on C5 (same bits): K = 8 11.1 -> 9.1 ms, K = 16 15.3 -> 11.4 ms,
+// K = 32 71.3 -> 50.7 ms; one step further (40 / 48 registers, or 80 for KP = 32) spills the list.
 #ifndef PGDVS_RASTER_MINBLOCKS
-#define PGDVS_RASTER_MINBLOCKS 1
+#define PGDVS_RASTER_MINBLOCKS ((KP <= 8) ? 5 : ((KP <= 16) ? 4 : ((KP <= 32) ? 2 : 1)))
 #endif
 
 // ---------------------------------------------------------------------------------------
