@@ -33,6 +33,44 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.pgdvs_abi_version() == 1
 
 
+def _ctype_class(t):
+    """pointer / i32 / i64 / u32 / size / f32 class of a ctypes argtype."""
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type(ctypes.POINTER(ctypes.c_int))) and \
+            issubclass(t, ctypes._Pointer):
+        return "ptr"
+    return {ctypes.c_int: "i32", ctypes.c_int32: "i32", ctypes.c_int64: "i64", ctypes.c_uint32: "u32",
+            ctypes.c_size_t: "size", ctypes.c_float: "f32"}[t]
+
+
+def _c_class(decl):
+    if "*" in decl or "[" in decl:
+        return "ptr"
+    for key, cls in (("size_t", "size"), ("int64_t", "i64"), ("uint32_t", "u32"), ("float", "f32"),
+                     ("int32_t", "i32"), ("int", "i32")):
+        if re.search(r"\b%s\b" % key, decl):
+            return cls
+    raise AssertionError(f"unparsed parameter {decl!r}")
+
+
+def test_ctypes_prototypes_match_header(lib):
+    """Every prototype in include/pgdvs_b200.h against the argtypes _cabi.py binds it with:
+    same arity, and per argument the same class (pointer, int32, int64, uint32, size_t, float)."""
+    header = (ROOT / "include" / "pgdvs_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|const char\s*\*)\s*(pgdvs_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 20
+    checked = 0
+    for name, params in protos:
+        params = " ".join(params.split())
+        want = [] if params in ("", "void") else [_c_class(x.strip()) for x in params.split(",")]
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, f"{name}: no argtypes bound in _cabi.py"
+        got = [_ctype_class(t) for t in fn.argtypes]
+        assert got == want, f"{name}: header {want} vs _cabi.py {got}"
+        checked += 1
+    assert checked == len(protos)
+
+
 def test_error_strings_and_host_side_validation(lib):
     assert lib.pgdvs_error_string(0) == b"ok"
     assert b"150" in lib.pgdvs_error_string(-2)
