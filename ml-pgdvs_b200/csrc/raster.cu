@@ -23,7 +23,11 @@
 //                  because records are sorted by cell), re-assigns its pixels to threads in
 //                  order of candidate count, walks them with shared-memory reads only, hands the
 //                  winners back to each pixel's own thread and runs the epilogue in raster order.
-//   k_raster_cells (any halo, per-point radii, K <= 150): candidates are read through L1.
+//   k_raster_cells (any halo, per-point radii, K <= 150): candidates are read through L1.  When a
+//                  window holds many more records than K, k_sort_cells first puts the records of
+//                  every small cell in ascending z order (in place) and the walk — one flattened
+//                  loop, a cursor per lane — leaves a cell at the first record behind the list's
+//                  last element.
 // DESIGN.md 4.1 walks through the tile kernel step by step.
 #include "common.cuh"
 
