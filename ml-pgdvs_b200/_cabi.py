@@ -6,7 +6,7 @@ raises immediately with the build command."""
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpgdvs_b200.so"

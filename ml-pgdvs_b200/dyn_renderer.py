@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes
 from types import SimpleNamespace
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 import torch

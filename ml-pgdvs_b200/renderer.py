@@ -10,7 +10,7 @@ Forward only (the reference runs under torch.no_grad: engines/evaluator_pgdvs.py
 """
 from __future__ import annotations
 
-from typing import List, NamedTuple, Optional, Sequence, Tuple, Union
+from typing import NamedTuple, Optional, Tuple, Union
 
 import torch
 

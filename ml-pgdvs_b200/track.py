@@ -9,7 +9,7 @@
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Sequence
+from typing import Sequence
 
 import numpy as np
 import torch

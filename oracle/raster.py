@@ -11,7 +11,6 @@ import this module.  The product package (pgdvs_b200) never does.
 from __future__ import annotations
 
 import ctypes
-import os
 import subprocess
 from pathlib import Path
 
