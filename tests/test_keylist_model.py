@@ -270,3 +270,21 @@ def test_sorted_cell_walk_matches_the_reference_unless_flagged(KP, K, ties):
     assert clean > 0
     if ties and KP > 1:
         assert flagged > 0
+
+
+def test_sort_cells_rank_formula_is_a_stable_permutation():
+    """k_sort_cells ranks record i by  #{j < i: key_j <= key_i} + #{j > i: key_j < key_i}  — for ANY
+    keys (duplicates, NaN patterns, all equal) that is the stable sort permutation, so no record
+    is lost or duplicated when the records are written back to their ranks."""
+    rng = np.random.default_rng(5)
+    for _ in range(500):
+        n = int(rng.integers(2, SORT_CAP + 1))
+        keys = rng.choice([0, 1, 7, 0x3F800000, 0x7F800000, 0x7FC00000, 0xFFFFFFFF], n).tolist() \
+            if rng.random() < 0.5 else rng.integers(0, 2 ** 32, n).tolist()
+        rank = [sum(keys[j] <= keys[i] for j in range(i)) + sum(keys[j] < keys[i] for j in range(i + 1, n))
+                for i in range(n)]
+        assert sorted(rank) == list(range(n))
+        out = [None] * n
+        for i, r in enumerate(rank):
+            out[r] = (keys[i], i)
+        assert out == sorted((k, i) for i, k in enumerate(keys))
