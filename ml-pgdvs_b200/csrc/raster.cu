@@ -717,10 +717,19 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
 #endif
     const int wmax = __reduce_max_sync(0xffffffffu, work);
     if ((tid & 31) == 0) atomicMax(&s_max, wmax);
+#ifdef PGDVS_TILE_FIXED_BINS
+    // (experiment, DESIGN.md 9 item 1a: one CTA barrier less) bin width from the host's density
+    // hint instead of the tile's own maximum, which is then first needed after the later barriers
+    const int width = (int)(p.density * (double)(SPAN * SPAN) * (2.5 / 64.0)) + 1;
+    const int bin = max(0, 63 - work / width);  // heaviest pixels first
+#else
     __syncthreads();  // s_max; also s_staged / s_delta of warp 0
+#endif
 #ifndef PGDVS_RASTER_NO_SORT
+#ifndef PGDVS_TILE_FIXED_BINS
     const int width = s_max / 64 + 1;
     const int bin = 63 - work / width;  // heaviest pixels first
+#endif
     const int my_rank = atomicAdd(&s_hist[bin], 1);
     __syncthreads();
     if (tid < 32) {  // exclusive scan of the 64 bins by one warp (2 per lane)

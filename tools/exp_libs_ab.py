@@ -5,6 +5,11 @@ rasterize-and-composite call and a bit-for-bit comparison against the in-tree bu
 the product.
 
     LIBS=occA,occB CASES="C5 K=8,C5 K=32" python tools/exp_libs_ab.py     (on the GPU box)
+
+A candidate build is made here with e.g.
+    PGDVS_NVCC_EXTRA=-DPGDVS_TILE_FIXED_BINS python -m pgdvs_b200._build --force
+    cp ml-pgdvs_b200/lib/libpgdvs_b200.so exp_libs/lib_fixedbins.so
+followed by a forced rebuild without the flag (exp_libs/ travels to the GPU box, is git-ignored).
 """
 import os
 import sys
@@ -19,6 +24,8 @@ from pgdvs_b200 import _cabi, synthetic  # noqa: E402
 from pgdvs_b200.dyn_renderer import prepare_views, render_prepared  # noqa: E402
 
 CASES = [
+    ("C2 K=8", "c2_nvidia_seq", dict()),
+    ("C4 K=8", "c4_davis", dict(n_views=16)),
     ("C5 K=8 r=0.01", "c5_stress", dict(K=8, radius=0.01, n_views=4)),
     ("C5 K=16 r=0.005", "c5_stress", dict(K=16, radius=0.005, n_views=4)),
     ("C5 K=32 r=0.02", "c5_stress", dict(K=32, radius=0.02, n_views=2)),
