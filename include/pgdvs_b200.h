@@ -33,6 +33,7 @@ extern "C" {
 #define PGDVS_E_WORKSPACE (-3)   /* workspace smaller than *_workspace_bytes() */
 #define PGDVS_E_CHANNELS (-4)    /* fused compositing supports C <= PGDVS_MAX_FUSED_CHANNELS */
 #define PGDVS_E_ALIGN (-5)       /* pointer not aligned as documented */
+#define PGDVS_E_KNN_K (-6)       /* knn K > 64 (dyn_pcl_outlier_knn + 1 must be <= 64) */
 
 /* pytorch3d's kMaxPointsPerPixel (rasterize_points.py): hard cap on K */
 #define PGDVS_MAX_POINTS_PER_PIXEL 150
@@ -106,6 +107,34 @@ int pgdvs_rasterize_composite(void* workspace, size_t workspace_bytes, int N, in
                               float rr_weight, const float* background, const float* static_rgb,
                               int32_t* idx, float* zbuf, float* dists, float* image, float* mask,
                               void* stream);
+
+/* Extended outputs of the same pass (HOST struct, may be NULL; every member may be NULL):
+ *  depth     f32 [N,H,W,1]  the compositor applied to the hits' view-space z as one more feature
+ *            channel — the "composited depth" of the north star (the reference never composites
+ *            depth: it discards pytorch3d's zbuf, pgdvs_renderer_dyn.py:717); 0 where idx[...,0] < 0.
+ *            zbuf[..., 0] is the nearest-hit depth.
+ *  image_u8  u8 [N,H,W,C]   the image (after the static blend, if any) as the reference's evaluator /
+ *            video writer quantise it (engines/evaluator_pgdvs.py:51-77: NaN -> 0, clamp(0,1),
+ *            (x*255).byte()); `image` may then be NULL.  Saves the separate pgdvs_quantize_u8 pass.
+ *  mask_u8   u8 [N,H,W,1]   mask * 255 */
+typedef struct PgdvsRasterExtra {
+  float* depth;
+  uint8_t* image_u8;
+  uint8_t* mask_u8;
+} PgdvsRasterExtra;
+int pgdvs_rasterize_composite_ex(void* workspace, size_t workspace_bytes, int N, int64_t P,
+                                 int H, int W, int K, float radius_max, int per_point_radius, int C,
+                                 int compositor, float rr_weight, const float* background,
+                                 const float* static_rgb, int32_t* idx, float* zbuf, float* dists,
+                                 float* image, float* mask, const PgdvsRasterExtra* extra, void* stream);
+
+/* Developer switches of the rasterizer (kernel selection only — results are bit-identical in
+ * every setting; tests and A/B harnesses use them).  which: 0 = z-sort the cells before the
+ * generic kernel, 1 = force the generic kernel, 2 = k_raster_tile instead of k_raster_pair
+ * (0 = k_raster_pair whenever it applies, even for launches too small to fill the GPU with it).
+ * value: -1 automatic, 0 off, 1 on.  Initial values come from the environment variables
+ * PGDVS_SORT_CELLS / PGDVS_RASTER_FORCE_GENERIC / PGDVS_RASTER_NO_PAIR, read once per process. */
+int pgdvs_debug_switch(int which, int value);
 
 /* --------------------------------------------------------------------------------------
  * 3. Stand-alone compositors (pytorch3d `_C.accum_alphacomposite`, `_C.accum_weightedsumnorm`,
@@ -205,6 +234,15 @@ int pgdvs_pack_rgbd(const PgdvsFramePack* frames_dev, int n_frames, int H, int W
 int pgdvs_project_points(const float* xyz_world, int64_t P, const PgdvsCamera* camera_dev,
                          float* xyz_ndc, void* stream);
 
+/* Projector.compute_projections (pgdvs/models/gnt/projector.py:41-73) — the `proj_func` the
+ * dynamic renderer is constructed with (pgdvs_renderer.py:78) and calls for the softsplat flow
+ * (pgdvs_renderer_dyn.py:470-473):  h = (K @ inv(c2w)) @ [xyz, 1];  uv = h.xy / clamp(h.z, min=1e-8),
+ * clamped to [-1e6, 1e6];  mask = h.z > 0.
+ *  xyz f32 [P,3];  proj f32 [n_cams,12] = rows 0..2 of K @ inv(c2w) (device);
+ *  uv f32 [n_cams,P,2];  mask u8 [n_cams,P] (nullable). */
+int pgdvs_compute_projections(const float* xyz, int64_t P, const float* proj, int n_cams, float* uv,
+                              uint8_t* mask, void* stream);
+
 /* --------------------------------------------------------------------------------------
  * 5. dyn/track merge + static blend, channels-first like the reference:
  *    mask_for_track = ~(dyn_mask>0) & (track_mask>0); rgb = (1-m)*dyn + m*track;
@@ -250,7 +288,8 @@ int pgdvs_track_points(const float* tracks, const uint8_t* visibles, int64_t Q, 
  *    from each query point to its K nearest reference points, dropping the first
  *    `skip_first` of them.  Replaces `pytorch3d.ops.knn_points(q, r, K, return_nn=True)` +
  *    `torch.mean(nn_dists[:, skip_first:], dim=1)` at pgdvs_renderer_dyn.py:405-419 and
- *    pgdvs_renderer_dyn_track.py:303-318, 345-361.  K <= 64.
+ *    pgdvs_renderer_dyn_track.py:303-318, 345-361.  K <= 64 (PGDVS_E_KNN_K above that).  As upstream,
+ *    the mean always divides by K - skip_first (knn_points zero-pads when R < K).
  *    query f32 [Q,3], ref f32 [R,3] -> mean_out f32 [Q].
  * ------------------------------------------------------------------------------------ */
 int pgdvs_knn_workspace_bytes(int64_t Q, int64_t R, size_t* bytes);
@@ -258,7 +297,8 @@ int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* ref, int64_t
                         int skip_first, float* mean_out, void* workspace, size_t workspace_bytes,
                         void* stream);
 /* Full `pytorch3d.ops.knn_points` result for one cloud pair: squared distances f32 [Q,K]
- * (ascending) and reference indices i64 [Q,K]; slots beyond R hold (0, -1).  K <= 64. */
+ * (ascending) and reference indices i64 [Q,K]; slots beyond R hold (0, 0) like pytorch3d's
+ * zero-initialised outputs.  K <= 64. */
 int pgdvs_knn_points(const float* query, int64_t Q, const float* ref, int64_t R, int K,
                      float* dists_out, int64_t* idx_out, void* stream);
 

@@ -18,7 +18,7 @@ MAX_FUSED_CHANNELS = 4
 # every symbol include/pgdvs_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = (
     "pgdvs_abi_version", "pgdvs_error_string", "pgdvs_struct_layout", "pgdvs_bin_workspace_bytes", "pgdvs_bin_points",
-    "pgdvs_rasterize_composite", "pgdvs_composite", "pgdvs_uwp_workspace_bytes",
+    "pgdvs_rasterize_composite", "pgdvs_rasterize_composite_ex", "pgdvs_compute_projections", "pgdvs_debug_switch", "pgdvs_composite", "pgdvs_uwp_workspace_bytes",
     "pgdvs_unproject_warp_project", "pgdvs_project_points", "pgdvs_merge_blend",
     "pgdvs_uwp_bin_workspace_bytes", "pgdvs_uwp_bin", "pgdvs_pack_rgbd",
     "pgdvs_knn_workspace_bytes", "pgdvs_knn_mean_dist", "pgdvs_knn_points",
@@ -41,6 +41,10 @@ class PgdvsUwpJob(ctypes.Structure):
         ("o2", c_float * 3), ("w1", c_float), ("w2", c_float), ("same_time", c_int32),
         ("view", c_int32),
     ]
+
+
+class PgdvsRasterExtra(ctypes.Structure):
+    _fields_ = [("depth", c_void_p), ("image_u8", c_void_p), ("mask_u8", c_void_p)]
 
 
 class PgdvsFramePack(ctypes.Structure):
@@ -84,6 +88,15 @@ def lib():
         c_void_p, c_size_t, c_int, c_int64, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
         c_float, POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
         c_void_p]
+    L.pgdvs_rasterize_composite_ex.restype = c_int
+    L.pgdvs_rasterize_composite_ex.argtypes = [
+        c_void_p, c_size_t, c_int, c_int64, c_int, c_int, c_int, c_float, c_int, c_int, c_int,
+        c_float, POINTER(c_float), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+        POINTER(PgdvsRasterExtra), c_void_p]
+    L.pgdvs_debug_switch.restype = c_int
+    L.pgdvs_debug_switch.argtypes = [c_int, c_int]
+    L.pgdvs_compute_projections.restype = c_int
+    L.pgdvs_compute_projections.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.pgdvs_composite.restype = c_int
     L.pgdvs_composite.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int64, c_int, c_void_p, c_void_p]
@@ -144,6 +157,15 @@ def lib():
         raise ImportError(f"struct layout mismatch between _cabi.py {mine} and libpgdvs_b200.so {list(lay)}")
     _lib = L
     return L
+
+
+DEBUG_SWITCHES = {"sort_cells": 0, "force_generic": 1, "no_pair": 2}
+
+
+def debug_switch(name: str, value: int):
+    """Kernel-selection switches of the rasterizer (-1 automatic, 0 off, 1 on); results are the
+    same bits in every setting.  For tests and A/B measurements."""
+    check(lib().pgdvs_debug_switch(DEBUG_SWITCHES[name], int(value)), "pgdvs_debug_switch")
 
 
 def check(rc: int, what: str):

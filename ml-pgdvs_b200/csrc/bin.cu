@@ -25,6 +25,7 @@ struct BinParams {
   int C;
   CellGrid g;
   int* cells;     // counts -> starts -> ends
+  uint32_t* zrange;  // [2 N] per-view range of the filed z patterns (common.cuh)
   int* cell_of;   // [P]
   float4* recA;
   float4* recB;
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(256) k_count(BinParams p) {
   const int n = blockIdx.y;
   const int64_t first = p.first_idx[n];
   const int64_t num = p.num_points[n];
+  uint32_t nlo = 0u, hi = 0u;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < num;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t q = first + i;
@@ -45,9 +47,15 @@ __global__ void __launch_bounds__(256) k_count(BinParams p) {
     const float y = __ldg(p.points + q * 3 + 1);
     const float z = __ldg(p.points + q * 3 + 2);
     const int cell = point_cell(p.g, n, x, y, z);
-    if (cell >= 0) atomicAdd(p.cells + cell, 1);  // result unused -> RED
+    if (cell >= 0) {
+      atomicAdd(p.cells + cell, 1);  // result unused -> RED
+      const uint32_t zb = z_pattern(z);
+      nlo = max(nlo, ~zb);
+      hi = max(hi, zb);
+    }
     p.cell_of[q] = cell;
   }
+  zrange_accumulate(p.zrange, n, 0xffffffffu, nlo, hi);  // (the loop has re-converged: all 32 lanes)
 }
 
 __global__ void __launch_bounds__(256) k_fill(BinParams p) {
@@ -213,6 +221,7 @@ int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_
   p.preA = reinterpret_cast<const float4*>(ws + T.off_preA);
   p.preB = reinterpret_cast<const float4*>(ws + T.off_preB);
   p.total = total_dev;
+
   k_scan<<<(unsigned)L.n_tiles, 1024, 0, stream>>>(
       p.cells, reinterpret_cast<unsigned long long*>(ws + L.off_state),
       reinterpret_cast<int*>(ws + L.off_ticket));
@@ -268,6 +277,7 @@ extern "C" int pgdvs_bin_points(const float* points, const float* features, int 
   p.C = features ? C : 0;
   p.g = make_cell_grid(H, W, L.halo);
   p.cells = reinterpret_cast<int*>(ws + L.off_cells);
+  p.zrange = reinterpret_cast<uint32_t*>(ws + L.off_zrange);
   p.cell_of = reinterpret_cast<int*>(ws + L.off_cell_of);
   p.recA = reinterpret_cast<float4*>(ws + L.off_recA);
   p.recB = reinterpret_cast<float4*>(ws + L.off_recB);

@@ -70,6 +70,8 @@ struct BinLayout {
   size_t off_cells;
   size_t off_state;   // uint64 [n_tiles]    decoupled look-back state
   size_t off_ticket;  // int32 [4]           scan ticket counter (+pad)
+  size_t off_zrange;  // uint32 [2 N]        per view: max(~bits(z)), max(bits(z)) over the filed points
+                      //                     (zero-initialised == empty); sizes the rasterizer's z keys
   size_t off_zero_end;  // everything in [0, off_zero_end) is zeroed before each binning
   size_t off_cell_of; // int32  [P]          cell of every packed point (-1 = never rasterized);
                       //                     staged path only (the fused path carries it in its records)
@@ -133,6 +135,8 @@ inline BinLayout make_bin_layout(int N, int H, int W, int64_t P, float radius_ma
   o = align256(o + sizeof(uint64_t) * (size_t)L.n_tiles);
   L.off_ticket = o;
   o = align256(o + 256);
+  L.off_zrange = o;
+  o = align256(o + sizeof(uint32_t) * 2 * (size_t)(N > 0 ? N : 1));
   L.off_zero_end = o;
   L.off_cell_of = o;
   o = align256(o + sizeof(int32_t) * (size_t)(P > 0 ? P : 1));
@@ -201,6 +205,25 @@ __device__ __forceinline__ int point_cell(const CellGrid& g, int n, float x, flo
   const int gy = __float2int_rn(rowf) + g.halo;
   if (gx < 0 || gx >= g.GW || gy < 0 || gy >= g.GH) return -1;
   return (n * g.GH + gy) * g.GW + gx;
+}
+
+// Range of the z bit patterns of the points filed under view n (sizes the rasterizer's sorted
+// 32-bit keys, raster.cu KeyCode).  z >= 0 for every filed point, so the pattern orders like the
+// value; -0.0 counts as +0.0.  Stored as (max ~bits, max bits) so that zero means "empty".
+// Every lane named in `mask` calls this with its own partial range (nlo = ~min pattern, or 0;
+// hi = max pattern, or 0): one pair of atomics per warp.
+__device__ __forceinline__ uint32_t z_pattern(float z) { return __float_as_uint(__fadd_rn(z, 0.0f)); }
+__device__ __forceinline__ void zrange_accumulate(uint32_t* zrange, int n, unsigned mask, uint32_t nlo,
+                                                  uint32_t hi) {
+  nlo = __reduce_max_sync(mask, nlo);
+  hi = __reduce_max_sync(mask, hi);
+  if ((threadIdx.x & 31) == (__ffs(mask) - 1) && (nlo | hi) != 0u) {
+    // thousands of warps update the same two words of a view: look first (an L2 read), and only
+    // the few warps that really widen the range pay for an atomic
+    const uint2 cur = __ldcg(reinterpret_cast<const uint2*>(zrange) + n);
+    if (nlo > cur.x) atomicMax(zrange + 2 * n, nlo);
+    if (hi > cur.y) atomicMax(zrange + 2 * n + 1, hi);
+  }
 }
 
 // PointsRasterizer.transform for PerspectiveCameras(in_ndc=True):

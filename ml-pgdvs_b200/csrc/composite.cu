@@ -120,6 +120,27 @@ __global__ void __launch_bounds__(256) k_project(const float* __restrict__ xyz, 
   }
 }
 
+// Projector.compute_projections (models/gnt/projector.py:41-73) for n_cams cameras
+__global__ void __launch_bounds__(256) k_compute_projections(const float* __restrict__ xyz, int64_t P,
+                                                             const float* __restrict__ proj, int n_cams,
+                                                             float* __restrict__ uv, uint8_t* __restrict__ mask) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = __ldg(xyz + i * 3), y = __ldg(xyz + i * 3 + 1), z = __ldg(xyz + i * 3 + 2);
+    for (int c = 0; c < n_cams; ++c) {
+      const float* m = proj + c * 12;
+      const float hx = m[0] * x + m[1] * y + m[2] * z + m[3];
+      const float hy = m[4] * x + m[5] * y + m[6] * z + m[7];
+      const float hz = m[8] * x + m[9] * y + m[10] * z + m[11];
+      const float d = fmaxf(hz, 1e-8f);  // torch.clamp(min=1e-8)
+      const float u = fminf(fmaxf(__fdiv_rn(hx, d), -1e6f), 1e6f);
+      const float v = fminf(fmaxf(__fdiv_rn(hy, d), -1e6f), 1e6f);
+      reinterpret_cast<float2*>(uv)[(int64_t)c * P + i] = make_float2(u, v);
+      if (mask) mask[(int64_t)c * P + i] = hz > 0.0f ? 1 : 0;
+    }
+  }
+}
+
 static inline int grid_for(int64_t total) {
   int64_t g = (total + 255) / 256;
   if (g < 1) g = 1;
@@ -179,6 +200,16 @@ extern "C" int pgdvs_project_points(const float* xyz_world, int64_t P, const Pgd
   return check_launch();
 }
 
+extern "C" int pgdvs_compute_projections(const float* xyz, int64_t P, const float* proj, int n_cams,
+                                         float* uv, uint8_t* mask, void* stream) {
+  if (P < 0 || n_cams < 0) return PGDVS_E_BADARG;
+  if (P == 0 || n_cams == 0) return PGDVS_OK;
+  if (!xyz || !proj || !uv) return PGDVS_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(uv) & 7) != 0) return PGDVS_E_ALIGN;
+  k_compute_projections<<<grid_for(P), 256, 0, (cudaStream_t)stream>>>(xyz, P, proj, n_cams, uv, mask);
+  return check_launch();
+}
+
 extern "C" int pgdvs_abi_version(void) { return PGDVS_B200_ABI_VERSION; }
 
 extern "C" int pgdvs_struct_layout(int32_t out[4]) {
@@ -198,6 +229,7 @@ extern "C" const char* pgdvs_error_string(int code) {
     case PGDVS_E_WORKSPACE: return "workspace smaller than *_workspace_bytes()";
     case PGDVS_E_CHANNELS: return "fused compositing supports at most 4 feature channels";
     case PGDVS_E_ALIGN: return "pointer is not aligned as documented";
+    case PGDVS_E_KNN_K: return "knn K exceeds 64 (dyn_pcl_outlier_knn + 1 must be <= 64)";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -86,16 +86,17 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn(const float* __restrict__ q
 #pragma unroll
     for (int j = 0; j < kKnnMaxK; ++j)
       if (j >= skip && j < kk) sum += best[j];
-    const int cnt = kk - skip;
+    // knn_points zero-pads the columns beyond R and the reference's torch.mean divides by all of them
+    const int cnt = K - skip;
     mean_out[qi] = cnt > 0 ? sum / (float)cnt : 0.f;
   }
   if (WITH_IDX) {
 #pragma unroll
     for (int j = 0; j < kKnnMaxK; ++j) {
       if (j < K) {
-        // pytorch3d pads with 0 / -1... the facade documents: slots beyond R hold (0, -1)
+        // slots beyond R hold (0, 0) like pytorch3d's zero-initialised outputs
         dists_out[qi * K + j] = (j < kk) ? best[j] : 0.f;
-        idx_out[qi * K + j] = (j < kk) ? (int64_t)bidx[j] : (int64_t)-1;
+        idx_out[qi * K + j] = (j < kk) ? (int64_t)bidx[j] : (int64_t)0;
       }
     }
   }
@@ -123,7 +124,7 @@ extern "C" int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* r
                                    int skip_first, float* mean_out, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   if (Q < 0 || R < 0 || K < 1 || skip_first < 0) return PGDVS_E_BADARG;
-  if (K > kKnnMaxK) return PGDVS_E_K_TOO_LARGE;
+  if (K > kKnnMaxK) return PGDVS_E_KNN_K;
   if (Q == 0) return PGDVS_OK;
   if (!query || !mean_out || (R > 0 && !ref)) return PGDVS_E_BADARG;
   // exact uniform-grid search when the caller provides the scratch (pgdvs_knn_workspace_bytes);
@@ -140,7 +141,7 @@ extern "C" int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* r
 extern "C" int pgdvs_knn_points(const float* query, int64_t Q, const float* ref, int64_t R, int K,
                                 float* dists_out, int64_t* idx_out, void* stream) {
   if (Q < 0 || R < 0 || K < 1) return PGDVS_E_BADARG;
-  if (K > kKnnMaxK) return PGDVS_E_K_TOO_LARGE;
+  if (K > kKnnMaxK) return PGDVS_E_KNN_K;
   if (Q == 0) return PGDVS_OK;
   if (!query || !dists_out || !idx_out || (R > 0 && !ref)) return PGDVS_E_BADARG;
   const unsigned grid = (unsigned)((Q + kKnnThreads - 1) / kKnnThreads);

@@ -52,10 +52,17 @@ struct RasterParams {
   float* dists;
   float* image;
   float* mask;
+  float* depth;        // [N,H,W,1] or null: view z composited like a further feature channel
+  uint8_t* image_u8;   // [N,H,W,C] or null: the image as 8-bit (NaN -> 0, clamp, x255 truncated)
+  uint8_t* mask_u8;    // [N,H,W,1] or null
   int smem_records;  // capacity of the staging buffer of k_raster_tile, in records
   double density;    // host-side hint: mean points per pixel (sizes the staging buffer)
   int cells_sorted;  // 1: every cell of at most kSortCap records is in ascending z order (k_sort_cells)
-  int force_generic; // developer switch (PGDVS_RASTER_FORCE_GENERIC): skip the tile kernel
+  int force_generic; // developer switch (PGDVS_RASTER_FORCE_GENERIC): skip the staged kernels
+  int no_pair;       // developer switch (PGDVS_RASTER_NO_PAIR): 1 = k_raster_tile instead of k_raster_pair,
+                     // 0 = k_raster_pair whenever applicable, -1 = automatic (pair kernel for large launches)
+  const uint32_t* zrange;  // [2 N] per view: max(~bits(z)), max(bits(z)) over the filed points (common.cuh)
+  float pair_bin_scale;    // k_raster_pair: work -> work-sort bin (64 bins span 2.5x the mean work)
 };
 
 // Cells holding up to kSortCap records can be put in ascending z order (k_sort_cells, run by the
@@ -66,6 +73,12 @@ struct RasterParams {
 constexpr int kSortCap = 16;
 
 constexpr float kInf = __builtin_huge_valf();
+
+// Developer switches: read from the environment ONCE per process, overridable at run time
+// through pgdvs_debug_switch (tests and the A/B harness flip them between calls).
+// -1 = automatic, 0 = off, 1 = on.
+enum { kSwSortCells = 0, kSwForceGeneric = 1, kSwNoPair = 2, kSwCount = 3 };
+int debug_switch(int which);
 
 // candidate (z, idx) strictly before list element (ze, slot se)?  Total order (z, idx).
 __device__ __forceinline__ bool cand_less(float z, int idx, float ze, int se,
@@ -349,6 +362,15 @@ struct StagedRecords {
   __device__ __forceinline__ float4 b(int j) const { return lds128(addr_a(j) ^ 16u); }
 };
 
+// The same staging buffer addressed by the float4 index of a record's A part (= rec_a(slot)):
+// what k_raster_pair's walkers hand to the epilogue threads, so that a winner costs one
+// multiply-add to address instead of three integer ops.
+struct StagedAddr {
+  uint32_t base;
+  __device__ __forceinline__ float4 a(int v) const { return StagedRecords::lds128(base + 16u * (uint32_t)v); }
+  __device__ __forceinline__ float4 b(int v) const { return StagedRecords::lds128((base + 16u * (uint32_t)v) ^ 16u); }
+};
+
 // SPEC: the PGDVS configuration (NormWeightedCompositor over rgb) with compositor and channel
 // count as compile-time constants — no per-winner mode branches, accumulators stay in registers.
 template <int KP, bool FULLK, typename Records, bool SPEC = false>
@@ -361,7 +383,9 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
   const int nch = SPEC ? 3 : p.C;
   // the static frame is only needed at the very end: fetch it now, use it after the K loop
   float st[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool blend = (p.static_rgb != nullptr) && (p.image != nullptr) && (mode != PGDVS_COMPOSITE_NONE);
+  const bool blend = (p.static_rgb != nullptr) && (p.image != nullptr || p.image_u8 != nullptr) &&
+                     (mode != PGDVS_COMPOSITE_NONE);
+  const bool want_depth = p.depth != nullptr;
   if (blend) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
@@ -373,6 +397,7 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
   // unnormalised and scaled once by 1/max(sum w, 1e-4) at the end; images are
   // tolerance-matched (|delta| <= 1e-5), not bit-matched.
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float zacc = 0.f;       // the same compositor applied to the view depth of the hits
   float wsum = 0.f;       // the same compositor applied to all-ones features (mask render)
   float cum_alpha = 1.0f;
   constexpr bool vec4 = FULLK && (KP % 4 == 0);  // K*4 B per pixel is a multiple of 16 B
@@ -405,6 +430,7 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
             acc[1] = __fadd_rn(acc[1], __fmul_rn(wk, f4.y));
             acc[2] = __fadd_rn(acc[2], __fmul_rn(wk, f4.z));
             acc[3] = __fadd_rn(acc[3], __fmul_rn(wk, f4.w));
+            if (want_depth) zacc = __fadd_rn(zacc, __fmul_rn(wk, a.z));
             wsum = __fadd_rn(wsum, wk);
           }
         }
@@ -435,6 +461,7 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
       // slack of the reciprocal would be amplified by 1/sum(w), so redo these few pixels with
       // the true division
       wsum = 0.f;
+      zacc = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) acc[ch] = 0.f;
 #pragma unroll
@@ -448,6 +475,7 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
           acc[1] = __fadd_rn(acc[1], __fmul_rn(w, f4.y));
           acc[2] = __fadd_rn(acc[2], __fmul_rn(w, f4.z));
           acc[3] = __fadd_rn(acc[3], __fmul_rn(w, f4.w));
+          zacc = __fadd_rn(zacc, __fmul_rn(w, a.z));
           wsum = __fadd_rn(wsum, w);
         }
       }
@@ -455,19 +483,118 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
     const float inv_t = __frcp_rn(fmaxf(wsum, 1e-4f));
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) acc[ch] = __fmul_rn(acc[ch], inv_t);
+    zacc = __fmul_rn(zacc, inv_t);
     ones_acc = __fmul_rn(wsum, inv_t);
   }
   const bool is_bg = sl.s[0] < 0;  // _add_background_color_to_images: idx[:, 0] < 0
   const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
   if (p.mask) p.mask[pix] = m;
-  if (p.image) {
+  if (p.mask_u8) p.mask_u8[pix] = (uint8_t)(m * 255.0f);
+  if (want_depth) p.depth[pix] = is_bg ? 0.0f : zacc;  // background depth 0, like a zero background colour
+  if (p.image != nullptr || p.image_u8 != nullptr) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       if (ch < nch) {
         float v = is_bg ? p.bg[ch] : acc[ch];
         // combined = (1 - mask) * static + mask * dyn   (pgdvs_renderer.py:169-172)
         if (blend) v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st[ch]), __fmul_rn(m, v));
-        p.image[pix * nch + ch] = v;
+        if (p.image) p.image[pix * nch + ch] = v;
+        if (p.image_u8) {
+          // engines/evaluator_pgdvs.py:51-77: NaN -> 0, clamp(0, 1), (x * 255).byte()
+          const float cl = (v != v) ? 0.0f : fminf(fmaxf(v, 0.0f), 1.0f);
+          p.image_u8[pix * nch + ch] = (uint8_t)(int)(cl * 255.0f);
+        }
+      }
+    }
+  }
+}
+
+// The PGDVS configuration of the epilogue (K == KP, NormWeightedCompositor over rgb) for the staged
+// kernels, written without a branch per winner: the 2 K record loads are issued back to back
+// (an empty slot reads slot 0, which the caller keeps FINITE — k_raster_pair zeroes it), everything
+// after them is selects.  Same operations in the same order as pixel_epilogue<KP, true, Records, true>, i.e.
+// the same bits.
+template <int KP, typename Records>
+__device__ __forceinline__ void spec_epilogue(const RasterParams& p, const Slots<KP>& sl, const PixelCtx& c,
+                                              int n, int x, int y, const Records rec) {
+  static_assert(KP % 4 == 0, "128-bit fragment stores");
+  const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
+  const bool want_image = (p.image != nullptr) || (p.image_u8 != nullptr);
+  const bool blend = (p.static_rgb != nullptr) && want_image;
+  const bool want_depth = p.depth != nullptr;
+  float st[3] = {0.f, 0.f, 0.f};
+  if (blend) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) st[ch] = __ldg(p.static_rgb + pix * 3 + ch);
+  }
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, zacc = 0.f, wsum = 0.f;
+  // four winners at a time: eight 128-bit loads in flight, then one 128-bit store per fragment array
+#pragma unroll
+  for (int k0 = 0; k0 < KP; k0 += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int s = max(sl.s[k0 + kk], 0);
+      a[kk] = rec.a(s);
+      b[kk] = rec.b(s);
+    }
+    int oi[4];
+    float oz[4], od[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const bool valid = sl.s[k0 + kk] >= 0;
+      const float d = dist2_rn(a[kk].x, a[kk].y, c.xf, c.yf);
+      // an empty slot weighs 0 and reads the (finite) dummy record: adding 0 * f changes nothing
+      const float w = valid ? __fsub_rn(1.0f, __fmul_rn(d, p.inv_rr_weight)) : 0.0f;
+      acc0 = __fadd_rn(acc0, __fmul_rn(w, b[kk].x));
+      acc1 = __fadd_rn(acc1, __fmul_rn(w, b[kk].y));
+      acc2 = __fadd_rn(acc2, __fmul_rn(w, b[kk].z));
+      zacc = __fadd_rn(zacc, __fmul_rn(w, a[kk].z));
+      wsum = __fadd_rn(wsum, w);
+      oi[kk] = valid ? __float_as_int(a[kk].w) : -1;
+      oz[kk] = valid ? a[kk].z : -1.0f;
+      od[kk] = valid ? d : -1.0f;
+    }
+    const int64_t o = pix * KP + k0;
+    if (p.idx) *reinterpret_cast<int4*>(p.idx + o) = make_int4(oi[0], oi[1], oi[2], oi[3]);
+    if (p.zbuf) *reinterpret_cast<float4*>(p.zbuf + o) = make_float4(oz[0], oz[1], oz[2], oz[3]);
+    if (p.dists) *reinterpret_cast<float4*>(p.dists + o) = make_float4(od[0], od[1], od[2], od[3]);
+  }
+  if (wsum < 0.25f && sl.s[0] >= 0) {
+    // ill-conditioned normalisation (every hit sits near the rim of its splat): redo these few
+    // pixels with the true division (see pixel_epilogue)
+    wsum = acc0 = acc1 = acc2 = zacc = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (sl.s[k] >= 0) {
+        const float4 a = rec.a(sl.s[k]), b = rec.b(sl.s[k]);
+        const float w = __fsub_rn(1.0f, __fdiv_rn(dist2_rn(a.x, a.y, c.xf, c.yf), p.rr_weight));
+        acc0 = __fadd_rn(acc0, __fmul_rn(w, b.x));
+        acc1 = __fadd_rn(acc1, __fmul_rn(w, b.y));
+        acc2 = __fadd_rn(acc2, __fmul_rn(w, b.z));
+        zacc = __fadd_rn(zacc, __fmul_rn(w, a.z));
+        wsum = __fadd_rn(wsum, w);
+      }
+    }
+  }
+  const float inv_t = __frcp_rn(fmaxf(wsum, 1e-4f));
+  float out[3] = {__fmul_rn(acc0, inv_t), __fmul_rn(acc1, inv_t), __fmul_rn(acc2, inv_t)};
+  zacc = __fmul_rn(zacc, inv_t);
+  const float ones_acc = __fmul_rn(wsum, inv_t);
+  const bool is_bg = sl.s[0] < 0;
+  const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
+  if (p.mask) p.mask[pix] = m;
+  if (p.mask_u8) p.mask_u8[pix] = (uint8_t)(m * 255.0f);
+  if (want_depth) p.depth[pix] = is_bg ? 0.0f : zacc;
+  if (want_image) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float v = is_bg ? p.bg[ch] : out[ch];
+      if (blend) v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st[ch]), __fmul_rn(m, v));
+      if (p.image) p.image[pix * 3 + ch] = v;
+      if (p.image_u8) {
+        const float cl = (v != v) ? 0.0f : fminf(fmaxf(v, 0.0f), 1.0f);
+        p.image_u8[pix * 3 + ch] = (uint8_t)(int)(cl * 255.0f);
       }
     }
   }
@@ -994,6 +1121,507 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
 }
 
 // ---------------------------------------------------------------------------------------
+// Pair kernel: HALO = 1, scalar radius, K <= 8 — the NVIDIA-Dynamic-Scenes configuration (C1, C2).
+//
+// Same ingredients as k_raster_tile (TMA-staged row runs, work sort, sorted 32-bit keys, winner
+// exchange, raster-order epilogue) re-cut so that the fixed costs are paid once per 512 pixels
+// and neighbouring pixels share their candidates:
+//   * a CTA covers 32x16 pixels with 256 threads; every thread walks a VERTICAL PIXEL PAIR
+//     (x, 2q) / (x, 2q+1).  Their windows overlap in two of three rows: the shared rows are walked
+//     once (one LDS.128, one dx*dx, one key per candidate, inserted into both lists), the two
+//     exclusive rows side by side (row 0 -> upper pixel, row 3 -> lower pixel in the same step).
+//     Per pixel that is 12 record loads instead of 17 and two independent min/max chains in flight;
+//   * the tile's cell boundaries (18 rows x 35 values) are read ONCE, coalesced, into shared
+//     memory; a pixel's runs are two table entries per row (no per-pixel global loads, no parked
+//     run descriptors);
+//   * the z range that sizes the keys comes from the binning pass (per view, RasterParams::zrange)
+//     instead of a scan over the staged records, and the work sort uses a fixed bin width from the
+//     density hint: four CTA barriers per 512 pixels where k_raster_tile needs six per 256;
+//   * winners travel to the epilogue threads as 16-bit float4 indices (StagedAddr).
+// Fragments are bit-identical to k_raster_tile's (same keys, same ambiguity test, same rescan).
+// ---------------------------------------------------------------------------------------
+constexpr int kPairW = 32, kPairH = 16, kPairRows = kPairH + 2, kPairTabW = 36, kPairCols = 35;
+constexpr int kPairNull = 8;  // record slots reserved at the front of the staging buffer (zeroed)
+
+#ifndef PGDVS_PAIR_MINBLOCKS
+#define PGDVS_PAIR_MINBLOCKS 3
+#endif
+// Measured defaults (profiles/r02_pair_ab.md): the flattened four-row walk and the walker-side
+// epilogue; -DPGDVS_PAIR_WALK_PHASED / -DPGDVS_PAIR_EXCHANGE build the alternatives.
+#if !defined(PGDVS_PAIR_WALK_PHASED) && !defined(PGDVS_PAIR_WALK_FLAT)
+#define PGDVS_PAIR_WALK_FLAT
+#endif
+#if !defined(PGDVS_PAIR_EXCHANGE) && !defined(PGDVS_PAIR_WALKER_EPILOGUE)
+#define PGDVS_PAIR_WALKER_EPILOGUE
+#endif
+
+// one pixel through the global records: tiles whose runs do not fit the staging buffer
+template <int KP>
+__device__ __noinline__ void pixel_via_global(const RasterParams& p, int n, int x, int y) {
+  PixelCtx c;
+  c.xf = pixel_center_ndc(p.ax, x);
+  c.yf = pixel_center_ndc(p.ay, y);
+  c.r2 = p.r2;
+  const int span = 2 * p.halo + 1;
+  const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
+  PairList<KP> q;
+  q.init();
+  for (int ry = 0; ry < span; ++ry) {
+    const int s = __ldg(cs + (int64_t)ry * p.GW);
+    const int e = __ldg(cs + (int64_t)ry * p.GW + span);
+    for (int j = s; j < e; ++j) {
+      const float4 a = __ldg(p.recA + rec_a(j));
+      if (a.z <= q.z[KP - 1]) q.push(hit_test<false>(c, a, p.recA, j), a.z, j);
+    }
+  }
+  Slots<KP> sl;
+#pragma unroll
+  for (int i = 0; i < KP; ++i) sl.s[i] = q.s[i];
+  finish_global<KP, false>(p, c, n, x, y, sl, q.ambiguous(p.K));
+}
+
+// The walk of one pixel pair over the staged records.  Rows 1 and 2 of the pair's four window
+// rows belong to both pixels, row 0 only to the upper (A), row 3 only to the lower (B).
+// Ordinals: 0 .. c12-1 = rows 1, 2 (shared numbering); c12 + t = t-th record of row 0 (A) / row 3 (B).
+template <int KP, bool EXACT>
+__device__ __forceinline__ void walk_pair(const StagedRecords rec, const KeyCode kc, const float xf,
+                                          const float yfa, const float yfb, const float r2, const int s0,
+                                          const int l0, const int s1, const int l1, const int s2, const int l2,
+                                          const int s3, const int l3, KeyList<KP>& qa, KeyList<KP>& qb) {
+  const uint32_t mul = 1u << kc.bits;
+  auto zkey = [&](float z, uint32_t tk, uint32_t t) -> uint32_t {
+    const uint32_t zb = __float_as_uint(__fadd_rn(z, 0.0f));
+    if (EXACT) {
+      uint32_t key;  // (zb - base) * 2^bits + t as one multiply-add: tk = t - base * 2^bits
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(zb), "r"(mul), "r"(tk));
+      return key;
+    }
+    return (((zb - kc.base) >> kc.sh) << kc.bits) | t;
+  };
+  const int c1 = l1, c12 = l1 + l2, o2 = s2 - c1;
+  uint32_t tk = 0u - kc.base * mul;
+  // ---- rows 1 and 2: every record is a candidate of both pixels
+  auto shared_cand = [&](int t, uint32_t tkk, uint32_t& ka, uint32_t& kb) {
+    const int j = t + (t < c1 ? s1 : o2);
+    const float4 a = rec.a(j);
+    const float dx = __fsub_rn(a.x, xf);
+    const float dx2 = __fmul_rn(dx, dx);
+    const float dya = __fsub_rn(a.y, yfa), dyb = __fsub_rn(a.y, yfb);
+    const float da = __fadd_rn(dx2, __fmul_rn(dya, dya));
+    const float db = __fadd_rn(dx2, __fmul_rn(dyb, dyb));
+    const uint32_t key = zkey(a.z, tkk, (uint32_t)t);
+    ka = (da < r2) ? key : kEmpty;
+    kb = (db < r2) ? key : kEmpty;
+  };
+  int t = 0;
+  for (; t + 1 < c12; t += 2, tk += 2) {
+    uint32_t a1, b1, a2, b2;
+    shared_cand(t, tk, a1, b1);
+    shared_cand(t + 1, tk + 1, a2, b2);
+    qa.insert2(a1, a2);
+    qb.insert2(b1, b2);
+  }
+  if (t < c12) {
+    uint32_t a1, b1;
+    shared_cand(t, tk, a1, b1);
+    qa.insert(a1);
+    qb.insert(b1);
+  }
+  // ---- rows 0 and 3 side by side: step u feeds row0[u] to A and row3[u] to B
+  tk = 0u - kc.base * mul + (uint32_t)c12;
+  auto own_cand = [&](int u, int s, int l, float yf, uint32_t tkk) -> uint32_t {
+    // past the end of the shorter run the last record is read again and discarded (l == 0: the
+    // zeroed slot in front of the run, the buffer starts with kPairNull of them)
+    const int j = s + min(u, l - 1);
+    const float4 a = rec.a(j);
+    const float d = dist2_rn(a.x, a.y, xf, yf);
+    const uint32_t key = zkey(a.z, tkk, (uint32_t)(c12 + u));
+    return (u < l && d < r2) ? key : kEmpty;
+  };
+  const int m03 = max(l0, l3);
+  int u = 0;
+  for (; u + 1 < m03; u += 2, tk += 2) {
+    const uint32_t a1 = own_cand(u, s0, l0, yfa, tk), a2 = own_cand(u + 1, s0, l0, yfa, tk + 1);
+    const uint32_t b1 = own_cand(u, s3, l3, yfb, tk), b2 = own_cand(u + 1, s3, l3, yfb, tk + 1);
+    qa.insert2(a1, a2);
+    qb.insert2(b1, b2);
+  }
+  if (u < m03) {
+    qa.insert(own_cand(u, s0, l0, yfa, tk));
+    qb.insert(own_cand(u, s3, l3, yfb, tk));
+  }
+}
+
+// Variant (-DPGDVS_PAIR_WALK_FLAT): ONE flattened loop over the four window rows, every record
+// tested against both pixels (a record of row 0 can never hit the lower pixel, nor one of row 3 the
+// upper: they are >= 1.5 pixels away while halo == 1 means r < 1.484 pixels — the test says so by
+// itself).  One loop instead of two means the lanes of a warp wait for each other once.
+template <int KP, bool EXACT>
+__device__ __forceinline__ void walk_pair_flat(const StagedRecords rec, const KeyCode kc, const float xf,
+                                               const float yfa, const float yfb, const float r2, const int s0,
+                                               const int l0, const int s1, const int l1, const int s2,
+                                               const int l2, const int s3, const int l3, KeyList<KP>& qa,
+                                               KeyList<KP>& qb) {
+  const uint32_t mul = 1u << kc.bits;
+  const int c0 = l0, c01 = l0 + l1, c012 = c01 + l2, total = c012 + l3;
+  const int o1 = s1 - c0, o2 = s2 - c01, o3 = s3 - c012;
+  uint32_t tk = 0u - kc.base * mul;
+  auto cand = [&](int t, uint32_t tkk, uint32_t& ka, uint32_t& kb) {
+    const int j = t + (t < c01 ? (t < c0 ? s0 : o1) : (t < c012 ? o2 : o3));
+    const float4 a = rec.a(j);
+    const float dx = __fsub_rn(a.x, xf);
+    const float dx2 = __fmul_rn(dx, dx);
+    const float dya = __fsub_rn(a.y, yfa), dyb = __fsub_rn(a.y, yfb);
+    const float da = __fadd_rn(dx2, __fmul_rn(dya, dya));
+    const float db = __fadd_rn(dx2, __fmul_rn(dyb, dyb));
+    const uint32_t zb = __float_as_uint(__fadd_rn(a.z, 0.0f));
+    uint32_t key;
+    if (EXACT)
+      asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(zb), "r"(mul), "r"(tkk));
+    else
+      key = (((zb - kc.base) >> kc.sh) << kc.bits) | (uint32_t)t;
+    ka = (da < r2) ? key : kEmpty;
+    kb = (db < r2) ? key : kEmpty;
+  };
+  int t = 0;
+  for (; t + 1 < total; t += 2, tk += 2) {
+    uint32_t a1, b1, a2, b2;
+    cand(t, tk, a1, b1);
+    cand(t + 1, tk + 1, a2, b2);
+    qa.insert2(a1, a2);
+    qb.insert2(b1, b2);
+  }
+  if (t < total) {
+    uint32_t a1, b1;
+    cand(t, tk, a1, b1);
+    qa.insert(a1);
+    qb.insert(b1);
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const __grid_constant__ RasterParams p) {
+  static_assert(KP >= 2 && KP <= 8 && (KP % 2) == 0, "pair kernel: K-lists of 2, 4 or 8 keys");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4* s_rec = reinterpret_cast<float4*>(smem_raw);
+  const StagedRecords staged_rec{smem_u32(smem_raw)};
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_tab[kPairRows][kPairTabW];  // s_tab[r][c] = end of extended cell (x0 - 1 + c) of tile row r
+  __shared__ int s_delta[kPairRows];           // smem record index = global record index + s_delta[row]
+  __shared__ int s_staged, s_max;
+  __shared__ int s_hist[64];
+  __shared__ unsigned char s_perm[256];
+  __shared__ float s_xf[kPairW], s_yf[kPairH];
+  __shared__ __align__(16) uint16_t s_win[kPairW * kPairH * KP];  // per pixel its K winners (float4 indices)
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * kPairW, y0 = blockIdx.y * kPairH;
+  const int n = blockIdx.z;
+
+  // ---- global reads first: the tile's cell boundaries (coalesced; rows below the grid read as
+  //      empty, columns right of it as the end of their row)
+  int tabv[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = tid + k * 256;
+    tabv[k] = 0;
+    if (i < kPairRows * kPairCols) {
+      const int r = i / kPairCols, c = i - r * kPairCols;
+      if (y0 + r < p.GH)
+        tabv[k] = __ldg(p.cell_end + ((int64_t)n * p.GH + y0 + r) * p.GW + min(x0 - 1 + c, p.GW - 1));
+    }
+  }
+  const uint32_t z_nlo = __ldg(p.zrange + 2 * n), z_hi = __ldg(p.zrange + 2 * n + 1);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_max = 0;
+  }
+  if (tid < 64) s_hist[tid] = 0;
+  if (tid >= 64 && tid < 64 + 2 * kPairNull) s_rec[tid - 64] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid >= 96 && tid < 96 + kPairW) s_xf[tid - 96] = pixel_center_ndc(p.ax, x0 + tid - 96);
+  if (tid >= 128 && tid < 128 + kPairH) s_yf[tid - 128] = pixel_center_ndc(p.ay, y0 + tid - 128);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = tid + k * 256;
+    if (i < kPairRows * kPairCols) {
+      const int r = i / kPairCols;
+      s_tab[r][i - r * kPairCols] = tabv[k];
+    }
+  }
+  __syncthreads();  // (1) table, histogram, mbarrier
+
+  // ---- place the rows, arm the barrier, issue one bulk copy per row.  Every warp computes the
+  //      placement (a shuffle scan over the 18 row lengths it reads from the table) and issues the
+  //      copies of rows warp, warp + 8, warp + 16, so that no warp is held up by 18 serial issues
+  {
+    int gs = 0, len = 0;
+    if (lane < kPairRows) {
+      gs = s_tab[lane][0];
+      len = s_tab[lane][kPairCols - 1] - gs;
+    }
+    // row r sits at slot base_r + (gs & 7), base_r a multiple of 8 (rec_a / rec_b agree on both sides)
+    const int pad_len = (len > 0) ? (((gs & 7) + len + 7) & ~7) : 0;
+    int inc = pad_len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int total = kPairNull + __shfl_sync(0xffffffffu, inc, kPairRows - 1);
+    int cnt = len;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    const bool fits = total <= p.smem_records;
+    const int dst_slot = kPairNull + (inc - pad_len) + (gs & 7);
+    if (warp == 0) {
+      if (lane < kPairRows) s_delta[lane] = dst_slot - gs;
+      if (lane == 0) {
+        s_staged = fits ? 1 : 0;
+        if (fits) {
+          const uint32_t bytes = (uint32_t)cnt * 32u;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&s_bar)), "r"(bytes)
+                       : "memory");
+        }
+      }
+    }
+    if (fits && lane < kPairRows && (lane & 7) == warp && len > 0) {
+      const float4* src = p.recA + (int64_t)2 * gs;
+      float4* dst = s_rec + 2 * dst_slot;
+      const uint32_t bytes = (uint32_t)len * 32u;
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              smem_u32(dst)),
+          "l"(src), "r"(bytes), "r"(smem_u32(&s_bar))
+          : "memory");
+    }
+  }
+
+  // ---- work of the identity pair (q = warp, column = lane) -> counting-sort bin
+  int my_rank, bin;
+  {
+    const int q = warp, x = x0 + lane, ya = y0 + 2 * q;
+    int l[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) l[r] = s_tab[2 * q + r][lane + 3] - s_tab[2 * q + r][lane];
+    if (x >= p.W || ya >= p.H) l[0] = l[1] = l[2] = l[3] = 0;
+    if (ya + 1 >= p.H) l[3] = 0;
+#ifdef PGDVS_PAIR_WALK_FLAT
+    const int work = l[0] + l[1] + l[2] + l[3];
+#else
+    const int work = l[1] + l[2] + max(l[0], l[3]);
+#endif
+    const int wmax = __reduce_max_sync(0xffffffffu, work);
+    if (lane == 0) atomicMax(&s_max, wmax);
+    bin = 63 - min(63, (int)((float)work * p.pair_bin_scale));  // heaviest pairs first
+    my_rank = atomicAdd(&s_hist[bin], 1);
+  }
+  __syncthreads();  // (2) histogram, s_max, s_staged / s_delta
+  {
+    // every warp scans the 64 bins itself (two per lane): cheaper than a barrier around one warp doing it
+    const int a0 = s_hist[2 * lane], a1 = s_hist[2 * lane + 1];
+    int inc = a0 + a1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int ex0 = inc - a0 - a1;  // exclusive prefix of bin 2 * lane
+    const int e = __shfl_sync(0xffffffffu, ex0, bin >> 1);
+    const int a = __shfl_sync(0xffffffffu, a0, bin >> 1);
+    s_perm[e + ((bin & 1) ? a : 0) + my_rank] = (unsigned char)tid;
+  }
+  if (!s_staged) {  // (uniform) the tile's runs do not fit: every thread takes its identity pixels
+    const int x = x0 + lane;
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int y = y0 + warp + 8 * h;
+      if (x < p.W && y < p.H) pixel_via_global<KP>(p, n, x, y);
+    }
+    return;
+  }
+  __syncthreads();  // (3) permutation
+
+  // ---- the pair this thread walks
+  const int mine = s_perm[tid];
+  const int q = mine >> 5, lx = mine & 31;
+  const int x = x0 + lx, ya = y0 + 2 * q;
+  int rs[4], rl[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int st = s_tab[2 * q + r][lx];
+    rl[r] = s_tab[2 * q + r][lx + 3] - st;
+    rs[r] = st + s_delta[2 * q + r];
+  }
+  const bool in_a = (x < p.W) && (ya < p.H), in_b = (x < p.W) && (ya + 1 < p.H);
+  if (!in_a) rl[0] = rl[1] = rl[2] = rl[3] = 0;
+  if (!in_b) rl[3] = 0;
+  const float xf = s_xf[lx], yfa = s_yf[2 * q], yfb = s_yf[2 * q + 1];
+  KeyCode kc;  // the same code for every pixel of the tile: candidates <= s_max, z range of the view
+  kc.init(s_max, ~z_nlo, z_hi);
+  {
+    const uint32_t bar = smem_u32(&s_bar);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\n\t"
+          "selp.u32 %0, 1, 0, P1;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+  KeyList<KP> qa, qb;
+  qa.init();
+  qb.init();
+#ifdef PGDVS_PAIR_WALK_FLAT
+#define PGDVS_WALK_PAIR walk_pair_flat
+#else
+#define PGDVS_WALK_PAIR walk_pair
+#endif
+  if (kc.sh == 0)
+    PGDVS_WALK_PAIR<KP, true>(staged_rec, kc, xf, yfa, yfb, p.r2, rs[0], rl[0], rs[1], rl[1], rs[2], rl[2], rs[3], rl[3], qa, qb);
+  else
+    PGDVS_WALK_PAIR<KP, false>(staged_rec, kc, xf, yfa, yfb, p.r2, rs[0], rl[0], rs[1], rl[1], rs[2], rl[2], rs[3], rl[3], qa, qb);
+
+  // ---- ordinal -> float4 index of the record's A part; hand the winners to the pixel's own thread
+  constexpr uint16_t kNone = 0u, kDone = 1u;  // indices 0 .. 2 * kPairNull - 1 are the zeroed null slots
+  const bool fullk = (p.K == KP);
+  {
+#ifdef PGDVS_PAIR_WALK_FLAT
+    const int c0 = rl[0], c01 = c0 + rl[1], c012 = c01 + rl[2];
+    const int f1 = rs[1] - c0, f2 = rs[2] - c01, f3 = rs[3] - c012;
+#else
+    const int c1 = rl[1], c12 = rl[1] + rl[2], o2 = rs[2] - c1;
+    const int oa = rs[0] - c12, ob = rs[3] - c12;
+#endif
+    bool amb_a = in_a && (fullk ? qa.ambiguous_full(kc) : qa.ambiguous(p.K, kc));
+    bool amb_b = in_b && (fullk ? qb.ambiguous_full(kc) : qb.ambiguous(p.K, kc));
+    uint32_t va[KP], vb[KP];
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+      const int o_a = (int)(qa.k[i] & kc.mask), o_b = (int)(qb.k[i] & kc.mask);
+      // (selects only; an empty key decodes to some valid slot that the last select discards)
+#ifdef PGDVS_PAIR_WALK_FLAT
+      const int ja = o_a + (o_a < c01 ? (o_a < c0 ? rs[0] : f1) : (o_a < c012 ? f2 : f3));
+      const int jb = o_b + (o_b < c01 ? (o_b < c0 ? rs[0] : f1) : (o_b < c012 ? f2 : f3));
+#else
+      const int ja = o_a + ((o_a < c12) ? (o_a < c1 ? rs[1] : o2) : oa);
+      const int jb = o_b + ((o_b < c12) ? (o_b < c1 ? rs[1] : o2) : ob);
+#endif
+      const uint32_t fa = (uint32_t)rec_a(ja), fb = (uint32_t)rec_a(jb);
+      va[i] = (qa.k[i] != kEmpty) ? fa : (uint32_t)kNone;
+      vb[i] = (qb.k[i] != kEmpty) ? fb : (uint32_t)kNone;
+    }
+    if (amb_a | amb_b) {  // rare: exact (z, idx) rescan over the global records, finished by the walker
+      PixelCtx c;
+      c.xf = xf;
+      c.r2 = p.r2;
+      Slots<KP> sl;
+#pragma unroll
+      for (int i = 0; i < KP; ++i) sl.s[i] = -1;
+      if (amb_a) {
+        c.yf = yfa;
+        finish_global<KP, false>(p, c, n, x, ya, sl, true);
+        va[0] = kDone;
+      }
+      if (amb_b) {
+        c.yf = yfb;
+        finish_global<KP, false>(p, c, n, x, ya + 1, sl, true);
+        vb[0] = kDone;
+      }
+    }
+#ifdef PGDVS_PAIR_WALKER_EPILOGUE
+    // (experiment) no exchange, no fourth barrier: the walker finishes its own two pixels
+    {
+      const StagedAddr sa{staged_rec.base};
+      PixelCtx c;
+      c.xf = xf;
+      c.r2 = p.r2;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        if (!(h ? in_b : in_a)) continue;
+        if ((h ? vb[0] : va[0]) == kDone) continue;
+        Slots<KP> sl;
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+          const uint32_t v = h ? vb[i] : va[i];
+          sl.s[i] = (v == kNone) ? -1 : (int)v;
+        }
+        c.yf = h ? yfb : yfa;
+        if (fullk && KP == 8 && p.compositor == PGDVS_COMPOSITE_NORM_WEIGHTED && p.C == 3)
+          spec_epilogue<8>(p, reinterpret_cast<const Slots<8>&>(sl), c, n, x, ya + h, sa);
+        else if (fullk)
+          pixel_epilogue<KP, true>(p, sl, c, n, x, ya + h, sa);
+        else
+          pixel_epilogue<KP, false>(p, sl, c, n, x, ya + h, sa);
+      }
+      return;
+    }
+#endif
+    uint16_t* dst_a = s_win + ((2 * q) * kPairW + lx) * KP;
+    uint16_t* dst_b = dst_a + kPairW * KP;
+    if constexpr (KP == 8) {
+      *reinterpret_cast<uint4*>(dst_a) = make_uint4(va[0] | (va[1] << 16), va[2] | (va[3] << 16), va[4] | (va[5] << 16), va[6] | (va[7] << 16));
+      *reinterpret_cast<uint4*>(dst_b) = make_uint4(vb[0] | (vb[1] << 16), vb[2] | (vb[3] << 16), vb[4] | (vb[5] << 16), vb[6] | (vb[7] << 16));
+    } else if constexpr (KP == 4) {
+      *reinterpret_cast<uint2*>(dst_a) = make_uint2(va[0] | (va[1] << 16), va[2] | (va[3] << 16));
+      *reinterpret_cast<uint2*>(dst_b) = make_uint2(vb[0] | (vb[1] << 16), vb[2] | (vb[3] << 16));
+    } else {
+      *reinterpret_cast<uint32_t*>(dst_a) = va[0] | (va[1] << 16);
+      *reinterpret_cast<uint32_t*>(dst_b) = vb[0] | (vb[1] << 16);
+    }
+  }
+  __syncthreads();  // (4) winners
+
+  // ---- epilogue in raster order: thread (warp, lane) finishes pixels (lane, warp) and (lane, warp + 8)
+  const StagedAddr staged_addr{staged_rec.base};
+  const int ex = x0 + lane;
+  if (ex >= p.W) return;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const int ly = warp + 8 * h;
+    const int ey = y0 + ly;
+    if (ey >= p.H) break;
+    const uint16_t* src = s_win + (ly * kPairW + lane) * KP;
+    uint32_t w[KP / 2];
+    if constexpr (KP == 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src);
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else if constexpr (KP == 4) {
+      const uint2 v = *reinterpret_cast<const uint2*>(src);
+      w[0] = v.x; w[1] = v.y;
+    } else {
+      w[0] = *reinterpret_cast<const uint32_t*>(src);
+    }
+    if ((w[0] & 0xFFFFu) == kDone) continue;  // finished by its walker
+    Slots<KP> sl;
+#pragma unroll
+    for (int i = 0; i < KP / 2; ++i) {
+      const int lo = (int)(w[i] & 0xFFFFu), hi = (int)(w[i] >> 16);
+      sl.s[2 * i] = (lo == kNone) ? -1 : lo;
+      sl.s[2 * i + 1] = (hi == kNone) ? -1 : hi;
+    }
+    PixelCtx c;
+    c.xf = s_xf[lane];
+    c.yf = s_yf[ly];
+    c.r2 = p.r2;
+    if (fullk) {
+#ifndef PGDVS_RASTER_NO_SPEC
+      if (KP == 8 && p.compositor == PGDVS_COMPOSITE_NORM_WEIGHTED && p.C == 3)
+        spec_epilogue<8>(p, reinterpret_cast<const Slots<8>&>(sl), c, n, ex, ey, staged_addr);
+      else
+#endif
+        pixel_epilogue<KP, true>(p, sl, c, n, ex, ey, staged_addr);
+    } else {
+      pixel_epilogue<KP, false>(p, sl, c, n, ex, ey, staged_addr);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // In-place z-sort of the small cells (generic path only).  One thread per cell: the cell's
 // records are read into registers, ranked by their z bit pattern (z >= 0, so the pattern orders
 // like the value; NaN patterns sort last; equal z keep their order) and written back to their
@@ -1004,6 +1632,18 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
 int maybe_sort_cells(RasterParams& p, int KP, cudaStream_t stream);
 
 #if !defined(PGDVS_RASTER_PART) || PGDVS_RASTER_PART == 0
+static int g_switch[kSwCount] = {-2, -2, -2};  // -2 = environment not read yet
+int debug_switch(int which) {
+  static const char* const names[kSwCount] = {"PGDVS_SORT_CELLS", "PGDVS_RASTER_FORCE_GENERIC", "PGDVS_RASTER_NO_PAIR"};
+  int v = g_switch[which];
+  if (v == -2) {
+    const char* env = getenv(names[which]);
+    v = (env == nullptr) ? -1 : (env[0] == '1' ? 1 : 0);
+    g_switch[which] = v;
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(128) k_sort_cells(const int* __restrict__ cell_end, float4* rec,
                                                     int64_t n_cells) {
   const int64_t cell = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -1043,7 +1683,8 @@ int maybe_sort_cells(RasterParams& p, int KP, cudaStream_t stream) {
   const double span = 2.0 * p.halo + 1.0;
   const double candidates = span * span * p.density;  // mean candidates per pixel
   bool sort = candidates >= 64.0 && candidates >= 4.0 * KP;
-  if (const char* env = getenv("PGDVS_SORT_CELLS")) sort = env[0] == '1';  // developer switch
+  const int sw_sort = debug_switch(kSwSortCells);
+  if (sw_sort >= 0) sort = sw_sort == 1;
   p.cells_sorted = 0;
   if (!sort) return 0;
   const int64_t n_cells = (int64_t)p.N * p.GH * p.GW;
@@ -1058,60 +1699,120 @@ int maybe_sort_cells(RasterParams& p, int KP, cudaStream_t stream) {
 #ifndef PGDVS_RASTER_SMEM_BYTES
 #define PGDVS_RASTER_SMEM_BYTES (24 * 1024)
 #endif
-#ifndef PGDVS_RASTER_SMEM_BYTES_WIDE
-#define PGDVS_RASTER_SMEM_BYTES_WIDE (100 * 1024)
-#endif
-
-template <int KP, int HALO>
-static bool launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, cudaStream_t stream) {
-  // size the staging buffer from the mean point density (points per pixel of the batch) with
-  // 1.5x head-room; tiles that still overflow fall back to global reads inside the kernel.
-  // If even the mean tile would not fit in PGDVS_RASTER_SMEM_BYTES_WIDE, the generic kernel
-  // (more resident CTAs, no staging) is the better choice.
-  const double tile_cells = (double)(kTileW + 2 * HALO) * (kTileH + 2 * HALO);
 #ifndef PGDVS_RASTER_HEADROOM
 #define PGDVS_RASTER_HEADROOM 1.5
 #endif
 #ifndef PGDVS_RASTER_HEADROOM_DENSE
 #define PGDVS_RASTER_HEADROOM_DENSE 1.15
 #endif
+#ifndef PGDVS_RASTER_SMEM_BYTES_WIDE
+#define PGDVS_RASTER_SMEM_BYTES_WIDE (100 * 1024)
+#endif
+
+// Opt-in limit for dynamic shared memory above 48 KB: a per-DEVICE function attribute, so the
+// value already granted is tracked per (instantiation, device).  Races between host threads are
+// benign (the attribute is only ever raised, and setting it twice is harmless).
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+static int raise_smem_limit(Kernel kernel, int (&granted)[kMaxDevices], int smem) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= kMaxDevices || smem > granted[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < kMaxDevices) granted[dev] = smem;
+  }
+  return 0;
+}
+
+// returns 1 = launched, 0 = not applicable (use the generic kernel), < 0 = -(CUDA error)
+template <int KP, int HALO>
+static int launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, cudaStream_t stream) {
+  // size the staging buffer from the mean point density (points per pixel of the batch) with
+  // 1.5x head-room; tiles that still overflow fall back to global reads inside the kernel.
+  // If even the mean tile would not fit in PGDVS_RASTER_SMEM_BYTES_WIDE, the generic kernel
+  // (more resident CTAs, no staging) is the better choice.
+  const double tile_cells = (double)(kTileW + 2 * HALO) * (kTileH + 2 * HALO);
   double need = PGDVS_RASTER_HEADROOM * density * tile_cells * 32.0;
   if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) {
     // dense clouds: trade head-room for staging at all (tiles that still overflow walk the
     // global records inside the kernel)
     need = PGDVS_RASTER_HEADROOM_DENSE * density * tile_cells * 32.0;
-    if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) return false;
+    if (need > (double)PGDVS_RASTER_SMEM_BYTES_WIDE) return 0;
   }
   int smem = (int)need;
   if (smem < 24 * 1024) smem = 24 * 1024;
   smem = (smem + 1023) & ~1023;
   if (HALO == 1 && smem < PGDVS_RASTER_SMEM_BYTES) smem = PGDVS_RASTER_SMEM_BYTES;
   p.smem_records = smem / 32;
-  static int attr_smem = 0;  // per instantiation: raise the opt-in limit when needed
-  if (smem > attr_smem) {
-    cudaFuncSetAttribute(k_raster_tile<KP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_smem = smem;
-  }
+  static int granted[kMaxDevices] = {};  // per instantiation and device
+  if (int rc = raise_smem_limit(k_raster_tile<KP, HALO>, granted, smem)) return -rc;
   k_raster_tile<KP, HALO><<<grid, block, smem, stream>>>(p);
-  return true;
+  return 1;
+}
+
+#ifndef PGDVS_PAIR_SMEM_MAX
+#define PGDVS_PAIR_SMEM_MAX (64 * 1024)
+#endif
+// returns 1 = launched, 0 = not applicable, < 0 = -(CUDA error)
+template <int KP>
+static int launch_pair(RasterParams& p, cudaStream_t stream) {
+  const double tile_cells = (double)(kPairW + 2) * kPairRows;
+  double need = PGDVS_RASTER_HEADROOM * p.density * tile_cells * 32.0;
+  if (need > (double)PGDVS_PAIR_SMEM_MAX) {
+    need = PGDVS_RASTER_HEADROOM_DENSE * p.density * tile_cells * 32.0;
+    if (need > (double)PGDVS_PAIR_SMEM_MAX) return 0;  // too dense to stage 32x16 tiles
+    need = (double)PGDVS_PAIR_SMEM_MAX;
+  }
+  int smem = (int)need + 32 * (kPairNull + 8 * kPairRows);  // null slots + per-row alignment padding
+  if (smem < 32 * 1024) smem = 32 * 1024;
+  if (smem > PGDVS_PAIR_SMEM_MAX) smem = PGDVS_PAIR_SMEM_MAX;
+  smem = (smem + 1023) & ~1023;
+  p.smem_records = smem / 32;
+  // a pair's work is ~9.9 window cells' worth of records (two shared rows + the longer of the two
+  // exclusive ones); 64 bins span 2.5x that
+#ifdef PGDVS_PAIR_WALK_FLAT
+  p.pair_bin_scale = (float)(64.0 / (2.5 * 12.0 * (p.density > 1e-3 ? p.density : 1e-3)));
+#else
+  p.pair_bin_scale = (float)(64.0 / (2.5 * 9.9 * (p.density > 1e-3 ? p.density : 1e-3)));
+#endif
+  dim3 grid((p.W + kPairW - 1) / kPairW, (p.H + kPairH - 1) / kPairH, p.N);
+  // small launches (a single NVIDIA-sized view is 306 of these CTAs for 444 resident slots) are
+  // better balanced by the 32x8 tiles of k_raster_tile: 0.032 vs 0.042 ms on C1
+  if ((int64_t)grid.x * grid.y * grid.z < (int64_t)2 * 148 * PGDVS_PAIR_MINBLOCKS && p.no_pair < 0) return 0;
+  static int granted[kMaxDevices] = {};
+  if (int rc = raise_smem_limit(k_raster_pair<KP>, granted, smem)) return -rc;
+  k_raster_pair<KP><<<grid, 256, smem, stream>>>(p);
+  return 1;
 }
 
 template <int KP>
 int launch_raster(RasterParams& p, cudaStream_t stream) {
   dim3 block(32, 8);
   dim3 grid((p.W + 31) / 32, (p.H + 7) / 8, p.N);
-  bool done = false;
+  int done = 0;
+#ifndef PGDVS_RASTER_NO_PAIR
+  if constexpr (KP == 2 || KP == 4 || KP == 8) {
+    if (p.halo == 1 && p.r2 >= 0.0f && !p.force_generic && p.no_pair != 1) {
+      done = launch_pair<KP>(p, stream);
+      if (done < 0) return -done;
+      if (done) return check_launch();
+    }
+  }
+#endif
 #ifndef PGDVS_RASTER_NO_TMA
   if constexpr (KP <= 32) {
     const double density = p.density;
     if (p.r2 < 0.0f || p.force_generic)
-      done = false;  // per-point radii: generic kernel
+      done = 0;  // per-point radii: generic kernel
     else if (p.halo == 1)
       done = launch_tile<KP, 1>(p, grid, block, density, stream);
     else if (p.halo == 2)
       done = launch_tile<KP, 2>(p, grid, block, density, stream);
     else if (p.halo == 3)
       done = launch_tile<KP, 3>(p, grid, block, density, stream);
+    if (done < 0) return -done;
   }
 #endif
   if (!done) {
@@ -1154,12 +1855,31 @@ PGDVS_RASTER_FOR_PART(PGDVS_RASTER_PART, PGDVS_RASTER_DEFINE)
 #if !defined(PGDVS_RASTER_PART) || PGDVS_RASTER_PART == 0
 using namespace pgdvs;
 
+extern "C" int pgdvs_debug_switch(int which, int value) {
+  if (which < 0 || which >= kSwCount || value < -1 || value > 1) return PGDVS_E_BADARG;
+  debug_switch(which);  // (settle the lazy environment read first)
+  g_switch[which] = value;
+  return PGDVS_OK;
+}
+
 extern "C" int pgdvs_rasterize_composite(void* workspace, size_t workspace_bytes, int N,
                                          int64_t P, int H, int W, int K, float radius_max,
                                          int per_point_radius, int C, int compositor,
                                          float rr_weight, const float* background,
                                          const float* static_rgb, int32_t* idx, float* zbuf,
                                          float* dists, float* image, float* mask, void* stream_) {
+  return pgdvs_rasterize_composite_ex(workspace, workspace_bytes, N, P, H, W, K, radius_max, per_point_radius, C,
+                                      compositor, rr_weight, background, static_rgb, idx, zbuf, dists, image,
+                                      mask, nullptr, stream_);
+}
+
+extern "C" int pgdvs_rasterize_composite_ex(void* workspace, size_t workspace_bytes, int N,
+                                            int64_t P, int H, int W, int K, float radius_max,
+                                            int per_point_radius, int C, int compositor,
+                                            float rr_weight, const float* background,
+                                            const float* static_rgb, int32_t* idx, float* zbuf,
+                                            float* dists, float* image, float* mask,
+                                            const PgdvsRasterExtra* extra, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (workspace == nullptr || N < 0 || H <= 0 || W <= 0 || P < 0 || K < 1 ||
       !(radius_max >= 0.0f))
@@ -1171,7 +1891,10 @@ extern "C" int pgdvs_rasterize_composite(void* workspace, size_t workspace_bytes
   if (compositor != PGDVS_COMPOSITE_NONE) {
     if (C < 1 || C > PGDVS_MAX_FUSED_CHANNELS) return PGDVS_E_CHANNELS;
     if (!(rr_weight > 0.0f)) return PGDVS_E_BADARG;
-    if (static_rgb != nullptr && (image == nullptr)) return PGDVS_E_BADARG;
+    if (static_rgb != nullptr && image == nullptr && (extra == nullptr || extra->image_u8 == nullptr))
+      return PGDVS_E_BADARG;
+  } else if (extra != nullptr && (extra->depth || extra->image_u8 || extra->mask_u8)) {
+    return PGDVS_E_BADARG;  // the extra outputs are products of a compositor
   }
   BinLayout L = make_bin_layout(N, H, W, P, radius_max);
   if (workspace_bytes < L.total) return PGDVS_E_WORKSPACE;
@@ -1203,12 +1926,15 @@ extern "C" int pgdvs_rasterize_composite(void* workspace, size_t workspace_bytes
   p.dists = dists;
   p.image = image;
   p.mask = mask;
+  p.depth = extra ? extra->depth : nullptr;
+  p.image_u8 = extra ? extra->image_u8 : nullptr;
+  p.mask_u8 = extra ? extra->mask_u8 : nullptr;
   p.smem_records = 0;
   p.cells_sorted = 0;
-  {
-    const char* env = getenv("PGDVS_RASTER_FORCE_GENERIC");  // developer switch
-    p.force_generic = (env != nullptr && env[0] == '1') ? 1 : 0;
-  }
+  p.zrange = reinterpret_cast<const uint32_t*>(ws + L.off_zrange);
+  p.pair_bin_scale = 1.0f;
+  p.force_generic = (debug_switch(kSwForceGeneric) == 1) ? 1 : 0;
+  p.no_pair = debug_switch(kSwNoPair);  // 1: never, 0: whenever applicable (also small launches), -1: automatic
   // mean points per pixel of the batch (P is the capacity of the packed cloud: an upper bound)
   p.density = (double)P / ((double)N * (double)H * (double)W);
 

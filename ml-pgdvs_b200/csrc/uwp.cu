@@ -50,6 +50,7 @@ struct UwpParams {
   // fused binning (all null/0 in the plain mode)
   CellGrid g;
   int* cell_count;
+  uint32_t* zrange;  // [2 * n_views] per-view range of the filed z patterns (common.cuh)
   float4* preA;      // [cap] (x_ndc, y_ndc, z, cell id)  in packed (reference) order
   float4* preB;      // [cap * 3 floats] (r, g, b), unpadded
 };
@@ -151,6 +152,11 @@ template <bool FUSED>
 __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const __grid_constant__ UwpParams p) {
   constexpr int kWarps = kUwpThreads / 32;
   __shared__ int s_cnt[kUwpPix * kWarps];  // survivors of (k, warp), k-major == pixel order
+  // fused mode: range of the z patterns this CTA files under each member's view (common.cuh),
+  // kZChunk members at a time: (max ~bits, max bits), zero == empty
+  constexpr int kZChunk = 32;
+  __shared__ uint32_t s_z[kZChunk][2];
+  if (FUSED && threadIdx.x < 2 * kZChunk) (&s_z[0][0])[threadIdx.x] = 0u;  // (published by the barrier below)
   const int g = blockIdx.x / p.tiles_per_job;
   const int jt = blockIdx.x - g * p.tiles_per_job;
   const PgdvsUwpJob& J = p.jobs[group_member(p, g, 0)];
@@ -183,7 +189,9 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
 #pragma unroll
     for (int k = 0; k < kUwpPix; ++k) rank[k] += __shfl_sync(0xffffffffu, excl, k * kWarps + warp);
   }
-  if (s.valid == 0) return;
+  // (no early exit for threads without survivors: in the fused mode the CTA meets again at the
+  //  barriers of the z-range flush; every load and store below is guarded by the validity bits)
+  if (!FUSED && s.valid == 0) return;
 
   // ------------------------------------------------------------ world point + colour, once
   const bool lerp = (J.same_time == 0);
@@ -284,6 +292,7 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
     const int view = p.jobs[job_m].view;
     const PgdvsCamera cam = p.cams[view];
     const int tile_base = __ldg(p.tile_off + (int64_t)job_m * p.tiles_per_job + jt);
+    uint32_t z_nlo = 0u, z_hi = 0u;
 #pragma unroll
     for (int k = 0; k < kUwpPix; ++k) {
       if (!((s.valid >> k) & 1u)) continue;
@@ -291,7 +300,12 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
       const int64_t out = (int64_t)tile_base + rank[k];
       if (FUSED) {
         const int cell = point_cell(p.g, view, ndc.x, ndc.y, ndc.z);
-        if (cell >= 0) atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
+        if (cell >= 0) {
+          atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
+          const uint32_t zb = z_pattern(ndc.z);
+          z_nlo = max(z_nlo, ~zb);
+          z_hi = max(z_hi, zb);
+        }
         // packed-order record: (x, y, z, cell) + (r, g, b); the packed index is the position itself
         p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float(cell));
         float* pb = reinterpret_cast<float*>(p.preB) + out * 3;
@@ -315,6 +329,32 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
         p.xyz_world[out * 3 + 2] = wz[k];
       }
       if (p.src_pix) p.src_pix[out] = (int32_t)s.pix[k];
+    }
+    if (FUSED) {
+      // z range of this member's view: warp reduction -> shared-memory max; the CTA publishes its
+      // ranges kZChunk members at a time (a look at the current value, an atomic only if wider)
+      const int slot = m % kZChunk;
+      z_nlo = __reduce_max_sync(0xffffffffu, z_nlo);
+      z_hi = __reduce_max_sync(0xffffffffu, z_hi);
+      if ((threadIdx.x & 31) == 0 && (z_nlo | z_hi) != 0u) {
+        atomicMax(&s_z[slot][0], z_nlo);
+        atomicMax(&s_z[slot][1], z_hi);
+      }
+      if (slot == kZChunk - 1 || m == n_members - 1) {
+        __syncthreads();
+        if ((int)threadIdx.x <= slot) {
+          const int vm = p.jobs[group_member(p, g, m - slot + (int)threadIdx.x)].view;
+          const uint32_t nlo = s_z[threadIdx.x][0], hi = s_z[threadIdx.x][1];
+          if ((nlo | hi) != 0u) {
+            const uint2 cur = __ldcg(reinterpret_cast<const uint2*>(p.zrange) + vm);
+            if (nlo > cur.x) atomicMax(p.zrange + 2 * vm, nlo);
+            if (hi > cur.y) atomicMax(p.zrange + 2 * vm + 1, hi);
+          }
+          s_z[threadIdx.x][0] = 0u;
+          s_z[threadIdx.x][1] = 0u;
+        }
+        __syncthreads();
+      }
     }
   }
 }
@@ -376,7 +416,7 @@ static inline UwpLayout make_uwp_layout(int n_jobs, int H, int W) {
 static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras, int n_views, int H,
                    int W, float* xyz_ndc, float* rgb, float* xyz_world, int32_t* src_pix,
                    int64_t* first_idx, int64_t* num_points, int64_t* total_points, char* ws,
-                   const UwpLayout& L, const CellGrid* grid, int* cell_count, float4* preA,
+                   const UwpLayout& L, const CellGrid* grid, int* cell_count, uint32_t* zrange, float4* preA,
                    float4* preB, const int32_t* group_first, const int32_t* group_members, int n_groups,
                    cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(ws, 0, L.off_zero_end, stream);
@@ -409,6 +449,7 @@ static int run_uwp(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* camer
     if (grid != nullptr) {
       p.g = *grid;
       p.cell_count = cell_count;
+      p.zrange = zrange;
       p.preA = preA;
       p.preB = preB;
       k_uwp<true><<<grid_blocks, kUwpThreads, 0, stream>>>(p);
@@ -450,7 +491,7 @@ extern "C" int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs,
   if ((int64_t)n_jobs * H * W >= (int64_t)INT32_MAX) return PGDVS_E_BADARG;
   if (n_jobs > 0 && (!jobs || !cameras || !xyz_ndc || !rgb)) return PGDVS_E_BADARG;
   return run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, xyz_world, src_pix, first_idx,
-                 num_points, total_points, static_cast<char*>(workspace), L, nullptr, nullptr, nullptr,
+                 num_points, total_points, static_cast<char*>(workspace), L, nullptr, nullptr, nullptr, nullptr,
                  nullptr, group_first, group_members, n_groups, (cudaStream_t)stream_);
 }
 
@@ -493,7 +534,7 @@ extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCam
   const CellGrid g = make_cell_grid(H, W, B.halo);
   int rc = run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, nullptr, nullptr, first_idx,
                    num_points, total_points, ws + T.total, U, &g,
-                   reinterpret_cast<int*>(ws + B.off_cells),
+                   reinterpret_cast<int*>(ws + B.off_cells), reinterpret_cast<uint32_t*>(ws + B.off_zrange),
                    reinterpret_cast<float4*>(ws + T.off_preA), reinterpret_cast<float4*>(ws + T.off_preB),
                    group_first, group_members, n_groups, stream);
   if (rc) return rc;

@@ -197,8 +197,11 @@ class PreparedViews:
                  pack_frames: bool = True, group_jobs: bool = True):
         self.n_jobs, self.n_views, self.H, self.W = len(pairs), len(cams_p3d), H, W
         self.device = torch.device(device)
-        assert all(pairs[i].view <= pairs[i + 1].view for i in range(self.n_jobs - 1)), \
-            "jobs must be sorted by view"
+        if not all(pairs[i].view <= pairs[i + 1].view for i in range(self.n_jobs - 1)):
+            raise ValueError("jobs must be sorted by view")
+        if self.n_jobs and not (0 <= pairs[0].view and pairs[-1].view < self.n_views):
+            raise ValueError(f"job view indices must lie in [0, {self.n_views}) (the kernels index the camera "
+                             "array with them)")
         # cameras: float32 [N,16] rows = PgdvsCamera (R[9], T[3], focal[2], p0[2])
         if isinstance(cams_p3d, np.ndarray):
             cam_arr = np.ascontiguousarray(cams_p3d, np.float32).reshape(-1, 16)
@@ -329,17 +332,20 @@ def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=
 
 def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int, compositor: str = "norm",
                     static_rgb: Optional[torch.Tensor] = None, return_fragments: bool = False,
-                    raster_events=None, fused: bool = True, return_cloud: bool = False):
+                    raster_events=None, fused: bool = True, return_cloud: bool = False,
+                    return_depth: bool = False, return_u8: bool = False, return_f32: bool = True):
     """uwp kernel -> binning -> rasterize+composite(+mask, +static blend) for prepared views:
     stream-ordered stages, zero host syncs.  `fused=False` runs the stage-by-stage variant
-    (uwp -> packed [P,3] cloud -> pgdvs_bin_points -> rasterize), which gives identical results."""
+    (uwp -> packed [P,3] cloud -> pgdvs_bin_points -> rasterize), which gives identical results.
+    return_depth adds `depth` [N,H,W,1] (composited view depth), return_u8 adds `image_u8` /
+    `mask_u8` quantised in the rasterizer's epilogue (return_f32=False drops the fp32 copies)."""
     if not fused:
         cloud = unproject_warp_project(prep)
         out = ops.render_packed(cloud["xyz_ndc"], cloud["rgb"], cloud["first_idx"], cloud["num_points"],
                                 (prep.H, prep.W), radius, points_per_pixel, compositor=compositor,
                                 background=(0.0, 0.0, 0.0), static_rgb=static_rgb,
                                 return_fragments=return_fragments, return_mask=True,
-                                raster_events=raster_events)
+                                raster_events=raster_events, return_depth=return_depth, return_u8=return_u8)
         out["first_idx"], out["num_points"], out["cloud"] = cloud["first_idx"], cloud["num_points"], cloud
         return out
     # fused: [pack frames] -> uwp kernel (also files points under raster cells) -> scan -> fill
@@ -372,7 +378,8 @@ def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int
     ops.LAUNCHES["count"] += 6  # k_uwp_count, k_scan, k_uwp, k_uwp_finalize, k_scan, k_fill_pre
     out = ops.rasterize_workspace(ws_ptr, nbytes.value, dev, n_views, cap, H, W, K, float(radius), False, 3,
                                   ops._COMPOSITORS[compositor], float(radius) * float(radius),
-                                  (0.0, 0.0, 0.0), static_rgb, return_fragments, True, raster_events)
+                                  (0.0, 0.0, 0.0), static_rgb, return_fragments, True, raster_events,
+                                  return_depth=return_depth, return_u8=return_u8, return_f32=return_f32)
     out["first_idx"], out["num_points"] = first_idx, num_points
     out["cloud"] = {"xyz_ndc": xyz_ndc, "rgb": rgb, "first_idx": first_idx, "num_points": num_points,
                     "total": total, "_keepalive": prep}
@@ -382,33 +389,83 @@ def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int
 def render_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, *, radius: float,
                  points_per_pixel: int, compositor: str = "norm", static_rgb: Optional[torch.Tensor] = None,
                  return_fragments: bool = False, device=None, fused: bool = True,
-                 return_cloud: bool = False):
+                 return_cloud: bool = False, return_depth: bool = False, return_u8: bool = False):
     """The whole hot path for a batch of target views.
 
     tgt_cams: per view (K44, c2w44) OpenCV; static_rgb optional [N,H,W,3] (GNT render).
-    Returns dict(image [N,H,W,3], mask [N,H,W,1], [idx,zbuf,dists], first_idx, num_points, cloud)."""
+    Returns dict(image [N,H,W,3], mask [N,H,W,1], [depth [N,H,W,1]], [image_u8, mask_u8],
+    [idx,zbuf,dists], first_idx, num_points, cloud)."""
     device = device if device is not None else pairs[0].depth_1.device
     prep = prepare_views(pairs, tgt_cams, H, W, device)
     return render_prepared(prep, radius=radius, points_per_pixel=points_per_pixel, compositor=compositor,
                            static_rgb=static_rgb, return_fragments=return_fragments, fused=fused,
-                           return_cloud=return_cloud)
+                           return_cloud=return_cloud, return_depth=return_depth, return_u8=return_u8)
 
 
 # ----------------------------------------------------------------------------- L2 class
 class PGDVSDynamicRenderer(torch.nn.Module):
-    """Drop-in for the `pcl` branch of pgdvs.renderers.pgdvs_renderer_dyn.PGDVSDynamicRenderer."""
+    """Drop-in for pgdvs.renderers.pgdvs_renderer_dyn.PGDVSDynamicRenderer (`dyn_render_type` pcl /
+    softsplat / mesh; the track branch lives in pgdvs_b200.track.PGDVSDynamicTrackRenderer)."""
 
     def __init__(self, *, cfg=None, softsplat_metric_abs_alpha=100.0, proj_func=None, local_rank=0,
-                 use_tracker=False):
+                 use_tracker=False, tracker=None):
         super().__init__()
         self.cfg = cfg
-        self.proj_func = proj_func
+        # `proj_func` (pgdvs_renderer.py:78: the static renderer's Projector.compute_projections);
+        # default = the kernel restatement of it
+        self.proj_func = proj_func if proj_func is not None else ops.compute_projections
         self.softsplat_metric_abs_alpha = float(softsplat_metric_abs_alpha)
-        self.use_tracker = use_tracker
-        if use_tracker:
+        self.use_tracker = bool(use_tracker)
+        self.tracker = tracker
+        if self.use_tracker and tracker is None:
             raise NotImplementedError(
-                "tracker inference (TAPIR / CoTracker) is outside the hot-path scope; pass tracks to "
-                "pgdvs_b200.track.render_with_tracks instead")
+                "tracker inference (TAPIR / CoTracker) is outside the hot-path scope: construct "
+                "pgdvs_b200.track.PGDVSDynamicTrackRenderer(tracker=callable) with a callable that maps "
+                "prepare_data()'s frame window to (query_pts, tracks, visibles)")
+
+    def render_with_track(self, *args, **kwargs):  # pgdvs_renderer_dyn.py:272 (defined by the track subclass)
+        raise NotImplementedError("use pgdvs_b200.track.PGDVSDynamicTrackRenderer")
+
+    # ---- pgdvs_renderer_dyn.py:259-270
+    @staticmethod
+    def resize_rgb_mask(rgb, mask, render_h, render_w):
+        """Bicubic (align_corners, antialias) for the colours, nearest for the mask — the same two
+        torch.nn.functional.interpolate calls the reference makes (this is glue around the hot
+        path, only reached when the render size differs from the source size)."""
+        rgb = torch.nn.functional.interpolate(rgb, size=(render_h, render_w), mode="bicubic", align_corners=True,
+                                              antialias=True)
+        mask = torch.nn.functional.interpolate(mask, size=(render_h, render_w), mode="nearest")
+        return rgb, mask
+
+    def render_clouds_batched(self, clouds, flat_cams_tgt, H, W, render_cfg, dev):
+        """render_dyn_pcl (:671-724) for MANY (cloud, camera) pairs in one launch: every world
+        cloud is projected with its own target camera, the NDC clouds are packed pytorch3d-style
+        (first_idx / num_points) and splatted as one batch.  Empty clouds give zero image and mask
+        (:680-682).  -> (img [B,H,W,3], mask [B,H,W,1])."""
+        n_b = len(clouds)
+        fc = flat_cams_tgt.detach().cpu()
+        cams = [opencv_to_p3d_camera(fc[b, 2:18], fc[b, 18:34], H, W) for b in range(n_b)]
+        cam_dev = ops.camera_struct_tensor(np.stack([c[0] for c in cams]), np.stack([c[1] for c in cams]),
+                                           np.stack([c[2] for c in cams]), np.stack([c[3] for c in cams]), dev)
+        counts = [int(c[0].shape[0]) for c in clouds]
+        total = sum(counts)
+        if total == 0:
+            return torch.zeros((n_b, H, W, 3), device=dev), torch.zeros((n_b, H, W, 1), device=dev)
+        ndc = torch.empty((total, 3), dtype=torch.float32, device=dev)
+        first, o = [], 0
+        for b, (pcl, _) in enumerate(clouds):
+            first.append(o)
+            if counts[b]:
+                ndc[o:o + counts[b]] = ops.project_points(pcl, cam_dev[b])
+            o += counts[b]
+        rgb = torch.cat([c[1].reshape(-1, 3).to(torch.float32) for c in clouds], dim=0)
+        out = ops.render_packed(
+            ndc, rgb, torch.tensor(first, dtype=torch.int64, device=dev),
+            torch.tensor(counts, dtype=torch.int64, device=dev), (H, W),
+            float(_cfg(render_cfg, "dyn_render_pcl_pt_radius")), int(_cfg(render_cfg, "dyn_render_pcl_pts_per_pixel")),
+            compositor=_cfg(render_cfg, "dyn_render_compositor"), background=(0.0, 0.0, 0.0),
+            return_fragments=False, return_mask=True)
+        return out["image"], out["mask"]
 
     # ---- pgdvs_renderer_dyn.py:671-724
     def render_dyn_pcl(self, *, dyn_mask, dyn_pcl, rgbs, flat_cam, render_cfg, for_debug=False,
@@ -582,7 +639,7 @@ class PGDVSDynamicRenderer(torch.nn.Module):
             flow_1_to_tgt=flow_t.view(n_b, H, W, 2), flow_12=data["flow_fwd"],
             alpha=self.softsplat_metric_abs_alpha, noise=noise)
 
-    # ---- pgdvs_renderer_dyn.py:63-257 (pcl / softsplat branches, no tracker)
+    # ---- pgdvs_renderer_dyn.py:63-257 (pcl / softsplat / mesh dyn_render_type, optional track branch)
     def forward(self, data: Dict[str, torch.Tensor], ray_batch=None, render_cfg=None, for_debug=False,
                 disable_tqdm=False, static_rgb: Optional[torch.Tensor] = None,
                 softsplat_noise: Optional[torch.Tensor] = None):
@@ -612,26 +669,40 @@ class PGDVSDynamicRenderer(torch.nn.Module):
             cams.append((fc_tgt[b, 2:18], fc_tgt[b, 18:34]))
         radius = float(_cfg(render_cfg, "dyn_render_pcl_pt_radius"))
         K = int(_cfg(render_cfg, "dyn_render_pcl_pts_per_pixel"))
-        if bool(_cfg(render_cfg, "dyn_pcl_remove_outlier")):
+        remove_outlier = bool(_cfg(render_cfg, "dyn_pcl_remove_outlier"))
+        base_pcl_info = None
+        if remove_outlier or self.use_tracker:
+            # world-space clouds per view: the outlier statistic lives in world space (:401-457) and
+            # the track branch needs the base cloud and its threshold (:211-217)
             p3d = [opencv_to_p3d_camera(Kc, c2w, H, W) for (Kc, c2w) in cams]
             cloud = unproject_warp_project(pairs, p3d, H, W, dev, want_world=True, want_src_pix=True)
-            first = cloud["first_idx"].tolist()
+            first = cloud["first_idx"].tolist()  # (the reference syncs per view at :104 and :333)
             num = cloud["num_points"].tolist()
             knn = int(_cfg(render_cfg, "dyn_pcl_outlier_knn"))
-            keep_of_group = {}  # the filter lives in world space: views that share the source pair
-            for b in range(n_b):  # and the target time (e.g. the 12 cameras of a time step) share it
+            std_thres = float(_cfg(render_cfg, "dyn_pcl_outlier_std_thres"))
+            base_pcl_info = {"pcl": [], "pcl_rgbs": [], "pcl_nn_dist_thres": []}
+            of_group = {}  # views that share the source pair and the target time (e.g. the 12
+            for b in range(n_b):  # cameras of a time step) share the world cloud and its statistics
                 gk = pairs[b].group_key()
-                if gk in keep_of_group:
-                    pairs[b].keep = keep_of_group[gk]
-                    continue
-                keep = torch.zeros(H * W, dtype=torch.uint8, device=dev)
-                keep_of_group[gk] = keep
-                if num[b] > 0:
+                if gk not in of_group:
+                    keep = torch.zeros(H * W, dtype=torch.uint8, device=dev) if remove_outlier else None
                     pw = cloud["xyz_world"][first[b]:first[b] + num[b]]
-                    avg = ops.knn_mean_dist(pw, pw, knn + 1, skip_first=1)
-                    thres = torch.median(avg) + torch.std(avg) * float(_cfg(render_cfg, "dyn_pcl_outlier_std_thres"))
-                    keep[cloud["src_pix"][first[b]:first[b] + num[b]].long()] = (avg < thres).to(torch.uint8)
-                pairs[b].keep = keep
+                    pc = cloud["rgb"][first[b]:first[b] + num[b]]
+                    thres = None
+                    if num[b] > 0:
+                        avg = ops.knn_mean_dist(pw, pw, knn + 1, skip_first=1)
+                        thres = torch.median(avg) + torch.std(avg) * std_thres
+                        if remove_outlier:
+                            flag = avg < thres
+                            keep[cloud["src_pix"][first[b]:first[b] + num[b]].long()] = flag.to(torch.uint8)
+                            pw, pc = pw[flag], pc[flag]
+                    of_group[gk] = (keep, pw, pc, thres)
+                keep, pw, pc, thres = of_group[gk]
+                if remove_outlier:
+                    pairs[b].keep = keep
+                base_pcl_info["pcl"].append(pw)
+                base_pcl_info["pcl_rgbs"].append(pc)
+                base_pcl_info["pcl_nn_dist_thres"].append(thres)
         if render_type == "softsplat":
             dyn_rgb, dyn_mask = self._forward_softsplat(data, pairs, cams, H, W, dev, softsplat_noise)
         else:
@@ -639,10 +710,27 @@ class PGDVSDynamicRenderer(torch.nn.Module):
                                compositor=_cfg(render_cfg, "dyn_render_compositor"))
             dyn_rgb = out["image"].permute(0, 3, 1, 2).contiguous()
             dyn_mask = out["mask"].permute(0, 3, 1, 2).contiguous()
-        rgb_final, mask_final, combined = ops.merge_blend(dyn_rgb, dyn_mask, None, None, static_rgb)
+        # ---- track branch (:211-227) and the dyn/track merge (:229-235) [+ static blend]
+        track_rgb = track_mask = None
+        if self.use_tracker:
+            track_rgb, track_mask = self.render_with_track(data, render_cfg=render_cfg, base_pcl_info=base_pcl_info,
+                                                           for_debug=for_debug, disable_tqdm=disable_tqdm)
+        rgb_final, mask_final, combined = ops.merge_blend(dyn_rgb, dyn_mask, track_rgb, track_mask, static_rgb)
+        if track_rgb is None:
+            track_rgb, track_mask = torch.zeros_like(dyn_rgb), torch.zeros_like(dyn_mask)
+        # ---- optional resize to the render size (:237-248)
+        if ray_batch is not None:
+            render_h, render_w = int(ray_batch["render_h"]), int(ray_batch["render_w"])
+            if render_h != H or render_w != W:
+                dyn_rgb, dyn_mask = self.resize_rgb_mask(dyn_rgb, dyn_mask, render_h, render_w)
+                track_rgb, track_mask = self.resize_rgb_mask(track_rgb, track_mask, render_h, render_w)
+                rgb_final, mask_final = self.resize_rgb_mask(rgb_final, mask_final, render_h, render_w)
+                if combined is not None:
+                    raise ValueError("static_rgb blending is done at the source resolution: pass ray_batch=None "
+                                     "or blend after the resize")
         info = {
             "temporal_closest_rgb": dyn_rgb, "temporal_closest_mask": dyn_mask,
-            "temporal_track_rgb": torch.zeros_like(dyn_rgb), "temporal_track_mask": torch.zeros_like(dyn_mask),
+            "temporal_track_rgb": track_rgb, "temporal_track_mask": track_mask,
         }
         if combined is not None:
             info["combined_rgb"] = combined

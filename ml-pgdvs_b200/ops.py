@@ -89,7 +89,8 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
                   radius: Union[float, torch.Tensor], points_per_pixel: int,
                   compositor: Optional[str] = "norm", background: Optional[Sequence[float]] = None,
                   static_rgb: Optional[torch.Tensor] = None, return_fragments: bool = True,
-                  return_mask: bool = True, rr_weight: Optional[float] = None, raster_events=None):
+                  return_mask: bool = True, rr_weight: Optional[float] = None, raster_events=None,
+                  return_depth: bool = False, return_u8: bool = False):
     """Fused bin -> rasterize -> composite of a packed batch of NDC clouds.
 
     points_ndc [P,3] (NDC x, NDC y, view z), features [P,C] (C<=4) or None, first_idx /
@@ -151,15 +152,22 @@ def render_packed(points_ndc: torch.Tensor, features: Optional[torch.Tensor],
         LAUNCHES["count"] += 3 if P > 0 else 1  # k_count, k_scan, k_fill
     return rasterize_workspace(ws_ptr, nbytes.value, dev, N, P, H, W, K, radius_max, radius_t is not None,
                                C, mode, rr_weight, background, static_rgb, return_fragments, return_mask,
-                               raster_events)
+                               raster_events, return_depth=return_depth, return_u8=return_u8)
 
 
 def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int, W: int, K: int,
                         radius_max: float, per_point_radius: bool, C: int, mode: int, rr_weight,
                         background, static_rgb, return_fragments: bool, return_mask: bool,
-                        raster_events=None):
+                        raster_events=None, return_depth: bool = False, return_u8: bool = False,
+                        return_f32: bool = True):
     """Rasterize-and-composite over a workspace that pgdvs_bin_points / pgdvs_uwp_bin left in
-    the binned state (N, P, radius_max must repeat what the binning call was given)."""
+    the binned state (N, P, radius_max must repeat what the binning call was given).
+
+    return_depth: also `depth` [N,H,W,1], the compositor applied to the hits' view-space z (the
+    "composited depth"; `zbuf[..., 0]` of the fragments is the nearest-hit depth).
+    return_u8: also `image_u8` / `mask_u8`, quantised in the same pass exactly like the reference's
+    evaluator (engines/evaluator_pgdvs.py:51-77); with return_f32=False the fp32 image / mask are
+    not written at all."""
     L = _cabi.lib()
     stream = _stream_ptr(dev)
     with torch.cuda.device(dev):
@@ -169,10 +177,19 @@ def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int,
             idx = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
             zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
             dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        depth = image_u8 = mask_u8 = None
         if mode != _cabi.COMPOSITE_NONE:
-            image = torch.empty((N, H, W, C), dtype=torch.float32, device=dev)
-            if return_mask or static_rgb is not None:
-                mask = torch.empty((N, H, W, 1), dtype=torch.float32, device=dev)
+            if return_f32 or not return_u8:
+                image = torch.empty((N, H, W, C), dtype=torch.float32, device=dev)
+                if return_mask or static_rgb is not None:
+                    mask = torch.empty((N, H, W, 1), dtype=torch.float32, device=dev)
+            if return_depth:
+                depth = torch.empty((N, H, W, 1), dtype=torch.float32, device=dev)
+            if return_u8:
+                image_u8 = torch.empty((N, H, W, C), dtype=torch.uint8, device=dev)
+                mask_u8 = torch.empty((N, H, W, 1), dtype=torch.uint8, device=dev)
+        elif return_depth or return_u8:
+            raise ValueError("depth / 8-bit outputs are products of a compositor")
         bg = None
         if background is not None and mode != _cabi.COMPOSITE_NONE:
             vals = [float(b) for b in background][:C]
@@ -187,7 +204,13 @@ def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int,
                 raise ValueError("static_rgb must be [N,H,W,C]")
         if raster_events is not None:
             raster_events[0].record(torch.cuda.current_stream(dev))
-        _cabi.check(L.pgdvs_rasterize_composite(
+        extra = None
+        if depth is not None or image_u8 is not None:
+            extra = _cabi.PgdvsRasterExtra(
+                depth.data_ptr() if depth is not None else None,
+                image_u8.data_ptr() if image_u8 is not None else None,
+                mask_u8.data_ptr() if mask_u8 is not None else None)
+        _cabi.check(L.pgdvs_rasterize_composite_ex(
             ws_ptr, ws_bytes, N, P, H, W, K, radius_max, 1 if per_point_radius else 0, C, mode,
             float(rr_weight) if rr_weight is not None else 1.0, bg,
             st.data_ptr() if st is not None else None,
@@ -195,11 +218,16 @@ def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int,
             zbuf.data_ptr() if zbuf is not None else None,
             dists.data_ptr() if dists is not None else None,
             image.data_ptr() if image is not None else None,
-            mask.data_ptr() if mask is not None else None, stream), "pgdvs_rasterize_composite")
+            mask.data_ptr() if mask is not None else None,
+            ctypes.byref(extra) if extra is not None else None, stream), "pgdvs_rasterize_composite_ex")
         if raster_events is not None:
             raster_events[1].record(torch.cuda.current_stream(dev))
         LAUNCHES["count"] += 1
     out.update(idx=idx, zbuf=zbuf, dists=dists, image=image, mask=mask)
+    if depth is not None:
+        out["depth"] = depth
+    if image_u8 is not None:
+        out["image_u8"], out["mask_u8"] = image_u8, mask_u8
     return out
 
 
@@ -276,6 +304,33 @@ def project_points(xyz_world: torch.Tensor, camera_dev: torch.Tensor) -> torch.T
     return out
 
 
+def compute_projections(xyz: torch.Tensor, train_cameras: torch.Tensor):
+    """Projector.compute_projections (/root/reference/pgdvs/models/gnt/projector.py:41-73), usable as
+    the dynamic renderer's `proj_func`: xyz [R,S,3], train_cameras [n,34] ->
+    (pixel_locations [n,R,S,2], mask [n,R,S] bool).  The 4x4 products K @ inv(c2w) are host
+    plumbing (fp32, like the reference's torch.inverse + bmm); the per-point work is one kernel."""
+    _require_cuda(xyz, "xyz")
+    if xyz.ndim != 3:
+        raise AttributeError(xyz.shape)  # same refusal as the reference (:59)
+    dev = xyz.device
+    cams = train_cameras.detach().to(torch.float32).cpu()
+    n = cams.shape[0]
+    Kmat = cams[:, 2:18].reshape(-1, 4, 4)
+    poses = cams[:, -16:].reshape(-1, 4, 4)
+    proj = Kmat.bmm(torch.inverse(poses))[:, :3, :].contiguous().to(dev)  # [n,3,4]
+    shape = tuple(xyz.shape[:2])
+    pts = _f32c(xyz).reshape(-1, 3)
+    P = pts.shape[0]
+    uv = torch.empty((n, P, 2), dtype=torch.float32, device=dev)
+    mask = torch.empty((n, P), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().pgdvs_compute_projections(pts.data_ptr(), P, proj.data_ptr(), n, uv.data_ptr(),
+                                                          mask.data_ptr(), _stream_ptr(dev)),
+                    "pgdvs_compute_projections")
+    LAUNCHES["count"] += 1
+    return uv.reshape((n,) + shape + (2,)), mask.reshape((n,) + shape).bool()
+
+
 def knn_mean_dist(query: torch.Tensor, ref: torch.Tensor, K: int, skip_first: int = 0) -> torch.Tensor:
     """mean_k d2(query, kNN_k(ref)) over k in [skip_first, K) — knn_points + mean of the reference."""
     _require_cuda(query, "query")
@@ -345,7 +400,18 @@ def merge_blend(dyn_rgb, dyn_mask, track_rgb=None, track_mask=None, static_rgb=N
     _require_cuda(dyn_rgb, "dyn_rgb")
     dev = dyn_rgb.device
     dyn_rgb, dyn_mask = _f32c(dyn_rgb), _f32c(dyn_mask)
+    if dyn_rgb.ndim != 4 or dyn_rgb.shape[1] != 3:
+        raise ValueError(f"dyn_rgb must be channels-first [B,3,H,W]; got {tuple(dyn_rgb.shape)}")
     B, _, H, W = dyn_rgb.shape
+    if tuple(dyn_mask.shape) != (B, 1, H, W):
+        raise ValueError(f"dyn_mask must be [B,1,H,W] = {(B, 1, H, W)}; got {tuple(dyn_mask.shape)}")
+    if (track_rgb is None) != (track_mask is None):
+        raise ValueError("track_rgb and track_mask must be given together")
+    for name, t, shp in (("track_rgb", track_rgb, (B, 3, H, W)), ("track_mask", track_mask, (B, 1, H, W)),
+                         ("static_rgb", static_rgb, (B, 3, H, W))):
+        if t is not None and tuple(t.shape) != shp:
+            raise ValueError(f"{name} must be channels-first {shp}; got {tuple(t.shape)} "
+                             "(the batched API's [N,H,W,3] frames need .permute(0, 3, 1, 2))")
     tr = _f32c(track_rgb) if track_rgb is not None else None
     tm = _f32c(track_mask) if track_mask is not None else None
     st = _f32c(static_rgb) if static_rgb is not None else None

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _cabi, ops
-from .dyn_renderer import PGDVSDynamicRenderer, _cfg, _fill, _np44, _plane, _upload_structs
+from .dyn_renderer import PGDVSDynamicRenderer, _cfg, _fill, _np44, _plane, _upload_structs  # noqa: F401
 
 
 def _mask_of(indices: Sequence[int]) -> int:
@@ -79,13 +79,9 @@ def _stat_outlier_threshold(avg, std_thres):
     return torch.median(avg) + torch.std(avg) * std_thres
 
 
-def compute_pcl_for_tgt(*, tracks, visibles, rgbs, depths, flat_cams, times, time_tgt,
-                        idx_temporal_closest, idx_real_track, render_cfg, base_pcl_info):
-    """Full pgdvs_renderer_dyn_track.py:98-396: track cloud, track-to-base filter (:296-331),
-    statistical self filter (:333-380), concatenation with the base cloud (:390-394)."""
-    pcl, rgb = track_points(tracks=tracks, visibles=visibles, rgbs=rgbs, depths=depths, flat_cams=flat_cams,
-                            times=times, time_tgt=time_tgt, idx_temporal_closest=idx_temporal_closest,
-                            idx_real_track=idx_real_track)
+def track_knn_filters(pcl, rgb, base_pcl_info, render_cfg):
+    """pgdvs_renderer_dyn_track.py:286-396: track-to-base distance filter (:296-331), statistical
+    self filter (:333-380), concatenation with the base cloud (:390-394)."""
     knn = int(_cfg(render_cfg, "dyn_pcl_outlier_knn"))
     base_pcl = base_pcl_info.get("pcl")
     base_thres = base_pcl_info.get("pcl_nn_dist_thres")
@@ -107,6 +103,15 @@ def compute_pcl_for_tgt(*, tracks, visibles, rgbs, depths, flat_cams, times, tim
     return pcl, rgb
 
 
+def compute_pcl_for_tgt(*, tracks, visibles, rgbs, depths, flat_cams, times, time_tgt,
+                        idx_temporal_closest, idx_real_track, render_cfg, base_pcl_info):
+    """Full pgdvs_renderer_dyn_track.py:98-396: track cloud, then the KNN filters."""
+    pcl, rgb = track_points(tracks=tracks, visibles=visibles, rgbs=rgbs, depths=depths, flat_cams=flat_cams,
+                            times=times, time_tgt=time_tgt, idx_temporal_closest=idx_temporal_closest,
+                            idx_real_track=idx_real_track)
+    return track_knn_filters(pcl, rgb, base_pcl_info, render_cfg)
+
+
 def render_with_track(*, tracks, visibles, rgbs, depths, flat_cams, times, time_tgt, idx_temporal_closest,
                       idx_real_track, flat_cam_tgt, render_cfg, base_pcl_info, H: int, W: int):
     """Steps 2-3 of render_with_track (pgdvs_renderer_dyn_track.py:54-81) for one target view:
@@ -118,6 +123,127 @@ def render_with_track(*, tracks, visibles, rgbs, depths, flat_cams, times, time_
     r = PGDVSDynamicRenderer()
     return r.render_dyn_pcl(dyn_mask=torch.zeros(H, W, 1, device=tracks.device), dyn_pcl=pcl, rgbs=rgb,
                             flat_cam=flat_cam_tgt, render_cfg=render_cfg)
+
+
+def prepare_data(i_b, data, n_views, device=None):
+    """PGDVSDynamicTrackRenderer.prepare_data (pgdvs_renderer_dyn_track.py:599-764): the frame
+    window of batch item i_b in the order [fwd2tgt frames, temporally closest, bwd2tgt frames],
+    times shifted to start at 0, images repeated to the fixed tracker window of `n_views` frames.
+    Same keys as upstream.  (`n_actual_*` are read on the host, as upstream's slicing does.)"""
+    rgbs, masks, depths, cams, times = [], [], [], [], []
+    idx_real_track, idx_fwd, idx_bwd = [], [], []
+    n_frames = 0
+
+    def take(suffix, n):
+        rgbs.append(data["rgb_src_temporal" + suffix][i_b, :n])
+        masks.append(data["dyn_mask_src_temporal" + suffix][i_b, :n])
+        depths.append(data["depth_src_temporal" + suffix][i_b, :n])
+        cams.append(data["flat_cam_src_temporal" + suffix][i_b, :n])
+        times.append(data["time_src_temporal" + suffix][i_b, :n])
+
+    n_fwd = int(data["n_actual_temporal_track_fwd2tgt"][i_b, 0])
+    if n_fwd > 0:
+        take("_track_fwd2tgt", n_fwd)
+        idx_fwd = list(range(n_fwd))
+        idx_real_track.extend(idx_fwd)
+        n_frames += n_fwd
+    n_tmp = int(data["n_actual_temporal"][i_b, 0])
+    idx_closest = [n_frames + i for i in range(n_tmp)]
+    take("", n_tmp)
+    n_frames += n_tmp
+    n_bwd = int(data["n_actual_temporal_track_bwd2tgt"][i_b, 0])
+    if n_bwd > 0:
+        take("_track_bwd2tgt", n_bwd)
+        idx_bwd = [n_frames + i for i in range(n_bwd)]
+        idx_real_track.extend(idx_bwd)
+    idx_full = idx_closest + idx_real_track
+    assert len(idx_full) == len(set(idx_full)) and set(idx_full) == set(range(len(idx_full))), f"{idx_full}"
+    rgbs, masks, depths = torch.cat(rgbs, 0), torch.cat(masks, 0), torch.cat(depths, 0)
+    cams, times = torch.cat(cams, 0), torch.cat(times, 0)
+    min_time = torch.min(times)
+    times = times - min_time
+    n_actual = rgbs.shape[0]
+    n_rep = int(np.ceil(n_views / n_actual))
+    return {
+        "n_actual_frames": n_actual,
+        "rgbs_for_track": rgbs.repeat(n_rep, 1, 1, 1)[:n_views],
+        "dyn_masks_for_track": masks.repeat(n_rep, 1, 1, 1)[:n_views],
+        "depths_for_track": depths,
+        "flat_cams_for_track": cams,
+        "time_for_track": times,
+        "time_tgt": data["time_tgt"][i_b, :] - min_time,
+        "idx_temporal_closest": idx_closest,
+        "idx_real_track": idx_real_track,
+        "idx_real_track_fwd": idx_fwd,
+        "idx_real_track_bwd": idx_bwd,
+        "time_real_track": times[idx_real_track],
+    }
+
+
+class PGDVSDynamicTrackRenderer(PGDVSDynamicRenderer):
+    """Drop-in for pgdvs.renderers.pgdvs_renderer_dyn_track.PGDVSDynamicTrackRenderer
+    (`dyn_render_track_temporal == "no_tgt"`, pgdvs_renderer.py:66-80).
+
+    Tracker INFERENCE (TAPIR / CoTracker, `run_track` :398-558) is outside the hot-path scope
+    (SURVEY.md §8): the tracker is injected — `tracker(data_for_track) -> (query_pts [Q,3] (t,row,col),
+    tracks [Q,F,2] (col,row), visibles [Q,F] bool)` over the `n_actual_frames` frames of
+    `prepare_data`'s window; `synthetic.SyntheticTracker` is the stand-in used by tests and bench.
+    Everything downstream of the tracker runs here: frame selection, sampling, unprojection,
+    time interpolation (csrc/track.cu), the KNN filters and one BATCHED splat of all views' track
+    clouds (the reference renders them one by one)."""
+
+    def __init__(self, *, cfg=None, softsplat_metric_abs_alpha=100.0, proj_func=None, local_rank=0,
+                 use_tracker=True, tracker=None):
+        super().__init__(cfg=cfg, softsplat_metric_abs_alpha=softsplat_metric_abs_alpha, proj_func=proj_func,
+                         local_rank=local_rank, use_tracker=use_tracker, tracker=tracker)
+
+    prepare_data = staticmethod(prepare_data)
+
+    def run_track(self, data_for_track, for_debug=False, disable_tqdm=True):
+        if self.tracker is None:
+            raise NotImplementedError("no tracker was injected (tracker inference is outside the hot-path scope)")
+        return self.tracker(data_for_track)
+
+    def compute_pcl_for_tgt(self, *, data_for_track, query_pts, tracks, track_visibles, render_cfg,
+                            base_pcl_info, device=None, for_debug=False):
+        """pgdvs_renderer_dyn_track.py:98-396 with upstream's argument names."""
+        n = data_for_track["n_actual_frames"]
+        return compute_pcl_for_tgt(
+            tracks=tracks[:, :n], visibles=track_visibles[:, :n], rgbs=data_for_track["rgbs_for_track"][:n],
+            depths=data_for_track["depths_for_track"], flat_cams=data_for_track["flat_cams_for_track"],
+            times=data_for_track["time_for_track"], time_tgt=float(data_for_track["time_tgt"].reshape(-1)[0]),
+            idx_temporal_closest=data_for_track["idx_temporal_closest"],
+            idx_real_track=data_for_track["idx_real_track"], render_cfg=render_cfg, base_pcl_info=base_pcl_info)
+
+    def track_clouds(self, data, render_cfg, base_pcl_info, for_debug=False, disable_tqdm=True):
+        """Steps 1-2 of render_with_track (:41-66) for every batch item: per view the world-space
+        track cloud (+ base cloud) and its colours, or an empty cloud (:82-86)."""
+        dev = data["rgb_src_temporal_track_fwd2tgt"].device
+        n_b, n_one_side = data["rgb_src_temporal_track_fwd2tgt"].shape[:2]
+        n_views = n_one_side * 2 + 2  # the last 2: the two temporally closest source views (:36)
+        clouds = []
+        for i_b in range(n_b):
+            dft = self.prepare_data(i_b, data, n_views, dev)
+            dyn = dft["dyn_masks_for_track"][dft["idx_real_track"]]
+            if dyn.numel() > 0 and float(dyn.sum()) > 0:
+                query_pts, tracks, vis = self.run_track(dft, for_debug=for_debug, disable_tqdm=disable_tqdm)
+                cur = {"pcl": base_pcl_info["pcl"][i_b], "pcl_rgbs": base_pcl_info["pcl_rgbs"][i_b],
+                       "pcl_nn_dist_thres": base_pcl_info["pcl_nn_dist_thres"][i_b]}
+                clouds.append(self.compute_pcl_for_tgt(data_for_track=dft, query_pts=query_pts, tracks=tracks,
+                                                       track_visibles=vis, render_cfg=render_cfg, base_pcl_info=cur,
+                                                       device=dev, for_debug=for_debug))
+            else:
+                z = torch.zeros((0, 3), device=dev)
+                clouds.append((z, z))
+        return clouds
+
+    def render_with_track(self, data, render_cfg, base_pcl_info, for_debug=False, disable_tqdm=True):
+        """pgdvs_renderer_dyn_track.py:27-96 -> (track_rgbs [B,3,H,W], track_masks [B,1,H,W])."""
+        n_b, _, H, W, _ = data["rgb_src_temporal"].shape
+        dev = data["rgb_src_temporal"].device
+        clouds = self.track_clouds(data, render_cfg, base_pcl_info, for_debug, disable_tqdm)
+        img, mask = self.render_clouds_batched(clouds, data["flat_cam_tgt"], H, W, render_cfg, dev)
+        return img.permute(0, 3, 1, 2).contiguous(), mask.permute(0, 3, 1, 2).contiguous()
 
 
 class StaticGeoPointRenderer(torch.nn.Module):

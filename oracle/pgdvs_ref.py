@@ -11,6 +11,9 @@ rather than re-derived), the PGDVS functions on the hot path:
   camera conversion         /root/reference/pgdvs/utils/pytorch3d_utils.py:5-47
   compute_projections       /root/reference/pgdvs/models/gnt/projector.py:41-73
   track -> point cloud      /root/reference/pgdvs/renderers/pgdvs_renderer_dyn_track.py:98-284
+  track KNN filters         /root/reference/pgdvs/renderers/pgdvs_renderer_dyn_track.py:286-396
+  prepare_data              /root/reference/pgdvs/renderers/pgdvs_renderer_dyn_track.py:599-764
+  resize_rgb_mask           /root/reference/pgdvs/renderers/pgdvs_renderer_dyn.py:259-270
 
 and the pytorch3d 0.7.4 glue they call (PointsRasterizer.transform, PointsRenderer.forward,
 knn_points) from the published algorithm (parity unpinned for those; see raster_cpu.cpp).
@@ -276,6 +279,106 @@ def compute_pcl_for_tgt(*, tracks, visibles, rgbs, depths, flat_cams, times, tim
     ratio = (time_tgt - t_use[:, :1]) / (t_use[:, 1:2] - t_use[:, :1] + 1e-8)
     pcl = pts[:, 0, :] + (pts[:, 1, :] - pts[:, 0, :]) * ratio
     return pcl, rgb, torch.nonzero(flag_valid)[:, 0]
+
+
+def knn_mean_sq_dist(query, ref_pts, K, chunk=2048):
+    """pytorch3d.ops.knn_points(query, ref, K) -> mean over all K squared distances (brute force).
+    When the reference cloud has fewer than K points pytorch3d pads the missing columns with 0 and
+    torch.mean still divides by K."""
+    Q, R = query.shape[0], ref_pts.shape[0]
+    k = min(K, R)
+    out = torch.empty(Q)
+    for s in range(0, Q, chunk):
+        q = query[s:s + chunk]
+        d2 = ((q[:, None, :] - ref_pts[None, :, :]) ** 2).sum(-1)
+        nn = torch.topk(d2, k, dim=1, largest=False, sorted=True).values
+        out[s:s + chunk] = nn.sum(dim=1) / K
+    return out
+
+
+def track_knn_filters(pcl_track, pcl_track_rgbs, base_pcl_info, *, knn=50, std_thres=0.1, track2base_mult=50.0):
+    """pgdvs_renderer_dyn_track.py:286-396: drop track points far from the base cloud
+    (mean of the knn+1 squared distances to it < base_thres * mult), then the statistical self
+    filter (mean of the knn nearest OTHER points < base_thres, or median + std*thres when the base
+    threshold is None), then append the base cloud."""
+    base_pcl, base_thres = base_pcl_info.get("pcl"), base_pcl_info.get("pcl_nn_dist_thres")
+    if pcl_track.shape[0] > 0:
+        if base_pcl is not None and base_pcl.shape[0] > 0:
+            avg = knn_mean_sq_dist(pcl_track, base_pcl, knn + 1)
+            flag = avg < base_thres * track2base_mult
+            pcl_track, pcl_track_rgbs = pcl_track[flag], pcl_track_rgbs[flag]
+        if pcl_track.shape[0] > 0:
+            P = pcl_track.shape[0]
+            k = min(knn + 1, P)
+            d2 = ((pcl_track[:, None, :] - pcl_track[None, :, :]) ** 2).sum(-1)
+            nn = torch.topk(d2, k, dim=1, largest=False, sorted=True).values
+            avg = nn[:, 1:].sum(dim=1) / knn  # torch.mean over the knn columns (zero-padded if P <= knn)
+            thres = base_thres if base_thres is not None else torch.median(avg) + torch.std(avg) * std_thres
+            flag = avg < thres
+            pcl_track, pcl_track_rgbs = pcl_track[flag], pcl_track_rgbs[flag]
+        if base_pcl is not None and pcl_track.shape[0] > 0:
+            pcl_track = torch.cat((pcl_track, base_pcl), dim=0)
+            pcl_track_rgbs = torch.cat((pcl_track_rgbs, base_pcl_info["pcl_rgbs"]), dim=0)
+    return pcl_track, pcl_track_rgbs
+
+
+def prepare_data(i_b, data, n_views):
+    """PGDVSDynamicTrackRenderer.prepare_data (pgdvs_renderer_dyn_track.py:599-764): assemble the
+    frame window of batch item i_b in the order [fwd2tgt frames, temporally closest, bwd2tgt frames]."""
+    rgbs, masks, depths, cams, times = [], [], [], [], []
+    idx_real_track, idx_fwd, idx_bwd = [], [], []
+    n_frames = 0
+    n_fwd = int(data["n_actual_temporal_track_fwd2tgt"][i_b, 0])
+    if n_fwd > 0:
+        rgbs.append(data["rgb_src_temporal_track_fwd2tgt"][i_b, :n_fwd])
+        masks.append(data["dyn_mask_src_temporal_track_fwd2tgt"][i_b, :n_fwd])
+        depths.append(data["depth_src_temporal_track_fwd2tgt"][i_b, :n_fwd])
+        cams.append(data["flat_cam_src_temporal_track_fwd2tgt"][i_b, :n_fwd])
+        times.append(data["time_src_temporal_track_fwd2tgt"][i_b, :n_fwd])
+        idx_fwd = list(range(n_fwd))
+        idx_real_track.extend(idx_fwd)
+        n_frames += n_fwd
+    n_tmp = int(data["n_actual_temporal"][i_b, 0])
+    idx_closest = [n_frames + i for i in range(n_tmp)]
+    rgbs.append(data["rgb_src_temporal"][i_b, :n_tmp])
+    depths.append(data["depth_src_temporal"][i_b, :n_tmp])
+    cams.append(data["flat_cam_src_temporal"][i_b, :n_tmp])
+    masks.append(data["dyn_mask_src_temporal"][i_b, :n_tmp])
+    times.append(data["time_src_temporal"][i_b, :n_tmp])
+    n_frames += n_tmp
+    n_bwd = int(data["n_actual_temporal_track_bwd2tgt"][i_b, 0])
+    if n_bwd > 0:
+        rgbs.append(data["rgb_src_temporal_track_bwd2tgt"][i_b, :n_bwd])
+        masks.append(data["dyn_mask_src_temporal_track_bwd2tgt"][i_b, :n_bwd])
+        depths.append(data["depth_src_temporal_track_bwd2tgt"][i_b, :n_bwd])
+        cams.append(data["flat_cam_src_temporal_track_bwd2tgt"][i_b, :n_bwd])
+        times.append(data["time_src_temporal_track_bwd2tgt"][i_b, :n_bwd])
+        idx_bwd = [n_frames + i for i in range(n_bwd)]
+        idx_real_track.extend(idx_bwd)
+    rgbs, masks, depths = torch.cat(rgbs, 0), torch.cat(masks, 0), torch.cat(depths, 0)
+    cams, times = torch.cat(cams, 0), torch.cat(times, 0)
+    min_time = torch.min(times)
+    times = times - min_time
+    n_actual = rgbs.shape[0]
+    n_rep = int(np.ceil(n_views / n_actual))
+    return {
+        "n_actual_frames": n_actual,
+        "rgbs_for_track": rgbs.repeat(n_rep, 1, 1, 1)[:n_views],
+        "dyn_masks_for_track": masks.repeat(n_rep, 1, 1, 1)[:n_views],
+        "depths_for_track": depths, "flat_cams_for_track": cams, "time_for_track": times,
+        "time_tgt": data["time_tgt"][i_b, :] - min_time,
+        "idx_temporal_closest": idx_closest, "idx_real_track": idx_real_track,
+        "idx_real_track_fwd": idx_fwd, "idx_real_track_bwd": idx_bwd,
+        "time_real_track": times[idx_real_track],
+    }
+
+
+def resize_rgb_mask(rgb, mask, render_h, render_w):
+    """pgdvs_renderer_dyn.py:259-270."""
+    rgb = torch.nn.functional.interpolate(rgb, size=(render_h, render_w), mode="bicubic", align_corners=True,
+                                          antialias=True)
+    mask = torch.nn.functional.interpolate(mask, size=(render_h, render_w), mode="nearest")
+    return rgb, mask
 
 
 # ----------------------------------------------------------------------------- softmax splatting

@@ -263,8 +263,22 @@ def _tile_case(rng, H, W, P, z_mode, cluster=0.0):
     ("ties", 0.5, 5, 30000),     # both at once, K not a template size
     ("smooth", 0.0, 16, 30000),  # long lists inside the tile kernel (pair list)
     ("wide", 0.3, 32, 30000),
+    ("ties", 0.0, 2, 20000),     # K = 2 and K = 3 (KP = 2 / 4 of the pair kernel, K < KP)
+    ("smooth", 0.3, 3, 20000),
 ])
-def test_tile_kernel_paths_bit_exact(z_mode, cluster, K, P):
+@pytest.mark.parametrize("kernel", ["tile", "pair"])
+def test_tile_kernel_paths_bit_exact(z_mode, cluster, K, P, kernel):
+    """Both staged kernels (k_raster_tile: 32x8 tiles, one pixel per thread; k_raster_pair: 32x16
+    tiles, a vertical pixel pair per thread, K in {2, 4, 8}) on every special path."""
+    from pgdvs_b200 import _cabi
+    _cabi.debug_switch("no_pair", 1 if kernel == "tile" else 0)
+    try:
+        _tile_kernel_case(z_mode, cluster, K, P)
+    finally:
+        _cabi.debug_switch("no_pair", -1)
+
+
+def _tile_kernel_case(z_mode, cluster, K, P):
     rng = np.random.default_rng(sum(map(ord, z_mode)) * 1000 + K * 10 + int(cluster * 10))
     H, W, r = 96, 128, 0.029
     pts = _tile_case(rng, H, W, P, z_mode, cluster)
@@ -278,12 +292,21 @@ def test_tile_kernel_paths_bit_exact(z_mode, cluster, K, P):
 
 
 @pytest.mark.parametrize("sort,K,r", [("1", 8, 0.25), ("0", 8, 0.25), ("1", 3, 0.4), ("1", 40, 0.6)])
-def test_generic_kernel_with_z_sorted_cells(monkeypatch, sort, K, r):
+def test_generic_kernel_with_z_sorted_cells(sort, K, r):
     """The generic kernel forced onto clouds the tile kernel would take, with and without the
     in-place z-sort of the small cells (k_sort_cells): exact ties, -0.0 / huge z, cells larger
     than the sort cap, per-point radii and a fused compositor all match the oracle bit for bit."""
-    monkeypatch.setenv("PGDVS_RASTER_FORCE_GENERIC", "1")
-    monkeypatch.setenv("PGDVS_SORT_CELLS", sort)
+    from pgdvs_b200 import _cabi
+    _cabi.debug_switch("force_generic", 1)
+    _cabi.debug_switch("sort_cells", int(sort))
+    try:
+        _generic_kernel_case(K, r)
+    finally:
+        _cabi.debug_switch("force_generic", -1)
+        _cabi.debug_switch("sort_cells", -1)
+
+
+def _generic_kernel_case(K, r):
     rng = np.random.default_rng(41 + K)
     H, W, P = 18, 26, 6000  # ~13 points per pixel: cells of 2..30 records
     pts = _cloud(rng, H, W, P, zq=4)

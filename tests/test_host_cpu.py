@@ -89,7 +89,8 @@ def test_error_strings_and_host_side_validation(lib):
                                          None, None, None, None, None, None) == -2
     assert lib.pgdvs_rasterize_composite(dummy, 16, 1, 0, 8, 8, 4, 0.1, 0, 0, 0, 1.0, None, None, None,
                                          None, None, None, None, None) == -3
-    assert lib.pgdvs_knn_mean_dist(None, 5, None, 5, 65, 0, None, None, 0, None) == -2
+    assert lib.pgdvs_knn_mean_dist(None, 5, None, 5, 65, 0, None, None, 0, None) == -6  # PGDVS_E_KNN_K
+    assert b"64" in lib.pgdvs_error_string(-6)
     # more records than int32 float4 indices can address are refused up front
     assert lib.pgdvs_bin_workspace_bytes(1, 8, 8, 1 << 30, 0.1, ctypes.byref(n)) == -1
     assert lib.pgdvs_rasterize_composite(dummy, 1 << 40, 1, 1 << 30, 8, 8, 4, 0.1, 0, 0, 0, 1.0, None, None,
