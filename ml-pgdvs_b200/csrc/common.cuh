@@ -75,6 +75,8 @@ struct BinLayout {
   size_t off_zero_end;  // everything in [0, off_zero_end) is zeroed before each binning
   size_t off_cell_of; // int32  [P]          cell of every packed point (-1 = never rasterized);
                       //                     staged path only (the fused path carries it in its records)
+  size_t off_zmin;    // float [cells + pad] smallest z of every cell (NaN = empty), written by the
+                      //                     rasterizer's k_sort_cells pass when it z-sorts the cells
   size_t off_recA;    // 32-byte records [P], cell-sorted: part A (x_ndc, y_ndc, z, packed idx as
   size_t off_recB;    // int bits) and part B (features C<=4, or f0,f1,f2,radius) at rec_a(j) / rec_b(j)
   size_t total;
@@ -140,6 +142,8 @@ inline BinLayout make_bin_layout(int N, int H, int W, int64_t P, float radius_ma
   L.off_zero_end = o;
   L.off_cell_of = o;
   o = align256(o + sizeof(int32_t) * (size_t)(P > 0 ? P : 1));
+  L.off_zmin = o;
+  o = align256(o + sizeof(float) * (size_t)(L.n_tiles * kScanTile));
   // records of one point sit next to each other (one full 32 B sector per point): the fill
   // pass's scatter then never leaves half-written sectors behind
   L.off_recA = o;

@@ -58,9 +58,14 @@ struct RasterParams {
   int smem_records;  // capacity of the staging buffer of k_raster_tile, in records
   double density;    // host-side hint: mean points per pixel (sizes the staging buffer)
   int cells_sorted;  // 1: every cell of at most kSortCap records is in ascending z order (k_sort_cells)
+  const float* zmin; // [cells] smallest z of every cell, NaN = empty (valid when cells_sorted)
+  float inner2;      // (r_px - 0.75)^2: every record of a cell nearer than that (centre to centre, in
+                     // cells) is a hit; < 0: unknown (per-point radii) or too few such cells
+  float outer2;      // (r_px + 0.75)^2: no record of a cell farther than that can be a hit
   int force_generic; // developer switch (PGDVS_RASTER_FORCE_GENERIC): skip the staged kernels
   int no_pair;       // developer switch (PGDVS_RASTER_NO_PAIR): 1 = k_raster_tile instead of k_raster_pair,
                      // 0 = k_raster_pair whenever applicable, -1 = automatic (pair kernel for large launches)
+  int plain;         // 1: fragments + fp32 image + mask wanted, no depth / 8-bit outputs (unpredicated epilogue)
   const uint32_t* zrange;  // [2 N] per view: max(~bits(z)), max(bits(z)) over the filed points (common.cuh)
   float pair_bin_scale;    // k_raster_pair: work -> work-sort bin (64 bins span 2.5x the mean work)
 };
@@ -514,16 +519,23 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
 // (an empty slot reads slot 0, which the caller keeps FINITE — k_raster_pair zeroes it), everything
 // after them is selects.  Same operations in the same order as pixel_epilogue<KP, true, Records, true>, i.e.
 // the same bits.
-template <int KP, typename Records>
+// PLAIN: every regular output (fragments, fp32 image, mask) is wanted and none of the extras
+// (depth, 8-bit frames) — the benchmark configuration — so no store is predicated.  PRELOADED: the
+// caller fetched the static pixel long before (st_pre), otherwise it is read here.
+template <int KP, typename Records, bool PLAIN = false, bool PRELOADED = false>
 __device__ __forceinline__ void spec_epilogue(const RasterParams& p, const Slots<KP>& sl, const PixelCtx& c,
-                                              int n, int x, int y, const Records rec) {
+                                              int n, int x, int y, const Records rec,
+                                              const float* st_pre = nullptr) {
   static_assert(KP % 4 == 0, "128-bit fragment stores");
   const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-  const bool want_image = (p.image != nullptr) || (p.image_u8 != nullptr);
+  const bool want_image = PLAIN || (p.image != nullptr) || (p.image_u8 != nullptr);
   const bool blend = (p.static_rgb != nullptr) && want_image;
-  const bool want_depth = p.depth != nullptr;
+  const bool want_depth = !PLAIN && p.depth != nullptr;
   float st[3] = {0.f, 0.f, 0.f};
-  if (blend) {
+  if (PRELOADED) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) st[ch] = st_pre[ch];
+  } else if (blend) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) st[ch] = __ldg(p.static_rgb + pix * 3 + ch);
   }
@@ -549,16 +561,16 @@ __device__ __forceinline__ void spec_epilogue(const RasterParams& p, const Slots
       acc0 = __fadd_rn(acc0, __fmul_rn(w, b[kk].x));
       acc1 = __fadd_rn(acc1, __fmul_rn(w, b[kk].y));
       acc2 = __fadd_rn(acc2, __fmul_rn(w, b[kk].z));
-      zacc = __fadd_rn(zacc, __fmul_rn(w, a[kk].z));
+      if (!PLAIN) zacc = __fadd_rn(zacc, __fmul_rn(w, a[kk].z));
       wsum = __fadd_rn(wsum, w);
       oi[kk] = valid ? __float_as_int(a[kk].w) : -1;
       oz[kk] = valid ? a[kk].z : -1.0f;
       od[kk] = valid ? d : -1.0f;
     }
     const int64_t o = pix * KP + k0;
-    if (p.idx) *reinterpret_cast<int4*>(p.idx + o) = make_int4(oi[0], oi[1], oi[2], oi[3]);
-    if (p.zbuf) *reinterpret_cast<float4*>(p.zbuf + o) = make_float4(oz[0], oz[1], oz[2], oz[3]);
-    if (p.dists) *reinterpret_cast<float4*>(p.dists + o) = make_float4(od[0], od[1], od[2], od[3]);
+    if (PLAIN || p.idx) *reinterpret_cast<int4*>(p.idx + o) = make_int4(oi[0], oi[1], oi[2], oi[3]);
+    if (PLAIN || p.zbuf) *reinterpret_cast<float4*>(p.zbuf + o) = make_float4(oz[0], oz[1], oz[2], oz[3]);
+    if (PLAIN || p.dists) *reinterpret_cast<float4*>(p.dists + o) = make_float4(od[0], od[1], od[2], od[3]);
   }
   if (wsum < 0.25f && sl.s[0] >= 0) {
     // ill-conditioned normalisation (every hit sits near the rim of its splat): redo these few
@@ -583,16 +595,16 @@ __device__ __forceinline__ void spec_epilogue(const RasterParams& p, const Slots
   const float ones_acc = __fmul_rn(wsum, inv_t);
   const bool is_bg = sl.s[0] < 0;
   const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
-  if (p.mask) p.mask[pix] = m;
-  if (p.mask_u8) p.mask_u8[pix] = (uint8_t)(m * 255.0f);
+  if (PLAIN || p.mask) p.mask[pix] = m;
+  if (!PLAIN && p.mask_u8) p.mask_u8[pix] = (uint8_t)(m * 255.0f);
   if (want_depth) p.depth[pix] = is_bg ? 0.0f : zacc;
   if (want_image) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       float v = is_bg ? p.bg[ch] : out[ch];
       if (blend) v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st[ch]), __fmul_rn(m, v));
-      if (p.image) p.image[pix * 3 + ch] = v;
-      if (p.image_u8) {
+      if (PLAIN || p.image) p.image[pix * 3 + ch] = v;
+      if (!PLAIN && p.image_u8) {
         const float cl = (v != v) ? 0.0f : fminf(fmaxf(v, 0.0f), 1.0f);
         p.image_u8[pix * 3 + ch] = (uint8_t)(int)(cl * 255.0f);
       }
@@ -625,7 +637,118 @@ __device__ __noinline__ void finish_global(const RasterParams& p, const PixelCtx
 // ---------------------------------------------------------------------------------------
 // Generic kernel: any halo, optional per-point radii, candidates read through L1.
 // ---------------------------------------------------------------------------------------
+// Large windows (z-sorted cells, scalar radius, enough cells strictly inside the splat radius):
+// bound the depth of the K-th hit BEFORE any record is read, then open only the cells whose
+// nearest record can still matter.
+//   Pass 1.  A point filed under a cell lies within half a pixel of the cell's centre in x and y,
+//   so every record of a cell whose centre is nearer than r - 0.75 pixels is a hit (`inner2`, in
+//   squared cells; the margin covers the cell's corner and all rounding).  K non-empty such cells
+//   hold K hits, hence the K-th smallest of their z-mins (one float per cell, written by
+//   k_sort_cells; NaN = empty) is an upper bound `zbound` on the K-th hit's depth.  Same trip counts
+//   in every lane, coalesced independent loads, and the list's own registers hold the K smallest.
+//   Pass 2.  Every cell that can hold a hit at all (centre within r + 0.75 pixels) is probed through
+//   its z-min; only cells with z-min <= min(zbound, current K-th) are opened, and a z-sorted cell is
+//   left at the first record behind that limit.  On smooth surfaces a scan-order walk without the
+//   bound opens most cells (the depth keeps decreasing along the walk for half of the pixels); with
+//   it, about K of them.
 template <int KP, bool PPR>
+__device__ __forceinline__ void walk_bounded(const RasterParams& p, const PixelCtx& c, int n, int x, int y,
+                                             PairList<KP>& q) {
+  const int h = p.halo, GW = p.GW;
+  const int ci0 = (n * p.GH + y + h) * GW + x + h;  // the pixel's own cell (cells < 2^31)
+  const float* __restrict__ zmin = p.zmin;
+#pragma unroll 1
+  for (int dy = -h; dy <= h; ++dy) {
+    const float rem = p.inner2 - (float)(dy * dy);
+    if (rem < 0.0f) continue;
+    const int w = (int)sqrtf(rem);
+    const int base = ci0 + dy * GW;
+#pragma unroll 1
+    for (int dx = -w; dx <= w; ++dx) {
+      float zm = __ldg(zmin + base + dx);
+      if (zm < q.z[KP - 1]) {  // keep the KP smallest (depths only)
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+          const float t = q.z[i];
+          q.z[i] = fminf(t, zm);
+          zm = fmaxf(t, zm);
+        }
+      }
+    }
+  }
+  float zbound = q.z[KP - 1];
+  if (p.K < KP) {
+#pragma unroll
+    for (int i = 0; i < KP - 1; ++i)
+      if (i == p.K - 1) zbound = q.z[i];
+  }
+  q.init();
+  // pass 2a: which cells can still matter?  Uniform trip counts again (every lane probes the same
+  // window offsets, coalesced); a lane notes the offsets of its candidate cells in its column of a
+  // shared-memory queue.  The queue decouples the lanes: a loop nest that opened cells on the spot
+  // would serialise the lanes' openings (each a chain of dependent loads), and per-lane cursors
+  // that probe as they go leave most lanes idle while one skips ahead (measured: 7.6 of 32 lanes
+  // active per instruction).
+  constexpr int QCAP = (KP <= 8) ? 24 : 48;
+  __shared__ uint16_t s_queue[QCAP][256];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int* __restrict__ cell_end = p.cell_end;
+  const float4* __restrict__ recA = p.recA;
+  int cnt = 0;
+  int j = 0, e = 0;
+  bool sorted = false;
+  // (shared by the overflow path of 2a and by 2b) the records of the cell that is open
+  auto drain = [&]() {
+    for (; j < e; ++j) {
+      const float4 a = __ldg(recA + rec_a(j));
+      if (a.z <= fminf(zbound, q.z[KP - 1]))
+        q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
+      else if (sorted)
+        break;
+    }
+  };
+#pragma unroll 1
+  for (int dy = -h; dy <= h; ++dy) {
+    const int w = min(h, (int)sqrtf(fmaxf(p.outer2 - (float)(dy * dy), 0.0f)));
+    const int base = ci0 + dy * GW;
+#pragma unroll 2
+    for (int dx = -w; dx <= w; ++dx) {
+      if (__ldg(zmin + base + dx) <= zbound) {
+        if (cnt < QCAP) {
+          s_queue[cnt++][tid] = (uint16_t)(((dy + h) << 6) | (dx + h));
+        } else {  // queue full (rare): open the cell on the spot
+          j = __ldg(cell_end + base + dx - 1);
+          e = __ldg(cell_end + base + dx);
+          sorted = (e - j) <= kSortCap;
+          drain();
+        }
+      }
+    }
+  }
+  // pass 2b: every lane walks its own queue; a trip of the loop opens a cell or reads a record
+  int qi = 0;
+  j = e = 0;
+  for (;;) {
+    if (j >= e) {
+      if (qi >= cnt) break;
+      const int code = s_queue[qi++][tid];
+      const int cell = ci0 + ((code >> 6) - h) * GW + (code & 63) - h;
+      j = __ldg(cell_end + cell - 1);
+      e = __ldg(cell_end + cell);
+      sorted = (e - j) <= kSortCap;
+    }
+    if (j < e) {
+      const float4 a = __ldg(recA + rec_a(j));
+      const int slot = j++;
+      if (a.z <= fminf(zbound, q.z[KP - 1]))
+        q.push(hit_test<PPR>(c, a, recA, slot), a.z, slot);
+      else if (sorted)
+        j = e;
+    }
+  }
+}
+
+template <int KP, bool PPR, bool BOUND>
 __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(const __grid_constant__ RasterParams p) {
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = blockIdx.y * 8 + threadIdx.y;
@@ -642,7 +765,9 @@ __global__ void __launch_bounds__(256, PGDVS_RASTER_MINBLOCKS) k_raster_cells(co
   const int* __restrict__ cs = p.cell_end + ((int64_t)n * p.GH + y) * p.GW + x - 1;
   PairList<KP> q;
   q.init();
-  if (p.cells_sorted) {
+  if (BOUND) {
+    walk_bounded<KP, PPR>(p, c, n, x, y, q);
+  } else if (p.cells_sorted) {
     // z-sorted cells, one flattened loop: every lane keeps its own cursor (window row, cell,
     // record) and leaves a sorted cell at the first record behind its list's last element, so a
     // warp runs for as long as its busiest lane has records to look at — not for the longest
@@ -1299,6 +1424,22 @@ __device__ __forceinline__ void walk_pair_flat(const StagedRecords rec, const Ke
   }
 }
 
+// the pair kernel's epilogue for everything but the benchmark configuration: out of line, so the
+// hot kernel carries one inlined copy of spec_epilogue per pixel and nothing else
+template <int KP>
+__device__ __noinline__ void pair_epilogue_generic(const RasterParams& p, const Slots<KP> sl, const PixelCtx c,
+                                                   int n, int x, int y, uint32_t staged_base) {
+  const StagedAddr sa{staged_base};
+  if (p.K == KP) {
+    if (KP == 8 && p.compositor == PGDVS_COMPOSITE_NORM_WEIGHTED && p.C == 3)
+      spec_epilogue<8>(p, reinterpret_cast<const Slots<8>&>(sl), c, n, x, y, sa);
+    else
+      pixel_epilogue<KP, true>(p, sl, c, n, x, y, sa);
+  } else {
+    pixel_epilogue<KP, false>(p, sl, c, n, x, y, sa);
+  }
+}
+
 template <int KP>
 __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const __grid_constant__ RasterParams p) {
   static_assert(KP >= 2 && KP <= 8 && (KP % 2) == 0, "pair kernel: K-lists of 2, 4 or 8 keys");
@@ -1489,6 +1630,19 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
   // ---- ordinal -> float4 index of the record's A part; hand the winners to the pixel's own thread
   constexpr uint16_t kNone = 0u, kDone = 1u;  // indices 0 .. 2 * kPairNull - 1 are the zeroed null slots
   const bool fullk = (p.K == KP);
+  // the static frame's two pixels are only needed at the very end of the epilogue: fetch them
+  // now, under the decode below (walker-side epilogue of the benchmark configuration only)
+  float st_a[3] = {0.f, 0.f, 0.f}, st_b[3] = {0.f, 0.f, 0.f};
+#ifdef PGDVS_PAIR_WALKER_EPILOGUE
+  if (KP == 8 && p.plain && p.static_rgb != nullptr) {
+    const float* sp = p.static_rgb + (((int64_t)n * p.H + ya) * p.W + x) * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (in_a) st_a[ch] = __ldg(sp + ch);
+      if (in_b) st_b[ch] = __ldg(sp + (int64_t)p.W * 3 + ch);
+    }
+  }
+#endif
   {
 #ifdef PGDVS_PAIR_WALK_FLAT
     const int c0 = rl[0], c01 = c0 + rl[1], c012 = c01 + rl[2];
@@ -1534,30 +1688,31 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
       }
     }
 #ifdef PGDVS_PAIR_WALKER_EPILOGUE
-    // (experiment) no exchange, no fourth barrier: the walker finishes its own two pixels
+    // no exchange, no fourth barrier: the walker finishes its own two pixels.  The two copies are
+    // inlined (va / vb stay in registers); the benchmark configuration takes the unpredicated
+    // epilogue with the static pixel that was fetched before the decode, everything else goes
+    // out of line.
     {
-      const StagedAddr sa{staged_rec.base};
-      PixelCtx c;
-      c.xf = xf;
-      c.r2 = p.r2;
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        if (!(h ? in_b : in_a)) continue;
-        if ((h ? vb[0] : va[0]) == kDone) continue;
+      const bool spec = KP == 8 && fullk && p.plain && p.compositor == PGDVS_COMPOSITE_NORM_WEIGHTED && p.C == 3;
+      auto finish = [&](const uint32_t(&v)[KP], const bool in, const float yf, const int y, const float(&st)[3]) {
+        if (!in || v[0] == kDone) return;
         Slots<KP> sl;
 #pragma unroll
-        for (int i = 0; i < KP; ++i) {
-          const uint32_t v = h ? vb[i] : va[i];
-          sl.s[i] = (v == kNone) ? -1 : (int)v;
+        for (int i = 0; i < KP; ++i) sl.s[i] = (v[i] == kNone) ? -1 : (int)v[i];
+        PixelCtx c;
+        c.xf = xf;
+        c.yf = yf;
+        c.r2 = p.r2;
+        if constexpr (KP == 8) {
+          if (spec) {
+            spec_epilogue<8, StagedAddr, true, true>(p, sl, c, n, x, y, StagedAddr{staged_rec.base}, st);
+            return;
+          }
         }
-        c.yf = h ? yfb : yfa;
-        if (fullk && KP == 8 && p.compositor == PGDVS_COMPOSITE_NORM_WEIGHTED && p.C == 3)
-          spec_epilogue<8>(p, reinterpret_cast<const Slots<8>&>(sl), c, n, x, ya + h, sa);
-        else if (fullk)
-          pixel_epilogue<KP, true>(p, sl, c, n, x, ya + h, sa);
-        else
-          pixel_epilogue<KP, false>(p, sl, c, n, x, ya + h, sa);
-      }
+        pair_epilogue_generic<KP>(p, sl, c, n, x, y, staged_rec.base);
+      };
+      finish(va, in_a, yfa, ya, st_a);
+      finish(vb, in_b, yfb, ya + 1, st_b);
       return;
     }
 #endif
@@ -1645,14 +1800,23 @@ int debug_switch(int which) {
 }
 
 __global__ void __launch_bounds__(128) k_sort_cells(const int* __restrict__ cell_end, float4* rec,
-                                                    int64_t n_cells) {
+                                                    int64_t n_cells, float* __restrict__ zmin) {
   const int64_t cell = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (cell >= n_cells) return;
   const int s = __ldg(cell_end + cell - 1), e = __ldg(cell_end + cell);
   const int n = e - s;
-  if (n < 2 || n > kSortCap) return;
+  // z-min of the cell for the walk's skip test: NaN = empty (never opened); by z pattern, like
+  // the sort below (NaN patterns last: a cell of NaN depths alone is never opened either, which
+  // is what the walk's `z <= last` test does with such records anyway)
+  if (n < 2 || n > kSortCap) {
+    uint32_t m = 0x7FC00000u;  // quiet NaN
+    for (int i = 0; i < n; ++i) m = min(m, __float_as_uint(__fadd_rn(rec[rec_a(s + i)].z, 0.0f)));
+    zmin[cell] = __uint_as_float(m);
+    return;
+  }
   float4 a[kSortCap], b[kSortCap];
   uint32_t key[kSortCap];
+  uint32_t kmin = 0xFFFFFFFFu;
 #pragma unroll
   for (int i = 0; i < kSortCap; ++i) {
     key[i] = 0xFFFFFFFFu;
@@ -1660,8 +1824,10 @@ __global__ void __launch_bounds__(128) k_sort_cells(const int* __restrict__ cell
       a[i] = rec[rec_a(s + i)];
       b[i] = rec[rec_b(s + i)];
       key[i] = __float_as_uint(__fadd_rn(a[i].z, 0.0f));
+      kmin = min(kmin, key[i]);
     }
   }
+  zmin[cell] = __uint_as_float(min(kmin, 0x7FC00000u));
 #pragma unroll
   for (int i = 0; i < kSortCap; ++i) {
     if (i < n) {
@@ -1689,7 +1855,8 @@ int maybe_sort_cells(RasterParams& p, int KP, cudaStream_t stream) {
   if (!sort) return 0;
   const int64_t n_cells = (int64_t)p.N * p.GH * p.GW;
   const int64_t blocks = (n_cells + 127) / 128;
-  k_sort_cells<<<(unsigned)blocks, 128, 0, stream>>>(p.cell_end, const_cast<float4*>(p.recA), n_cells);
+  k_sort_cells<<<(unsigned)blocks, 128, 0, stream>>>(p.cell_end, const_cast<float4*>(p.recA), n_cells,
+                                                     const_cast<float*>(p.zmin));
   if (int rc = check_launch()) return rc;
   p.cells_sorted = 1;
   return 0;
@@ -1818,10 +1985,18 @@ int launch_raster(RasterParams& p, cudaStream_t stream) {
   if (!done) {
     // many more candidates per pixel than kept hits: z-sort the cells first (see kSortCap)
     if (int rc = maybe_sort_cells(p, KP, stream)) return rc;
-    if (p.r2 < 0.0f)
-      k_raster_cells<KP, true><<<grid, block, 0, stream>>>(p);
-    else
-      k_raster_cells<KP, false><<<grid, block, 0, stream>>>(p);
+    if (p.r2 < 0.0f) {
+      k_raster_cells<KP, true, false><<<grid, block, 0, stream>>>(p);
+    } else {
+      bool bounded = false;
+      if constexpr (KP <= 32) {
+        if (p.cells_sorted && p.inner2 >= 0.0f && p.halo <= 31) {  // (6-bit window offsets in the queue)
+          bounded = true;
+          k_raster_cells<KP, false, true><<<grid, block, 0, stream>>>(p);
+        }
+      }
+      if (!bounded) k_raster_cells<KP, false, false><<<grid, block, 0, stream>>>(p);
+    }
   }
   return check_launch();
 }
@@ -1931,6 +2106,20 @@ extern "C" int pgdvs_rasterize_composite_ex(void* workspace, size_t workspace_by
   p.mask_u8 = extra ? extra->mask_u8 : nullptr;
   p.smem_records = 0;
   p.cells_sorted = 0;
+  p.zmin = reinterpret_cast<const float*>(ws + L.off_zmin);
+  {
+    const float r_px = radius_max * 0.5f * (float)(H < W ? H : W);
+    const float r_in = (per_point_radius ? -1.0f : r_px) - 0.75f;
+    p.inner2 = (r_in > 0.0f) ? r_in * r_in : -1.0f;
+    p.outer2 = (r_px + 0.75f) * (r_px + 0.75f);
+    // the bound needs K non-empty inner cells: ask for half as many again
+    int inner_cells = 0;
+    if (p.inner2 >= 0.0f)
+      for (int dy = -L.halo; dy <= L.halo; ++dy)
+        for (int dx = -L.halo; dx <= L.halo; ++dx) inner_cells += ((float)(dx * dx + dy * dy) <= p.inner2) ? 1 : 0;
+    if (2 * inner_cells < 3 * K) p.inner2 = -1.0f;
+  }
+  p.plain = (idx && zbuf && dists && image && mask && !p.depth && !p.image_u8 && !p.mask_u8) ? 1 : 0;
   p.zrange = reinterpret_cast<const uint32_t*>(ws + L.off_zrange);
   p.pair_bin_scale = 1.0f;
   p.force_generic = (debug_switch(kSwForceGeneric) == 1) ? 1 : 0;
