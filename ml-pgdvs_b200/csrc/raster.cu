@@ -645,7 +645,7 @@ __device__ __noinline__ void finish_global(const RasterParams& p, const PixelCtx
 //   squared cells; the margin covers the cell's corner and all rounding).  K non-empty such cells
 //   hold K hits, hence the K-th smallest of their z-mins (one float per cell, written by
 //   k_sort_cells; NaN = empty) is an upper bound `zbound` on the K-th hit's depth.  Same trip counts
-//   in every lane, coalesced independent loads, and the list's own registers hold the K smallest.
+//   in every lane, coalesced independent loads.
 //   Pass 2.  Every cell that can hold a hit at all (centre within r + 0.75 pixels) is probed through
 //   its z-min; only cells with z-min <= min(zbound, current K-th) are opened, and a z-sorted cell is
 //   left at the first record behind that limit.  On smooth surfaces a scan-order walk without the
@@ -657,77 +657,88 @@ __device__ __forceinline__ void walk_bounded(const RasterParams& p, const PixelC
   const int h = p.halo, GW = p.GW;
   const int ci0 = (n * p.GH + y + h) * GW + x + h;  // the pixel's own cell (cells < 2^31)
   const float* __restrict__ zmin = p.zmin;
+  // pass 1: the KP smallest z-mins of the inner cells, kept sorted in registers (depths only).
+  // (A branch-free variant — KP interleaved groups, bound = largest group minimum — was measured:
+  // its bound is ~3x looser on multi-surface clouds, the queue below overflows, 12.7 vs 4.1 ms.)
+  float g[KP];
+#pragma unroll
+  for (int u = 0; u < KP; ++u) g[u] = kInf;
 #pragma unroll 1
   for (int dy = -h; dy <= h; ++dy) {
     const float rem = p.inner2 - (float)(dy * dy);
     if (rem < 0.0f) continue;
     const int w = (int)sqrtf(rem);
-    const int base = ci0 + dy * GW;
+    const float* __restrict__ zr = zmin + ci0 + dy * GW;
 #pragma unroll 1
     for (int dx = -w; dx <= w; ++dx) {
-      float zm = __ldg(zmin + base + dx);
-      if (zm < q.z[KP - 1]) {  // keep the KP smallest (depths only)
+      float zm = __ldg(zr + dx);
+      if (zm < g[KP - 1]) {
 #pragma unroll
         for (int i = 0; i < KP; ++i) {
-          const float t = q.z[i];
-          q.z[i] = fminf(t, zm);
+          const float t = g[i];
+          g[i] = fminf(t, zm);
           zm = fmaxf(t, zm);
         }
       }
     }
   }
-  float zbound = q.z[KP - 1];
+  float zbound = g[KP - 1];
   if (p.K < KP) {
 #pragma unroll
     for (int i = 0; i < KP - 1; ++i)
-      if (i == p.K - 1) zbound = q.z[i];
+      if (i == p.K - 1) zbound = g[i];
   }
-  q.init();
   // pass 2a: which cells can still matter?  Uniform trip counts again (every lane probes the same
-  // window offsets, coalesced); a lane notes the offsets of its candidate cells in its column of a
-  // shared-memory queue.  The queue decouples the lanes: a loop nest that opened cells on the spot
-  // would serialise the lanes' openings (each a chain of dependent loads), and per-lane cursors
-  // that probe as they go leave most lanes idle while one skips ahead (measured: 7.6 of 32 lanes
-  // active per instruction).
-  constexpr int QCAP = (KP <= 8) ? 24 : 48;
-  __shared__ uint16_t s_queue[QCAP][256];
+  // window offsets, coalesced, no branch); a lane notes the offsets of its candidate cells in its
+  // column of a shared-memory queue.  The queue decouples the lanes: a loop nest that opened
+  // cells on the spot would serialise the lanes' openings (each a chain of dependent loads), and
+  // per-lane cursors that probe as they go leave most lanes idle while one skips ahead (measured:
+  // 7.6 of 32 lanes active per instruction).
+  constexpr int QCAP = (KP <= 8) ? 32 : 64;
+  __shared__ uint16_t s_queue[QCAP + 1][256];  // (row QCAP: overflow writes land here)
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int* __restrict__ cell_end = p.cell_end;
   const float4* __restrict__ recA = p.recA;
   int cnt = 0;
-  int j = 0, e = 0;
-  bool sorted = false;
-  // (shared by the overflow path of 2a and by 2b) the records of the cell that is open
-  auto drain = [&]() {
-    for (; j < e; ++j) {
-      const float4 a = __ldg(recA + rec_a(j));
-      if (a.z <= fminf(zbound, q.z[KP - 1]))
-        q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
-      else if (sorted)
-        break;
-    }
-  };
 #pragma unroll 1
   for (int dy = -h; dy <= h; ++dy) {
     const int w = min(h, (int)sqrtf(fmaxf(p.outer2 - (float)(dy * dy), 0.0f)));
-    const int base = ci0 + dy * GW;
-#pragma unroll 2
+    const float* __restrict__ zr = zmin + ci0 + dy * GW;
+    const int code0 = ((dy + h) << 6) + h;
+#pragma unroll 4
     for (int dx = -w; dx <= w; ++dx) {
-      if (__ldg(zmin + base + dx) <= zbound) {
-        if (cnt < QCAP) {
-          s_queue[cnt++][tid] = (uint16_t)(((dy + h) << 6) | (dx + h));
-        } else {  // queue full (rare): open the cell on the spot
-          j = __ldg(cell_end + base + dx - 1);
-          e = __ldg(cell_end + base + dx);
-          sorted = (e - j) <= kSortCap;
-          drain();
-        }
-      }
+      const bool open = __ldg(zr + dx) <= zbound;
+      s_queue[min(cnt, QCAP)][tid] = (uint16_t)(code0 + dx);
+      cnt += open ? 1 : 0;
     }
   }
+  if (cnt > QCAP) {
+    // more candidate cells than the queue holds (rare: no useful bound, e.g. next to empty
+    // regions): the plain walk over the whole window, every cell opened in turn
+    const int span = 2 * h + 1;
+    const int* __restrict__ row = cell_end + ci0 - h * GW - h - 1;
+#pragma unroll 1
+    for (int ry = 0; ry < span; ++ry, row += GW) {
+      int j = __ldg(row);
+#pragma unroll 1
+      for (int cx = 1; cx <= span; ++cx) {
+        const int e = __ldg(row + cx);
+        const bool sorted = (e - j) <= kSortCap;
+        for (; j < e; ++j) {
+          const float4 a = __ldg(recA + rec_a(j));
+          if (a.z <= q.z[KP - 1])
+            q.push(hit_test<PPR>(c, a, recA, j), a.z, j);
+          else if (sorted)
+            break;
+        }
+        j = e;
+      }
+    }
+    return;
+  }
   // pass 2b: every lane walks its own queue; a trip of the loop opens a cell or reads a record
-  int qi = 0;
-  j = e = 0;
+  int qi = 0, j = 0, e = 0;
+  bool sorted = false;
   for (;;) {
     if (j >= e) {
       if (qi >= cnt) break;
