@@ -24,6 +24,7 @@ CONFIGS: Dict[str, dict] = {
     "c4_davis": dict(H=480, W=854, frames=80, S=2, K=8, radius=0.01, views=80),
     "c5_stress": dict(H=1080, W=1920, frames=9, S=8, K=8, radius=0.01, views=8),
     "tiny": dict(H=24, W=40, frames=3, S=2, K=4, radius=0.06, views=3),
+    "tiny_track": dict(H=32, W=48, frames=8, S=2, K=4, radius=0.05, views=4),
 }
 
 
@@ -202,3 +203,99 @@ def make_workload(name: str, device, n_views: Optional[int] = None, seed: int = 
         static = torch.rand((V, H, W, 3), generator=g, device=device)
     return Workload(name, H, W, K, radius, scene, view_pairs, view_cams, static,
                     meta=dict(S=S, frames=F, mask_mode=mask_mode, seed=seed, flow_mode=flow_mode))
+
+
+# ------------------------------------------------------------------ reference-shaped `data` dicts
+def _flat_cam(H, W, K44, c2w44) -> torch.Tensor:
+    """[h, w, K(4x4 row-major), c2w(4x4 row-major)] (datasets/nvidia_eval.py:827-832)."""
+    return torch.from_numpy(np.concatenate([np.array([H, W], np.float32), np.asarray(K44, np.float32).reshape(-1),
+                                            np.asarray(c2w44, np.float32).reshape(-1)]))
+
+
+def make_data_dict(name: str, device, n_views: Optional[int] = None, seed: int = 1234, n_track_one_side: int = 3,
+                   track_mask_mode: str = "ellipse", scene: Optional[Scene] = None) -> Dict[str, torch.Tensor]:
+    """The `data` dict PGDVSDynamic(Track)Renderer.forward consumes, with the reference's keys,
+    shapes and dtypes (datasets/nvidia_eval.py:545-604): per batch item the two temporally closest
+    source frames (+ forward / backward flow between them) and, for the track branch, up to
+    `n_track_one_side` older (`*_track_fwd2tgt`) and newer (`*_track_bwd2tgt`) frames in ascending
+    time, padded with the nearest closest frame (nvidia_eval.py:281-317).  The closest frames carry
+    the config's full dynamic mask (worst case P = H*W, like the batched workloads); the track
+    frames carry `track_mask_mode` (a centred ellipse, ~15 % of the pixels, by default) because
+    every dynamic pixel of a track frame becomes a query point (pgdvs_renderer_dyn_track.py:482-489)."""
+    cfg = dict(CONFIGS[name])
+    H, W, F = cfg["H"], cfg["W"], cfg["frames"]
+    B = n_views if n_views is not None else cfg["views"]
+    n = n_track_one_side
+    sc = scene if scene is not None else make_scene(H, W, F, device, seed=seed)
+    tmask = sc.mask if track_mask_mode == "full" else make_scene(H, W, 1, device, seed=seed, mask_mode=track_mask_mode).mask.expand(F, -1, -1, -1)
+    keys = ("rgb", "depth", "dyn_mask", "flat_cam", "time")
+    out = {f"{k}_src_temporal{s}": [] for k in keys for s in ("", "_track_fwd2tgt", "_track_bwd2tgt")}
+    extra = {k: [] for k in ("flow_fwd", "flow_bwd", "flow_fwd_occ_mask", "flow_bwd_occ_mask", "flat_cam_tgt", "time_tgt",
+                             "n_actual_temporal", "n_actual_temporal_track_fwd2tgt", "n_actual_temporal_track_bwd2tgt")}
+    fcs = [_flat_cam(H, W, sc.K, sc.c2w[f]) for f in range(F)]
+
+    def frames(ids, suffix, mask):
+        out["rgb_src_temporal" + suffix].append(torch.stack([sc.rgb[i] for i in ids]))
+        out["depth_src_temporal" + suffix].append(torch.stack([sc.depth[i] for i in ids]))
+        out["dyn_mask_src_temporal" + suffix].append(torch.stack([mask[i] for i in ids]))
+        out["flat_cam_src_temporal" + suffix].append(torch.stack([fcs[i] for i in ids]))
+        out["time_src_temporal" + suffix].append(torch.tensor([float(sc.times[i]) for i in ids]))
+
+    for v in range(B):
+        a = v % max(F - 1, 1)
+        b = a + 1
+        t_tgt = float(sc.times[a]) + 0.5
+        frames([a, b], "", sc.mask)
+        older = list(range(max(0, a - n), a))
+        newer = list(range(b + 1, min(F, b + 1 + n)))
+        frames(older + [a] * (n - len(older)), "_track_fwd2tgt", tmask)
+        frames(newer + [b] * (n - len(newer)), "_track_bwd2tgt", tmask)
+        extra["n_actual_temporal"].append(torch.tensor([2]))
+        extra["n_actual_temporal_track_fwd2tgt"].append(torch.tensor([len(older)]))
+        extra["n_actual_temporal_track_bwd2tgt"].append(torch.tensor([len(newer)]))
+        extra["flow_fwd"].append(sc.flow_next[a])
+        extra["flow_bwd"].append(sc.flow_prev[b])
+        extra["flow_fwd_occ_mask"].append(torch.zeros((H, W, 1), device=sc.rgb.device))
+        extra["flow_bwd_occ_mask"].append(torch.zeros((H, W, 1), device=sc.rgb.device))
+        Kt, c2wt = _target_cam(sc, t_tgt, v, max(B, 1))
+        extra["flat_cam_tgt"].append(_flat_cam(H, W, Kt, c2wt))
+        extra["time_tgt"].append(torch.tensor([t_tgt]))
+    data = {k: torch.stack(v).to(device) for k, v in {**out, **extra}.items()}
+    return data
+
+
+class SyntheticTracker:
+    """Stand-in for TAPIR / CoTracker inference (outside the hot-path scope): maps
+    prepare_data()'s frame window to (query_pts [Q,3] (t,row,col), tracks [Q,F,2] (col,row),
+    visibles [Q,F] bool) exactly as run_track_func does for its queries — every dynamic pixel of
+    every real-track frame is a query (pgdvs_renderer_dyn_track.py:482-489) — with
+    tracks = query position + a cumulative N(0, step_px) walk away from the query frame and
+    visibles ~ Bernoulli(p_visible) (always visible at the query frame), SURVEY.md §8(d)."""
+
+    def __init__(self, seed: int = 1234, step_px: float = 1.0, p_visible: float = 0.8):
+        self.seed, self.step_px, self.p_visible = seed, step_px, p_visible
+        self.calls = 0
+
+    def __call__(self, data_for_track):
+        masks = data_for_track["dyn_masks_for_track"]
+        dev = masks.device
+        n_f = int(data_for_track["n_actual_frames"])
+        H, W = masks.shape[1], masks.shape[2]
+        qs = []
+        for idx in data_for_track["idx_real_track"]:
+            rows, cols = torch.nonzero(masks[idx, ..., 0] > 0.0, as_tuple=True)
+            qs.append(torch.stack((torch.full_like(rows, idx), rows, cols), dim=1).float())
+        query = torch.cat(qs, dim=0) if qs else torch.zeros((0, 3), device=dev)
+        Q = query.shape[0]
+        g = torch.Generator(device=dev).manual_seed(self.seed + self.calls)
+        self.calls += 1
+        steps = self.step_px * torch.randn((Q, n_f, 2), generator=g, device=dev)
+        walk = torch.cumsum(steps, dim=1)
+        qf = query[:, 0].long()
+        walk = walk - walk[torch.arange(Q, device=dev), qf][:, None, :]  # zero displacement at the query frame
+        tracks = torch.stack((query[:, 2], query[:, 1]), dim=1)[:, None, :] + walk  # (col, row)
+        tracks[..., 0].clamp_(0, W - 1)
+        tracks[..., 1].clamp_(0, H - 1)
+        vis = torch.rand((Q, n_f), generator=g, device=dev) < self.p_visible
+        vis[torch.arange(Q, device=dev), qf] = True
+        return query, tracks, vis

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import pgdvs_ref as ref
+from _attrib import attribute_mismatches
 from oracle import raster as oracle
 
 pytestmark = pytest.mark.gpu
@@ -337,10 +338,13 @@ def test_forward_end_to_end_vs_oracle():
         time_2=torch.tensor(1.0), time_tgt=torch.tensor(0.25), use_flow_consistency=True)
     e_img, e_mask = ref.render_dyn_pcl(H=H, W=W, dyn_pcl=o["pcl"], rgbs=o["rgb"], flat_cam=data["flat_cam_tgt"][0],
                                        radius=0.05, points_per_pixel=4)
-    m_agree = (mask[0, 0].cpu() == e_mask[..., 0]).float().mean()
-    assert m_agree > 0.995
+    # the two sides project their own clouds (fused kernel vs torch CPU ops): a differing pixel must
+    # be a boundary flip or a z tie of the oracle's cloud, anything else fails
     diff = (rgb[0].cpu().permute(1, 2, 0) - e_img).abs().max(dim=-1).values
-    assert (diff < 1e-4).float().mean() > 0.99  # boundary flips allowed on <1% of pixels
+    bad = (diff > 1e-4) | (mask[0, 0].cpu() != e_mask[..., 0])
+    ndc = ref.world_to_ndc(o["pcl"], ref.camera_from_flat_cam(data["flat_cam_tgt"][0])).numpy()
+    attribute_mismatches(bad.numpy(), ndc, H, W, 0.05, 4)
+    assert bad.float().mean() < 0.01
     comb = info["combined_rgb"].cpu()
     e_comb = ref.blend_static_dynamic(static, rgb.cpu(), mask.cpu())
     assert torch.equal(comb, e_comb)
@@ -379,9 +383,11 @@ def test_compat_namespace_runs_the_reference_call_sequence(golden_dir):
     # --- checks ---
     e_img, e_mask = ref.render_dyn_pcl(H=h, W=w, dyn_pcl=dyn_pcl.cpu(), rgbs=rgbs.cpu(), flat_cam=flat_cam.cpu(),
                                        radius=radius, points_per_pixel=ppp)
-    assert (mesh_mask.cpu() == e_mask).float().mean() > 0.995
     diff = (mesh_img.cpu() - e_img).abs().max(dim=-1).values
-    assert (diff < 1e-4).float().mean() > 0.99
+    bad = (diff > 1e-4) | (mesh_mask.cpu() != e_mask)[..., 0]
+    ndc = ref.world_to_ndc(dyn_pcl.cpu(), ref.camera_from_flat_cam(flat_cam.cpu())).numpy()
+    attribute_mismatches(bad.numpy(), ndc, h, w, radius, ppp)  # boundary flip or z tie, else fail
+    assert bad.float().mean() < 0.01
     _, _, e_avg = ref.knn_outlier_flags(dyn_pcl.cpu(), knn=8)
     np.testing.assert_allclose(avg_nn_dist.cpu().numpy(), e_avg.numpy(), rtol=2e-5, atol=1e-7)
     assert nn_idxs.shape == (1, dyn_pcl.shape[0], 9) and nn_pts.shape == (1, dyn_pcl.shape[0], 9, 3)

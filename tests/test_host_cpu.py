@@ -239,3 +239,44 @@ def test_mesh_faces_match_oracle_construction():
     b = ref.mesh_faces_from_mask(rows, cols, H, W)
     assert a.dtype == torch.int32 and torch.equal(a.long(), b) and b.shape[0] > 10
     assert int((a == 0).sum()) == 0  # vertex 0 never appears in a face (upstream uses `> 0`)
+
+
+def test_prepare_data_and_resize_match_the_restatement():
+    """PGDVSDynamicTrackRenderer.prepare_data (pgdvs_renderer_dyn_track.py:599-764) and
+    resize_rgb_mask (pgdvs_renderer_dyn.py:259-270) are host glue: same keys, values and index
+    lists as the oracle restatement on a reference-shaped synthetic data dict (window truncated at
+    both ends of the video, padded frames ignored through n_actual_*)."""
+    import torch
+    from oracle import pgdvs_ref as ref
+    from pgdvs_b200 import synthetic, track
+    data = synthetic.make_data_dict("tiny_track", torch.device("cpu"), n_views=7, n_track_one_side=3)
+    n_views = 3 * 2 + 2
+    seen = set()
+    for b in range(7):
+        a, e = track.prepare_data(b, data, n_views), ref.prepare_data(b, data, n_views)
+        assert a.keys() == e.keys()
+        for k in a:
+            if torch.is_tensor(a[k]):
+                assert torch.equal(a[k], e[k]), k
+            else:
+                assert a[k] == e[k], k
+        assert a["rgbs_for_track"].shape[0] == n_views and a["depths_for_track"].shape[0] == a["n_actual_frames"]
+        assert float(a["time_for_track"].min()) == 0.0
+        seen.add((len(a["idx_real_track_fwd"]), len(a["idx_real_track_bwd"])))
+    assert (0, 3) in seen and (3, 3) in seen and (3, 0) in seen  # start, middle and end of the video
+    # the synthetic tracker keeps the reference's conventions: (t,row,col) queries on the real-track
+    # frames' dynamic pixels, (col,row) tracks that pass through the query, visible at the query frame
+    dft = track.prepare_data(3, data, n_views)
+    q, tr, vis = synthetic.SyntheticTracker(seed=1)(dft)
+    n = dft["n_actual_frames"]
+    assert tr.shape == (q.shape[0], n, 2) and vis.shape == (q.shape[0], n) and vis.dtype == torch.bool
+    assert set(q[:, 0].long().tolist()) == set(dft["idx_real_track"])
+    ar = torch.arange(q.shape[0])
+    assert torch.equal(tr[ar, q[:, 0].long()], torch.stack((q[:, 2], q[:, 1]), 1)) and bool(vis[ar, q[:, 0].long()].all())
+    # resize: the same two interpolate calls as upstream
+    g = torch.Generator().manual_seed(0)
+    rgb, mask = torch.rand(2, 3, 24, 40, generator=g), (torch.rand(2, 1, 24, 40, generator=g) > 0.5).float()
+    from pgdvs_b200.dyn_renderer import PGDVSDynamicRenderer
+    a_rgb, a_mask = PGDVSDynamicRenderer.resize_rgb_mask(rgb, mask, 36, 60)
+    e_rgb, e_mask = ref.resize_rgb_mask(rgb, mask, 36, 60)
+    assert torch.equal(a_rgb, e_rgb) and torch.equal(a_mask, e_mask) and a_rgb.shape == (2, 3, 36, 60)
