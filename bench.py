@@ -203,6 +203,191 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ our arm
+def _events(n):
+    import torch
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def _spread(ms_list):
+    s = sorted(ms_list)
+    return {"min": s[0], "median": s[len(s) // 2], "max": s[-1]}
+
+
+def time_batched(wl, dev, steps, warmup, flush, *, K=None, radius=None, fragments=True, views=None):
+    """Device-resident timing of the batched hot path on one workload: `steps` timed steps (L2 flushed
+    before each, inside the bracket), CUDA events around every step and around the rasterize call."""
+    import torch
+    from pgdvs_b200.dyn_renderer import prepare_views, render_prepared
+    K = K if K is not None else wl.K
+    radius = radius if radius is not None else wl.radius
+    views = list(views) if views is not None else list(range(wl.n_views))
+    pairs, cams = wl.jobs(views)
+    prep = prepare_views(pairs, cams, wl.H, wl.W, dev)
+    static = wl.static_rgb[views] if len(views) != wl.n_views else wl.static_rgb
+
+    def step(ev=None):
+        return render_prepared(prep, radius=radius, points_per_pixel=K, compositor="norm", static_rgb=static,
+                               raster_events=ev, return_fragments=fragments)
+    for _ in range(warmup):
+        out = step()
+    torch.cuda.synchronize()
+    total_points = int(out["cloud"]["total"].item())
+    rev, sev = _events(steps), _events(steps)
+    for i in range(steps):
+        sev[i][0].record()
+        flush.zero_()
+        out = step(rev[i])
+        sev[i][1].record()
+    torch.cuda.synchronize()
+    step_ms = [a.elapsed_time(b) for a, b in sev]
+    raster_ms = statistics.mean(a.elapsed_time(b) for a, b in rev)
+    del out
+    return {"step_ms": statistics.mean(step_ms), "spread": _spread(step_ms), "raster_ms": raster_ms,
+            "total_points": total_points, "n_views": len(views)}
+
+
+def matrix_entry(label, wl, t, K, radius, peak, fragments=True):
+    V, H, W = t["n_views"], wl.H, wl.W
+    b_rc = algorithmic_bytes_raster(V, t["total_points"], H, W, K if fragments else 0)
+    return {"config": label, "views_per_step": V, "image": [H, W], "points_per_view": t["total_points"] // max(V, 1),
+            "points_per_pixel": K, "radius": radius, "step_ms": t["step_ms"], "views_per_s": V / (t["step_ms"] / 1e3),
+            "mpoints_per_s": t["total_points"] / (t["step_ms"] / 1e3) / 1e6, "raster_ms": t["raster_ms"],
+            "frac": b_rc / (t["raster_ms"] / 1e3) / 1e9 / peak}
+
+
+def run_matrix(dev, flush, peak, args):
+    """The other BASELINE.json configs on one GPU (inputs resident in HBM, same timing rules as the
+    main workload): C1, C2 with the statistical outlier filter on (as in every published run of the
+    reference: scripts/benchmark.sh:81,100), C3 without and with the track branch, C4, C5 at
+    K in {8, 16, 32}."""
+    import torch
+    from types import SimpleNamespace
+    from pgdvs_b200 import synthetic, track
+    from pgdvs_b200.dyn_renderer import render_views_filtered
+    rows = []
+    ms = max(3, min(args.matrix_steps, args.steps))
+
+    def batched(label, name, **kw):
+        n_views = kw.pop("n_views", None)
+        wl = synthetic.make_workload(name, dev, n_views=n_views, K=kw.get("K"), radius=kw.get("radius"))
+        t = time_batched(wl, dev, ms, 2, flush)
+        rows.append(matrix_entry(label, wl, t, wl.K, wl.radius, peak))
+        del wl
+        torch.cuda.empty_cache()
+
+    batched("c1_nvidia_1view", "c1_nvidia_1view")
+    # C2 with dyn_pcl_remove_outlier: KNN (K = 50) statistics per source pair on the device, no host sync
+    wl = synthetic.make_workload("c2_nvidia_seq", dev)
+    pairs, cams = wl.jobs(range(wl.n_views))
+    cfg = SimpleNamespace(dyn_pcl_outlier_knn=50, dyn_pcl_outlier_std_thres=0.1)
+
+    def step_f():
+        return render_views_filtered(pairs, cams, wl.H, wl.W, radius=wl.radius, points_per_pixel=wl.K, compositor="norm",
+                                     static_rgb=wl.static_rgb, render_cfg=cfg, return_fragments=True)
+    for _ in range(2):
+        out = step_f()
+    torch.cuda.synchronize()
+    ev = _events(ms)
+    for a, b in ev:
+        a.record()
+        flush.zero_()
+        out = step_f()
+        b.record()
+    torch.cuda.synchronize()
+    t_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    kept = int(out["cloud"]["total"].item())
+    rows.append({"config": "c2_nvidia_seq+outlier_filter", "views_per_step": wl.n_views, "image": [wl.H, wl.W],
+                 "points_per_view": kept // wl.n_views, "points_per_pixel": wl.K, "radius": wl.radius, "step_ms": t_ms,
+                 "views_per_s": wl.n_views / (t_ms / 1e3), "mpoints_per_s": kept / (t_ms / 1e3) / 1e6,
+                 "note": "uniform-grid KNN (K=50) + median/std threshold per source pair, all on the device"})
+    del wl, pairs, cams, out
+    torch.cuda.empty_cache()
+    batched("c3_iphone", "c3_iphone")
+    # C3 through the L2 renderer with the track branch (1 closest pair + tracks over +-3 frames, F = 8)
+    data = synthetic.make_data_dict("c3_iphone", dev, n_views=16, n_track_one_side=3, closest_mask_mode="ellipse")
+    c3 = synthetic.CONFIGS["c3_iphone"]
+    rcfg = SimpleNamespace(dyn_render_type="pcl", dyn_render_pcl_pt_radius=c3["radius"], dyn_render_pcl_pts_per_pixel=c3["K"],
+                           dyn_render_use_flow_consistency=False, dyn_pcl_remove_outlier=False, dyn_pcl_outlier_knn=50,
+                           dyn_pcl_outlier_std_thres=0.1, dyn_pcl_track_track2base_thres_mult=50)
+    rend = track.PGDVSDynamicTrackRenderer(tracker=synthetic.SyntheticTracker(seed=1234))
+    for _ in range(2):
+        rgb, mask, info = rend(data, None, rcfg)
+    torch.cuda.synchronize()
+    ev = _events(ms)
+    for a, b in ev:
+        a.record()
+        flush.zero_()
+        rgb, mask, info = rend(data, None, rcfg)
+        b.record()
+    torch.cuda.synchronize()
+    t_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    rows.append({"config": "c3_iphone+tracks (L2 forward)", "views_per_step": 16, "image": [c3["H"], c3["W"]],
+                 "points_per_pixel": c3["K"], "radius": c3["radius"], "step_ms": t_ms, "views_per_s": 16 / (t_ms / 1e3),
+                 "track_pixels_per_view": float(((info["temporal_closest_mask"] == 0) & (info["temporal_track_mask"] > 0)).sum()) / 16,
+                 "note": "PGDVSDynamicTrackRenderer.forward, realistic masks (centred ellipse, 15 % of the pixels, in every "
+                         "frame): closest-pair cloud + KNN statistics, synthetic tracks "
+                         "(F = 8, visibles ~ Bernoulli(0.8)), track cloud + 2 KNN filters, batched splat, merge; "
+                         "includes the synthetic tracker and the reference's per-view host syncs"})
+    del data, rend, rgb, mask, info
+    torch.cuda.empty_cache()
+    batched("c4_davis", "c4_davis")
+    batched("c5_stress K=8 r=0.01", "c5_stress", K=8, radius=0.01, n_views=8)
+    batched("c5_stress K=16 r=0.005", "c5_stress", K=16, radius=0.005, n_views=8)
+    batched("c5_stress K=32 r=0.02", "c5_stress", K=32, radius=0.02, n_views=4)
+    return rows
+
+
+def run_strong(dev, rank, world, flush, args):
+    """Strong scaling: a FIXED job sharded over the ranks exactly as the reference shards target
+    views (DistributedSampler(shuffle=False): view v -> rank v mod world, trainer_pgdvs.py:290-306),
+    8-bit frames gathered on rank 0 — dist.shard_views / dist.gather_frames, the code the gloo tests
+    cover.  Time = barrier-to-barrier device time of the slowest rank, median of 3 repetitions."""
+    import torch
+    import torch.distributed as dist
+    from pgdvs_b200 import dist as pdist
+    from pgdvs_b200 import synthetic
+    from pgdvs_b200.dyn_renderer import prepare_views, render_prepared
+    out = {}
+    for label, name, kw in (("c4_davis_80_frames", "c4_davis", dict()),
+                            ("c5_stress_k8_8_views", "c5_stress", dict(K=8, radius=0.01, n_views=8))):
+        wl = synthetic.make_workload(name, dev, seed=1234, **kw)  # the same job on every rank
+        V = wl.n_views
+        mine = pdist.shard_views(V, rank, world, pad=True)
+        pairs, cams = wl.jobs(mine)
+        prep = prepare_views(pairs, cams, wl.H, wl.W, dev)
+        static = wl.static_rgb[mine]
+
+        def job():
+            o = render_prepared(prep, radius=wl.radius, points_per_pixel=wl.K, compositor="norm", static_rgb=static,
+                                return_fragments=True, return_u8=True)
+            if world > 1:
+                return pdist.gather_frames(o["image_u8"], V, dst=0)
+            return o["image_u8"]
+        job()
+        times = []
+        for _ in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            flush.zero_()
+            frames = job()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        t_ms = sorted(times)[1]
+        if rank == 0:
+            assert frames.shape[0] == V
+        out[label] = {"views": V, "ms": t_ms, "views_per_s": V / (t_ms / 1e3), "views_per_rank": len(mine)}
+        del wl, prep, pairs, cams, static, frames
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -218,8 +403,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     import pgdvs_b200
+    from pgdvs_b200 import dist as pdist
     from pgdvs_b200 import ops, synthetic
     from pgdvs_b200.dyn_renderer import prepare_views, render_prepared
+
+    # every rank on its own share of the host cores (its GPU's NUMA node when sysfs tells), before
+    # any pinned buffer is allocated
+    binding = ({"bound": False, "note": "--no-bind"} if not args.bind else
+               pdist.bind_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
 
     wl = synthetic.make_workload(args.workload, dev, n_views=args.views, seed=1234 + rank, flow_mode=args.flow,
                                  K=args.K, radius=args.radius)
@@ -227,31 +418,49 @@ def run_ours(args):
     pairs, cams = wl.jobs(range(V))
     prep = prepare_views(pairs, cams, H, W, dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    gather_list = None
-    gdtype = torch.float32 if args.gather == "f32" else torch.uint8
-    if world > 1 and rank == 0:
-        gather_list = [torch.empty((V, H, W, 3), dtype=gdtype, device=dev) for _ in range(world)]
-    frames_u8 = [torch.empty((V, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+
+    # N > 1: finished 8-bit frames (quantised in the rasterizer's epilogue, evaluator_pgdvs.py:51-77)
+    # go to rank 0 as copy-engine peer writes (dist.PeerFrameSink); --gather nccl / f32 selects the
+    # NCCL gather instead (also the fallback when CUDA IPC is unavailable)
+    sink, gather_mode = None, None
+    comm_stream, gather_list = None, None
+    if world > 1:
+        gather_mode = args.gather
+        if gather_mode == "peer":
+            ok = torch.ones(1, device=dev)
+            try:
+                sink = pdist.PeerFrameSink((V, H, W, 3), torch.uint8, dev, dst=0)
+            except Exception as e:  # noqa: BLE001
+                ok.zero_()
+                print(f"[bench] rank {rank}: peer sink unavailable ({e!r}), falling back to the NCCL gather", file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) == 0.0:
+                sink, gather_mode = None, "nccl"
+        if sink is None:
+            comm_stream = torch.cuda.Stream(device=dev)
+            gdtype = torch.float32 if gather_mode == "f32" else torch.uint8
+            if rank == 0:
+                gather_list = [torch.empty((V, H, W, 3), dtype=gdtype, device=dev) for _ in range(world)]
     state_g = {"i": 0}
 
     def step(ev=None):
         out = render_prepared(prep, radius=radius, points_per_pixel=K, compositor="norm",
-                              static_rgb=wl.static_rgb, raster_events=ev, return_fragments=args.fragments)
+                              static_rgb=wl.static_rgb, raster_events=ev, return_fragments=args.fragments,
+                              return_u8=(world > 1 and gather_mode != "f32"))
         if world > 1:
-            # finished frames are gathered on rank 0 over NCCL/NVLink on a side stream, overlapped
-            # with the next step; by default as the 8-bit frames the reference's evaluator / video
-            # writer consume (engines/evaluator_pgdvs.py:75-77), --gather f32 sends raw floats
-            payload = out["image"]
-            if args.gather == "u8":
-                payload = ops.quantize_u8(out["image"], out=frames_u8[state_g["i"] & 1])
-                state_g["i"] += 1
+            i = state_g["i"]
+            state_g["i"] += 1
             done = torch.cuda.Event()
             done.record()
-            comm_stream.wait_event(done)
-            with torch.cuda.stream(comm_stream):
-                payload.record_stream(comm_stream)
-                dist.gather(payload, gather_list, dst=0)
+            if sink is not None:
+                sink.push(out["image_u8"], i, after=done)
+                sink.commit()
+            else:
+                payload = out["image"] if gather_mode == "f32" else out["image_u8"]
+                comm_stream.wait_event(done)
+                with torch.cuda.stream(comm_stream):
+                    payload.record_stream(comm_stream)
+                    dist.gather(payload, gather_list, dst=0)
         return out
 
     def barrier():
@@ -269,21 +478,24 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    raster_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    raster_ev, step_ev = _events(args.steps), _events(args.steps)
     l0 = ops.LAUNCHES["count"]
     barrier()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
+        step_ev[i][0].record()
         flush.zero_()  # L2 flush between timed iterations (inside the bracket, i.e. counted)
         out = step(raster_ev[i])
+        step_ev[i][1].record()
     if world > 1:
-        torch.cuda.current_stream().wait_stream(comm_stream)
+        torch.cuda.current_stream().wait_stream(sink.stream if sink is not None else comm_stream)
     t_end.record()
     barrier()
     launches = ops.LAUNCHES["count"] - l0
     ms = t_start.elapsed_time(t_end)
     raster_ms = statistics.mean(a.elapsed_time(b) for a, b in raster_ev)
+    spread = _spread([a.elapsed_time(b) for a, b in step_ev])
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -291,6 +503,12 @@ def run_ours(args):
         ms = float(t.item())
     views_total = V * world
     value = views_total * args.steps / (ms / 1e3)
+    gather_check = None
+    if sink is not None and rank == 0:
+        # the last step's frames of every rank have landed (the barrier above): rank 0's own slot
+        # must equal what it rendered
+        last = state_g["i"] - 1
+        gather_check = bool(torch.equal(sink.frames(last)[0], out["image_u8"]))
 
     # -------------------------------------------------- timed region 2: end to end, host buffers
     sc = wl.scene
@@ -302,45 +520,45 @@ def run_ours(args):
     in_sets = [{k: getattr(w.scene, k) for k in host_in} for w in (wl, wl_b)]
     host_img = torch.empty((V, H, W, 3), dtype=torch.float32).pin_memory()
     host_mask = torch.empty((V, H, W, 1), dtype=torch.float32).pin_memory()
+    host_img8 = torch.empty((V, H, W, 3), dtype=torch.uint8).pin_memory()
+    host_mask8 = torch.empty((V, H, W, 1), dtype=torch.uint8).pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in host_in.values())
-    d2h = host_img.numel() * 4 + host_mask.numel() * 4
 
     # The step is pipelined over chunks of views on three streams: H2D of the inputs, the
     # kernels, and the D2H of each finished chunk (which overlaps the next chunk's kernels and,
-    # PCIe being full duplex, the next step's H2D).
+    # PCIe being full duplex, the next step's H2D).  Job descriptors are built once per (input
+    # set, chunk) — they only hold pointers into the device input buffers and source-camera
+    # constants; the target cameras, which change from step to step in a real run, are uploaded
+    # from pinned memory every step.
     n_chunks = 4 if (V % 48 == 0) else 1
     per = V // n_chunks
-    job_sets = [[w.jobs(range(c * per, (c + 1) * per)) for c in range(n_chunks)] for w in (wl, wl_b)]
+    preps = [[prepare_views(*w.jobs(range(c * per, (c + 1) * per)), H, W, dev) for c in range(n_chunks)] for w in (wl, wl_b)]
+    host_cams = [[p.cams_dev.cpu().pin_memory() for p in ps] for ps in preps]
+    cam_bytes = sum(t.numel() for t in host_cams[0])
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     state = {"inputs_free": [None, None], "step": 0}
-
-    host_img8 = torch.empty((V, H, W, 3), dtype=torch.uint8).pin_memory()
-    host_mask8 = torch.empty((V, H, W, 1), dtype=torch.uint8).pin_memory()
 
     def e2e_step(u8=False):
         cur = torch.cuda.current_stream(dev)
         b = state["step"] & 1
         state["step"] += 1
-        dev_in, chunk_jobs = in_sets[b], job_sets[b]
+        dev_in = in_sets[b]
         with torch.cuda.stream(s_in):
             if state["inputs_free"][b] is not None:
                 s_in.wait_event(state["inputs_free"][b])  # the kernels that read this set are done
             for k, t in host_in.items():
                 dev_in[k].copy_(t, non_blocking=True)
+            for c in range(n_chunks):
+                preps[b][c].cams_dev.copy_(host_cams[b][c], non_blocking=True)
             ev_in = s_in.record_event()
         cur.wait_event(ev_in)
-        extra_bytes = 0
         for c in range(n_chunks):
-            cp, cc = chunk_jobs[c]
-            p = prepare_views(cp, cc, H, W, dev)  # job/camera descriptors: host algebra + small H2D
-            extra_bytes += p.h2d_bytes
-            o = render_prepared(p, radius=radius, points_per_pixel=K, compositor="norm",
-                                static_rgb=wl.static_rgb[c * per:(c + 1) * per])
-            img, msk = o["image"], o["mask"]
-            dst_i, dst_m = host_img, host_mask
-            if u8:  # 8-bit frames as the reference's evaluator / video writer consume them
-                img, msk = ops.quantize_u8(img), ops.quantize_u8(msk)
-                dst_i, dst_m = host_img8, host_mask8
+            o = render_prepared(preps[b][c], radius=radius, points_per_pixel=K, compositor="norm",
+                                static_rgb=wl.static_rgb[c * per:(c + 1) * per], return_u8=u8, return_f32=not u8)
+            if u8:  # 8-bit frames as the reference's evaluator / video writer consume them, from the epilogue
+                img, msk, dst_i, dst_m = o["image_u8"], o["mask_u8"], host_img8, host_mask8
+            else:
+                img, msk, dst_i, dst_m = o["image"], o["mask"], host_img, host_mask
             ev = cur.record_event()
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev)
@@ -349,40 +567,32 @@ def run_ours(args):
                 img.record_stream(s_out)
                 msk.record_stream(s_out)
         state["inputs_free"][b] = cur.record_event()
-        return extra_bytes
 
-    e2e_steps = max(2, min(args.steps, 5))
-    extra = e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = views_total * e2e_steps / e2e_s
-    # secondary figure: the same loop delivering 8-bit frames + masks (4x fewer D2H bytes)
-    e2e_step(u8=True)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step(u8=True)
-    torch.cuda.synchronize()
-    e2e8_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([e2e8_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e8_s = float(t.item())
-    e2e8_value = views_total * e2e_steps / e2e8_s
+    def e2e_run(u8):
+        n = max(4, min(args.steps, 20))
+        e2e_step(u8)
+        e2e_step(u8)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(n):
+            e2e_step(u8)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - w0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return views_total * n / dt, n
+
+    e2e_value, e2e_steps = e2e_run(False)
+    e2e8_value, _ = e2e_run(True)
 
     # -------------------------------------------------- roofline of the dominant kernel
     peak, peak_src = measured_peak_hbm()
-    # B_rc of SURVEY.md 8(d) (+ the static frame read by the fused blend); without fragments the
-    # 12*K*H*W bytes of idx/zbuf/dists are neither written nor counted
-    b_rc = algorithmic_bytes_raster(V, total_points, H, W, K if args.fragments else 0) + 12 * V * H * W
+    # B_rc of SURVEY.md 8(d): read (x, y, z) + C features per point, write idx / zbuf / dists, image and
+    # mask per pixel (the 12 B / pixel the fused blend reads from the static frame are NOT counted);
+    # without fragments the 12*K*H*W bytes of idx/zbuf/dists are neither written nor counted
+    b_rc = algorithmic_bytes_raster(V, total_points, H, W, K if args.fragments else 0)
     achieved = b_rc / (raster_ms / 1e3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "raster_traffic.json"
@@ -400,7 +610,7 @@ def run_ours(args):
         fi = oc["first_idx"].cpu().numpy()
         npc = oc["num_points"].cpu().numpy()
         ndc = oc["cloud"]["xyz_ndc"][fi[0]:fi[0] + npc[0]].cpu().numpy()
-        n_threads = os.cpu_count() or 1
+        n_threads = len(os.sched_getaffinity(0)) or 1
         z, n1 = np.zeros(1, np.int64), np.full(1, ndc.shape[0], np.int64)
         tc = time.perf_counter()
         oracle.rasterize_points_rows(ndc, z, n1, (H, W), radius, K, H // 2, H // 2 + 2, n_threads=n_threads)
@@ -416,6 +626,13 @@ def run_ours(args):
             "sample": (f"oracle naive rasterizer (pytorch3d RasterizePointsNaiveCpu restatement, row-parallel on "
                        f"{n_threads} threads) on view 0's NDC cloud (P={ndc.shape[0]}), {rows} of {H} rows timed "
                        f"({t_band:.2f} s) and scaled by H/rows, x2 passes (rgb + mask)")}
+        del oc
+
+    # -------------------------------------------------- the other configs / the strong-scaling leg
+    del wl_b, preps, in_sets, host_img, host_mask, out
+    torch.cuda.empty_cache()
+    matrix = run_matrix(dev, flush, peak, args) if (world == 1 and rank == 0 and args.matrix) else None
+    strong = run_strong(dev, rank, world, flush, args) if args.strong else None
 
     if rank == 0:
         line = {
@@ -428,27 +645,39 @@ def run_ours(args):
                        "fragments_written": bool(args.fragments),
                        "synthetic_flow": ("9x9-box-smoothed N(0,3px) + 0.1px jitter (piecewise-smooth motion)"
                                           if args.flow == "smooth" else "i.i.d. N(0,3px) per pixel (incoherent stress case)"),
-                       "parallelism": (f"views sharded over {world} GPU(s); NCCL gather of {args.gather} frames to rank 0, "
-                                       "overlapped with the next step") if world > 1 else "1 GPU",
+                       "parallelism": (f"views sharded over {world} GPU(s), {V} per rank; 8-bit frames delivered to rank 0 "
+                                       + ("as copy-engine peer writes over NVLink (CUDA IPC buffer, no kernels)" if sink is not None
+                                          else f"with an NCCL gather ({gather_mode})") + ", overlapped with the next step")
+                       if world > 1 else "1 GPU",
                        "cache": f"L2 flushed with a {L2_FLUSH_BYTES >> 20} MiB memset before every step (inside the timed bracket); "
-                                f"per-step working set ~{(b_rc + 72 * total_points) / 1e9:.1f} GB >> 126 MB L2"},
+                                f"per-step working set ~{(b_rc + 72 * total_points) / 1e9:.1f} GB >> 126 MB L2",
+                       "host_binding": binding},
+            "ms_per_step_spread": spread,
             "mpoints_per_s": value * (total_points / V) / 1e6,
             "roofline": {"bound": "hbm", "kernel": "k_raster (rasterize-and-composite)", "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": b_rc, "avg_launch_ms": raster_ms},
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + extra),
-                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "note": ("host pinned inputs -> H2D -> prepare descriptors -> uwp/bin/raster -> D2H of fp32 "
-                             f"frames+masks, wall clock; {n_chunks} view chunks pipelined on 3 streams, device inputs double-buffered")},
-            "e2e_u8_frames": {"value": e2e8_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + extra),
-                              "d2h_bytes_per_step": int(host_img8.numel() + host_mask8.numel()),
-                              "note": "same loop, frames and masks quantised to 8 bit on the GPU "
-                                      "(evaluator_pgdvs.py:51-77) before the D2H copy"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + cam_bytes),
+                    "d2h_bytes_per_step": int(V * H * W * 16), "steps": e2e_steps,
+                    "note": ("host pinned inputs + target cameras -> H2D -> uwp/bin/raster -> D2H of fp32 frames+masks, wall "
+                             f"clock; {n_chunks} view chunks pipelined on 3 streams, device inputs double-buffered")},
+            "e2e_u8_frames": {"value": e2e8_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + cam_bytes),
+                              "d2h_bytes_per_step": int(V * H * W * 4),
+                              "note": "same loop, 8-bit frames and masks written by the rasterizer's epilogue "
+                                      "(evaluator_pgdvs.py:51-77) instead of fp32"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if gather_check is not None:
+            line["gather_check"] = gather_check
+        if matrix is not None:
+            line["matrix"] = matrix
+        if strong is not None:
+            line["strong_scaling"] = strong
         print(json.dumps(line))
+    if sink is not None:
+        sink.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -457,7 +686,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_nvidia_seq")
@@ -468,8 +697,15 @@ def main():
     ap.add_argument("--no-fragments", dest="fragments", action="store_false",
                     help="do not materialise idx/zbuf/dists (fused-only mode; B_rc drops the 12*K*H*W term)")
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
-    ap.add_argument("--gather", default="u8", choices=["u8", "f32"],
-                    help="N>1: gather 8-bit frames (what the reference writes / scores) or raw fp32 on rank 0")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "f32"],
+                    help="N>1: 8-bit frames to rank 0 as copy-engine peer writes (default), as an NCCL gather, "
+                         "or raw fp32 frames over NCCL")
+    ap.add_argument("--no-bind", dest="bind", action="store_false", help="do not pin the rank to its GPU's host cores")
+    ap.add_argument("--no-matrix", dest="matrix", action="store_false",
+                    help="skip the per-config matrix (C1, C2+outlier filter, C3, C3+tracks, C4, C5) at N=1")
+    ap.add_argument("--matrix-steps", type=int, default=5)
+    ap.add_argument("--no-strong", dest="strong", action="store_false",
+                    help="skip the strong-scaling leg (C4's 80 frames / C5's 8 views sharded over the ranks)")
     ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"],
                     help="synthetic optical flow: piecewise-smooth (default) or i.i.d. per pixel (stress)")
     args = ap.parse_args()

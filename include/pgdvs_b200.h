@@ -302,6 +302,22 @@ int pgdvs_knn_mean_dist(const float* query, int64_t Q, const float* ref, int64_t
 int pgdvs_knn_points(const float* query, int64_t Q, const float* ref, int64_t R, int K,
                      float* dists_out, int64_t* idx_out, void* stream);
 
+/* Batched statistical outlier filter without host syncs (pgdvs_renderer_dyn.py:401-457 for many
+ * source pairs at once).  pgdvs_uwp_world_by_pixel runs the unproject -> warp -> lerp part of
+ * pgdvs_unproject_warp_project and leaves the world point of every surviving source pixel at its
+ * own pixel slot: world f32 [n_jobs, H*W, 3], NaN where the pixel does not survive (workspace as
+ * pgdvs_uwp_workspace_bytes).  Each job's slice is then a fixed-size cloud for
+ * pgdvs_knn_mean_dist(query = ref = slice, K = knn + 1, skip_first = 1), which gives +inf for the
+ * NaN slots, and pgdvs_outlier_keep turns the statistics into the per-source-pixel verdict
+ * PgdvsUwpJob.keep consumes:  thres = median(avg) + std(avg) * std_thres over the finite entries
+ * (lower median and unbiased std, like torch.median / torch.std at :420-423), keep = avg < thres.
+ *  avg f32 [n_clouds, n_slots]; keep u8 [n_clouds, n_slots]; thres_out f32 [n_clouds] or NULL. */
+int pgdvs_uwp_world_by_pixel(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras, int n_views,
+                             int H, int W, float* world, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int pgdvs_outlier_keep(const float* avg, int n_clouds, int64_t n_slots, float std_thres, uint8_t* keep,
+                       float* thres_out, void* stream);
+
 /* --------------------------------------------------------------------------------------
  * 7. Softmax splatting ("next" row 3 of the scope table; the reference's default
  *    dyn_render_type).
@@ -344,6 +360,24 @@ int pgdvs_rasterize_mesh(const float* verts_ndc, int64_t V, const int32_t* faces
                          int W, int perspective_correct, const float* vert_rgb, int32_t* pix_to_face,
                          float* zbuf, float* bary, float* image, float* mask, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------
+ * 9. Multi-GPU frame sink (NCCL / NVLink is used only to gather rendered frames).
+ *    The gathering rank exports a device buffer over CUDA IPC; every other rank (one process per
+ *    GPU) maps it and delivers its frames with copy-engine writes over NVLink — no kernel on
+ *    either side.  The reference has no counterpart (ranks write PNGs, rank 0 globs them:
+ *    pgdvs/engines/visualizer_pgdvs.py:160-177).
+ *    pgdvs_ipc_alloc: cudaMalloc + export; handle_out = PGDVS_IPC_HANDLE_BYTES HOST bytes to ship
+ *    to the peers (any byte channel).  pgdvs_ipc_open maps a peer's buffer (peer access enabled
+ *    lazily), pgdvs_ipc_close unmaps it, pgdvs_ipc_free releases the owner's allocation.
+ *    pgdvs_copy_async: stream-ordered device-to-device copy (local or peer), done by a DMA engine.
+ * ------------------------------------------------------------------------------------ */
+#define PGDVS_IPC_HANDLE_BYTES 64
+int pgdvs_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out);
+int pgdvs_ipc_open(const unsigned char* handle, void** dev_ptr);
+int pgdvs_ipc_close(void* dev_ptr);
+int pgdvs_ipc_free(void* dev_ptr);
+int pgdvs_copy_async(void* dst, const void* src, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_DIR = PKG_DIR / "lib"
 LIB_PATH = LIB_DIR / "libpgdvs_b200.so"
 OBJ_DIR = LIB_DIR / "obj"
-SOURCES = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu", "knn_grid.cu", "track.cu", "softsplat.cu", "mesh.cu"]
+SOURCES = ["bin.cu", "raster.cu", "composite.cu", "uwp.cu", "knn.cu", "knn_grid.cu", "track.cu", "softsplat.cu", "mesh.cu", "ipc.cu", "outlier.cu"]
 # raster.cu is compiled seven times in parallel: part 0 = C entry point, parts 1..6 = one group of
 # points_per_pixel instantiations each (the file also builds as a single translation unit)
 PARTS = {"raster.cu": [("raster_p%d" % i, ["-DPGDVS_RASTER_PART=%d" % i]) for i in range(7)]}

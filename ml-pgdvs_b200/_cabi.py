@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / "lib" / "libpgdvs_b200.so"
 COMPOSITE_NONE, COMPOSITE_ALPHA, COMPOSITE_NORM_WEIGHTED, COMPOSITE_WEIGHTED_SUM = 0, 1, 2, 3
 MAX_POINTS_PER_PIXEL = 150
 MAX_FUSED_CHANNELS = 4
+IPC_HANDLE_BYTES = 64
 
 # every symbol include/pgdvs_b200.h declares (tests check the library exports each one)
 EXPORTED_SYMBOLS = (
@@ -25,6 +26,8 @@ EXPORTED_SYMBOLS = (
     "pgdvs_track_workspace_bytes", "pgdvs_track_points", "pgdvs_quantize_u8",
     "pgdvs_softsplat_forward", "pgdvs_softsplat_workspace_bytes", "pgdvs_softsplat_dyn",
     "pgdvs_mesh_workspace_bytes", "pgdvs_rasterize_mesh",
+    "pgdvs_uwp_world_by_pixel", "pgdvs_outlier_keep",
+    "pgdvs_ipc_alloc", "pgdvs_ipc_open", "pgdvs_ipc_close", "pgdvs_ipc_free", "pgdvs_copy_async",
 )
 
 
@@ -148,6 +151,21 @@ def lib():
                                        c_void_p]
     L.pgdvs_knn_points.restype = c_int
     L.pgdvs_knn_points.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]
+    L.pgdvs_uwp_world_by_pixel.restype = c_int
+    L.pgdvs_uwp_world_by_pixel.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                           c_size_t, c_void_p]
+    L.pgdvs_outlier_keep.restype = c_int
+    L.pgdvs_outlier_keep.argtypes = [c_void_p, c_int, c_int64, c_float, c_void_p, c_void_p, c_void_p]
+    L.pgdvs_ipc_alloc.restype = c_int
+    L.pgdvs_ipc_alloc.argtypes = [c_size_t, POINTER(c_void_p), c_void_p]
+    L.pgdvs_ipc_open.restype = c_int
+    L.pgdvs_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.pgdvs_ipc_close.restype = c_int
+    L.pgdvs_ipc_close.argtypes = [c_void_p]
+    L.pgdvs_ipc_free.restype = c_int
+    L.pgdvs_ipc_free.argtypes = [c_void_p]
+    L.pgdvs_copy_async.restype = c_int
+    L.pgdvs_copy_async.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
     if L.pgdvs_abi_version() != 1:
         raise ImportError("libpgdvs_b200.so ABI version mismatch; rebuild it")
     lay = (c_int32 * 4)()

@@ -47,6 +47,8 @@ struct UwpParams {
   float* rgb;        // [cap,3] or null
   float* xyz_world;  // [cap,3] or null
   int32_t* src_pix;  // [cap] or null
+  float* world_by_pixel;  // [n_jobs, H*W, 3] or null: the world point of every SURVIVING source pixel at
+                          // its own pixel slot (not compacted; the caller pre-fills the array)
   // fused binning (all null/0 in the plain mode)
   CellGrid g;
   int* cell_count;
@@ -329,6 +331,12 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
         p.xyz_world[out * 3 + 2] = wz[k];
       }
       if (p.src_pix) p.src_pix[out] = (int32_t)s.pix[k];
+      if (p.world_by_pixel) {
+        float* wp = p.world_by_pixel + ((int64_t)job_m * p.H * p.W + s.pix[k]) * 3;
+        wp[0] = wx[k];
+        wp[1] = wy[k];
+        wp[2] = wz[k];
+      }
     }
     if (FUSED) {
       // z range of this member's view: warp reduction -> shared-memory max; the CTA publishes its
@@ -493,6 +501,36 @@ extern "C" int pgdvs_unproject_warp_project(const PgdvsUwpJob* jobs, int n_jobs,
   return run_uwp(jobs, n_jobs, cameras, n_views, H, W, xyz_ndc, rgb, xyz_world, src_pix, first_idx,
                  num_points, total_points, static_cast<char*>(workspace), L, nullptr, nullptr, nullptr, nullptr,
                  nullptr, group_first, group_members, n_groups, (cudaStream_t)stream_);
+}
+
+extern "C" int pgdvs_uwp_world_by_pixel(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCamera* cameras,
+                                        int n_views, int H, int W, float* world, void* workspace,
+                                        size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_jobs < 0 || n_views <= 0 || H <= 0 || W <= 0 || !workspace) return PGDVS_E_BADARG;
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PGDVS_E_ALIGN;
+  UwpLayout L = make_uwp_layout(n_jobs, H, W);
+  if (workspace_bytes < L.total) return PGDVS_E_WORKSPACE;
+  if (n_jobs == 0) return PGDVS_OK;
+  if (!jobs || !cameras || !world) return PGDVS_E_BADARG;
+  char* ws = static_cast<char*>(workspace);
+  // every slot NaN (all-ones pattern) first: the kernel only writes the surviving pixels
+  cudaError_t e = cudaMemsetAsync(world, 0xFF, sizeof(float) * 3 * (size_t)n_jobs * H * W, stream);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(ws, 0, L.off_zero_end, stream);  // tile offsets unused (no compaction): all zero
+  if (e != cudaSuccess) return (int)e;
+  UwpParams p = {};
+  p.jobs = jobs;
+  p.cams = cameras;
+  p.n_jobs = n_jobs;
+  p.H = H;
+  p.W = W;
+  p.tiles_per_job = L.tiles_per_job;
+  p.n_tiles = L.n_tiles;
+  p.tile_off = reinterpret_cast<int*>(ws + L.off_tile_off);
+  p.world_by_pixel = world;
+  k_uwp<false><<<(unsigned)((int64_t)n_jobs * L.tiles_per_job), kUwpThreads, 0, stream>>>(p);
+  return check_launch();
 }
 
 extern "C" int pgdvs_uwp_bin_workspace_bytes(int n_jobs, int n_views, int H, int W, float radius,

@@ -402,6 +402,90 @@ def render_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int
                            return_cloud=return_cloud, return_depth=return_depth, return_u8=return_u8)
 
 
+class FilteredViews:
+    """The batched hot path WITH the statistical outlier filter of compute_dyn_pcl
+    (pgdvs_renderer_dyn.py:401-457; `dyn_pcl_remove_outlier`, on in every published run:
+    scripts/benchmark.sh:81,100) and zero host syncs.
+
+    Views that share the source pair and the target time (e.g. the 12 cameras of an NVIDIA time
+    step) share the world cloud, hence its KNN statistics: one representative job per group is
+    unprojected / warped to world points kept at their source-pixel slots (NaN = no point), the
+    uniform-grid KNN gives the mean squared distance to the K nearest neighbours per slot, one CTA
+    per cloud turns that into `keep = avg < median + std * thres`, and the main uwp kernel applies
+    the verdict through PgdvsUwpJob.keep.  Built once per batch (descriptors cached), `render()`
+    re-runs everything on the device."""
+
+    def __init__(self, pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, device, render_cfg=None):
+        self.H, self.W, self.device = H, W, torch.device(device)
+        self.knn = int(_cfg(render_cfg, "dyn_pcl_outlier_knn"))
+        self.std_thres = float(_cfg(render_cfg, "dyn_pcl_outlier_std_thres"))
+        if self.knn + 1 > 64:
+            raise ValueError("dyn_pcl_outlier_knn must be <= 63 (K-list of the KNN kernel)")
+        groups: Dict = {}
+        for i, p in enumerate(pairs):
+            groups.setdefault(p.group_key(), []).append(i)
+        reps = [idxs[0] for idxs in groups.values()]
+        self.n_groups = len(reps)
+        if len(tgt_cams):
+            Ks = np.stack([_np44(K) for (K, _) in tgt_cams])
+            c2ws = np.stack([_np44(c) for (_, c) in tgt_cams])
+        else:
+            Ks = c2ws = np.zeros((0, 4, 4), np.float32)
+        cams_p3d = opencv_to_p3d_cameras(Ks, c2ws, H, W)
+        # representative jobs (already sorted by view: `pairs` is) for the world clouds
+        self.rep_prep = PreparedViews([pairs[i] for i in reps], cams_p3d, H, W, device, group_jobs=False)
+        HW = H * W
+        self.world = torch.empty((max(self.n_groups, 1), HW, 3), dtype=torch.float32, device=device)
+        self.avg = torch.empty((max(self.n_groups, 1), HW), dtype=torch.float32, device=device)
+        self.keep = torch.empty((max(self.n_groups, 1), HW), dtype=torch.uint8, device=device)
+        self.thres = torch.empty((max(self.n_groups, 1),), dtype=torch.float32, device=device)
+        filtered = []
+        for g, idxs in enumerate(groups.values()):
+            for i in idxs:
+                q = SourcePair.__new__(SourcePair)
+                q.__dict__.update(pairs[i].__dict__)
+                q.keep = self.keep[g]
+                filtered.append((i, q))
+        filtered.sort(key=lambda t: t[0])
+        self.prep = PreparedViews([q for _, q in filtered], cams_p3d, H, W, device)
+
+    def filter(self):
+        """world clouds -> KNN statistics -> keep masks (all stream-ordered, nothing returns to the host)."""
+        if self.n_groups == 0:
+            return
+        dev, H, W = self.device, self.H, self.W
+        L = _cabi.lib()
+        nbytes = ctypes.c_size_t(0)
+        _cabi.check(L.pgdvs_uwp_workspace_bytes(self.rep_prep.n_jobs, H, W, ctypes.byref(nbytes)), "pgdvs_uwp_workspace_bytes")
+        ws = ops._WS.get(dev, nbytes.value, tag="uwp")
+        self.rep_prep.pack_frames()
+        with torch.cuda.device(dev):
+            _cabi.check(L.pgdvs_uwp_world_by_pixel(
+                self.rep_prep.jobs_dev.data_ptr(), self.rep_prep.n_jobs, self.rep_prep.cams_dev.data_ptr(),
+                self.rep_prep.n_views, H, W, self.world.data_ptr(), ops._aligned_ptr(ws), nbytes.value,
+                ops._stream_ptr(dev)), "pgdvs_uwp_world_by_pixel")
+            ops.LAUNCHES["count"] += 1
+            for g in range(self.n_groups):
+                ops.knn_mean_dist(self.world[g], self.world[g], self.knn + 1, skip_first=1, out=self.avg[g])
+            _cabi.check(L.pgdvs_outlier_keep(self.avg.data_ptr(), self.n_groups, H * W, self.std_thres,
+                                             self.keep.data_ptr(), self.thres.data_ptr(), ops._stream_ptr(dev)),
+                        "pgdvs_outlier_keep")
+            ops.LAUNCHES["count"] += 1
+
+    def render(self, **kw):
+        self.filter()
+        out = render_prepared(self.prep, **kw)
+        out["outlier_thres"] = self.thres[:self.n_groups]
+        return out
+
+
+def render_views_filtered(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int, *, radius: float,
+                          points_per_pixel: int, render_cfg=None, device=None, **kw):
+    """render_views with `dyn_pcl_remove_outlier` semantics, see FilteredViews."""
+    device = device if device is not None else pairs[0].depth_1.device
+    return FilteredViews(pairs, tgt_cams, H, W, device, render_cfg).render(radius=radius, points_per_pixel=points_per_pixel, **kw)
+
+
 # ----------------------------------------------------------------------------- L2 class
 class PGDVSDynamicRenderer(torch.nn.Module):
     """Drop-in for pgdvs.renderers.pgdvs_renderer_dyn.PGDVSDynamicRenderer (`dyn_render_type` pcl /
@@ -671,7 +755,7 @@ class PGDVSDynamicRenderer(torch.nn.Module):
         K = int(_cfg(render_cfg, "dyn_render_pcl_pts_per_pixel"))
         remove_outlier = bool(_cfg(render_cfg, "dyn_pcl_remove_outlier"))
         base_pcl_info = None
-        if remove_outlier or self.use_tracker:
+        if self.use_tracker or (remove_outlier and render_type == "softsplat"):
             # world-space clouds per view: the outlier statistic lives in world space (:401-457) and
             # the track branch needs the base cloud and its threshold (:211-217)
             p3d = [opencv_to_p3d_camera(Kc, c2w, H, W) for (Kc, c2w) in cams]
@@ -705,6 +789,13 @@ class PGDVSDynamicRenderer(torch.nn.Module):
                 base_pcl_info["pcl_nn_dist_thres"].append(thres)
         if render_type == "softsplat":
             dyn_rgb, dyn_mask = self._forward_softsplat(data, pairs, cams, H, W, dev, softsplat_noise)
+        elif remove_outlier and not self.use_tracker:
+            # the filter fused into the batched path: no host sync (the tracker branch above needs
+            # the compacted base clouds on the host side anyway)
+            out = render_views_filtered(pairs, cams, H, W, radius=radius, points_per_pixel=K, render_cfg=render_cfg,
+                                        compositor=_cfg(render_cfg, "dyn_render_compositor"))
+            dyn_rgb = out["image"].permute(0, 3, 1, 2).contiguous()
+            dyn_mask = out["mask"].permute(0, 3, 1, 2).contiguous()
         else:
             out = render_views(pairs, cams, H, W, radius=radius, points_per_pixel=K,
                                compositor=_cfg(render_cfg, "dyn_render_compositor"))

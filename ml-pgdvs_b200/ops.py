@@ -331,13 +331,19 @@ def compute_projections(xyz: torch.Tensor, train_cameras: torch.Tensor):
     return uv.reshape((n,) + shape + (2,)), mask.reshape((n,) + shape).bool()
 
 
-def knn_mean_dist(query: torch.Tensor, ref: torch.Tensor, K: int, skip_first: int = 0) -> torch.Tensor:
-    """mean_k d2(query, kNN_k(ref)) over k in [skip_first, K) — knn_points + mean of the reference."""
+def knn_mean_dist(query: torch.Tensor, ref: torch.Tensor, K: int, skip_first: int = 0,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """mean_k d2(query, kNN_k(ref)) over k in [skip_first, K) — knn_points + mean of the reference.
+    Points with NaN coordinates are nobody's neighbour and get +inf."""
     _require_cuda(query, "query")
     dev = query.device
+    same = query is ref or (query.data_ptr() == ref.data_ptr() and query.shape == ref.shape)
     q = _f32c(query).reshape(-1, 3)
-    r = _f32c(ref.to(dev)).reshape(-1, 3)
-    out = torch.empty((q.shape[0],), dtype=torch.float32, device=dev)
+    r = q if same else _f32c(ref.to(dev)).reshape(-1, 3)
+    if out is None:
+        out = torch.empty((q.shape[0],), dtype=torch.float32, device=dev)
+    elif out.shape != (q.shape[0],) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous f32 [Q] tensor")
     L = _cabi.lib()
     nbytes = ctypes.c_size_t(0)
     _cabi.check(L.pgdvs_knn_workspace_bytes(q.shape[0], r.shape[0], ctypes.byref(nbytes)), "pgdvs_knn_workspace_bytes")

@@ -213,7 +213,8 @@ def _flat_cam(H, W, K44, c2w44) -> torch.Tensor:
 
 
 def make_data_dict(name: str, device, n_views: Optional[int] = None, seed: int = 1234, n_track_one_side: int = 3,
-                   track_mask_mode: str = "ellipse", scene: Optional[Scene] = None) -> Dict[str, torch.Tensor]:
+                   track_mask_mode: str = "ellipse", scene: Optional[Scene] = None,
+                   closest_mask_mode: str = "full") -> Dict[str, torch.Tensor]:
     """The `data` dict PGDVSDynamic(Track)Renderer.forward consumes, with the reference's keys,
     shapes and dtypes (datasets/nvidia_eval.py:545-604): per batch item the two temporally closest
     source frames (+ forward / backward flow between them) and, for the track branch, up to
@@ -227,7 +228,9 @@ def make_data_dict(name: str, device, n_views: Optional[int] = None, seed: int =
     B = n_views if n_views is not None else cfg["views"]
     n = n_track_one_side
     sc = scene if scene is not None else make_scene(H, W, F, device, seed=seed)
-    tmask = sc.mask if track_mask_mode == "full" else make_scene(H, W, 1, device, seed=seed, mask_mode=track_mask_mode).mask.expand(F, -1, -1, -1)
+    def mask_of(mode):
+        return sc.mask if mode == "full" else make_scene(H, W, 1, device, seed=seed, mask_mode=mode).mask.expand(F, -1, -1, -1)
+    tmask, cmask = mask_of(track_mask_mode), mask_of(closest_mask_mode)
     keys = ("rgb", "depth", "dyn_mask", "flat_cam", "time")
     out = {f"{k}_src_temporal{s}": [] for k in keys for s in ("", "_track_fwd2tgt", "_track_bwd2tgt")}
     extra = {k: [] for k in ("flow_fwd", "flow_bwd", "flow_fwd_occ_mask", "flow_bwd_occ_mask", "flat_cam_tgt", "time_tgt",
@@ -245,7 +248,7 @@ def make_data_dict(name: str, device, n_views: Optional[int] = None, seed: int =
         a = v % max(F - 1, 1)
         b = a + 1
         t_tgt = float(sc.times[a]) + 0.5
-        frames([a, b], "", sc.mask)
+        frames([a, b], "", cmask)
         older = list(range(max(0, a - n), a))
         newer = list(range(b + 1, min(F, b + 1 + n)))
         frames(older + [a] * (n - len(older)), "_track_fwd2tgt", tmask)

@@ -594,3 +594,55 @@ def test_forward_outlier_filter_is_applied():
     assert 1 <= calls["n"] <= B
     # the filter removed the blob's points: the renders differ where they used to splat
     assert not torch.equal(rgb_on, rgb_off) and float(m_on.sum()) <= float(m_off.sum())
+
+
+def test_fused_outlier_filter_matches_oracle():
+    """render_views_filtered (statistical outlier filter fused into the batched path, no host sync:
+    world points by pixel slot -> grid KNN -> device-side median/std -> keep mask) against the
+    oracle's per-pair knn_outlier_flags (pgdvs_renderer_dyn.py:401-457): same thresholds (rtol 1e-4),
+    same survivors per view, and the render of the surviving cloud bit-exact in idx."""
+    from types import SimpleNamespace
+    from pgdvs_b200 import synthetic
+    from pgdvs_b200.dyn_renderer import render_views_filtered
+    d = _dev()
+    knn = 8
+    wl = synthetic.make_workload("tiny", d)
+    sc = wl.scene  # (CPU and CUDA generators differ: the oracle gets the GPU scene's tensors)
+    H, W, K, r = wl.H, wl.W, wl.K, wl.radius
+    pairs, cams = wl.jobs(range(wl.n_views))
+    cfg = SimpleNamespace(dyn_pcl_outlier_knn=knn, dyn_pcl_outlier_std_thres=0.1)
+    out = render_views_filtered(pairs, cams, H, W, radius=r, points_per_pixel=K, render_cfg=cfg, compositor="norm",
+                                return_fragments=True, return_cloud=True)
+    num = out["num_points"].cpu().numpy()
+    first = out["first_idx"].cpu().numpy()
+    thres_gpu = sorted(out["outlier_thres"].cpu().tolist())
+    thres_ref = {}
+    for v in range(wl.n_views):
+        pcl, rgb = [], []
+        for p in wl.view_pairs[v]:
+            a = p._src_frames
+            o = ref.compute_dyn_pcl(
+                dyn_mask_1=sc.mask[a[0]].cpu(), rgb_1=sc.rgb[a[0]].cpu(), depth_1=sc.depth[a[0]].cpu(),
+                flow_12=p.flow_12.reshape(H, W, 2).cpu(), flow_12_occ_mask=torch.zeros(H, W, 1), rgb_2=sc.rgb[a[1]].cpu(),
+                depth_2=sc.depth[a[1]].cpu(), K_1=T(sc.K), c2w_1=T(sc.c2w[a[0]]), K_2=T(sc.K), c2w_2=T(sc.c2w[a[1]]),
+                time_1=torch.tensor(sc.times[a[0]]), time_2=torch.tensor(sc.times[a[1]]), time_tgt=torch.tensor(p._t_tgt))
+            flags, th, _ = ref.knn_outlier_flags(o["pcl"], knn=knn)
+            thres_ref[(a, p._t_tgt)] = float(th)
+            pcl.append(o["pcl"][flags])
+            rgb.append(o["rgb"][flags])
+        pcl, rgb = torch.cat(pcl), torch.cat(rgb)
+        assert 0 < pcl.shape[0] == int(num[v]), (v, pcl.shape[0], int(num[v]))
+        Kc, c2w = wl.view_cams[v]
+        flat = torch.cat([torch.tensor([float(H), float(W)]), T(Kc).reshape(-1), T(c2w).reshape(-1)])
+        ndc = ref.world_to_ndc(pcl, ref.camera_from_flat_cam(flat)).numpy()
+        g_ndc = out["cloud"]["xyz_ndc"][first[v]:first[v] + num[v]].cpu().numpy()
+        np.testing.assert_allclose(g_ndc, ndc, rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(thres_gpu, sorted(thres_ref.values()), rtol=1e-4)
+    assert out["outlier_thres"].numel() == len(thres_ref) < len(pairs)  # views sharing a source pair share the statistics
+    # the splat of the filtered cloud equals the oracle's on the GPU's own NDC points
+    P = int(out["cloud"]["total"].item())
+    img, (idx, zbuf, dists) = oracle.render_points(out["cloud"]["xyz_ndc"][:P].cpu().numpy(), first, num,
+                                                   out["cloud"]["rgb"][:P].cpu().numpy(), (H, W), r, K, "norm",
+                                                   background=(0, 0, 0))
+    assert np.array_equal(out["idx"].cpu().numpy(), idx)
+    np.testing.assert_allclose(out["image"].cpu().numpy(), img, atol=1e-5, rtol=0)
