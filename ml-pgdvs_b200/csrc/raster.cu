@@ -65,7 +65,7 @@ struct RasterParams {
   int force_generic; // developer switch (PGDVS_RASTER_FORCE_GENERIC): skip the staged kernels
   int no_pair;       // developer switch (PGDVS_RASTER_NO_PAIR): 1 = k_raster_tile instead of k_raster_pair,
                      // 0 = k_raster_pair whenever applicable, -1 = automatic (pair kernel for large launches)
-  int plain;         // 1: fragments + fp32 image + mask wanted, no depth / 8-bit outputs (unpredicated epilogue)
+  int plain;         // 1: an image (fp32 and / or 8-bit) wanted, no composited depth
   const uint32_t* zrange;  // [2 N] per view: max(~bits(z)), max(bits(z)) over the filed points (common.cuh)
   float pair_bin_scale;    // k_raster_pair: work -> work-sort bin (64 bins span 2.5x the mean work)
 };
@@ -519,8 +519,8 @@ __device__ __forceinline__ void pixel_epilogue(const RasterParams& p, const Slot
 // (an empty slot reads slot 0, which the caller keeps FINITE — k_raster_pair zeroes it), everything
 // after them is selects.  Same operations in the same order as pixel_epilogue<KP, true, Records, true>, i.e.
 // the same bits.
-// PLAIN: every regular output (fragments, fp32 image, mask) is wanted and none of the extras
-// (depth, 8-bit frames) — the benchmark configuration — so no store is predicated.  PRELOADED: the
+// PLAIN: an image (fp32 and / or 8-bit) is wanted and no composited depth — the benchmark
+// configurations — so the K loop carries no depth sum; the output-pointer tests left are uniform.  PRELOADED: the
 // caller fetched the static pixel long before (st_pre), otherwise it is read here.
 template <int KP, typename Records, bool PLAIN = false, bool PRELOADED = false>
 __device__ __forceinline__ void spec_epilogue(const RasterParams& p, const Slots<KP>& sl, const PixelCtx& c,
@@ -568,9 +568,9 @@ __device__ __forceinline__ void spec_epilogue(const RasterParams& p, const Slots
       od[kk] = valid ? d : -1.0f;
     }
     const int64_t o = pix * KP + k0;
-    if (PLAIN || p.idx) *reinterpret_cast<int4*>(p.idx + o) = make_int4(oi[0], oi[1], oi[2], oi[3]);
-    if (PLAIN || p.zbuf) *reinterpret_cast<float4*>(p.zbuf + o) = make_float4(oz[0], oz[1], oz[2], oz[3]);
-    if (PLAIN || p.dists) *reinterpret_cast<float4*>(p.dists + o) = make_float4(od[0], od[1], od[2], od[3]);
+    if (p.idx) *reinterpret_cast<int4*>(p.idx + o) = make_int4(oi[0], oi[1], oi[2], oi[3]);
+    if (p.zbuf) *reinterpret_cast<float4*>(p.zbuf + o) = make_float4(oz[0], oz[1], oz[2], oz[3]);
+    if (p.dists) *reinterpret_cast<float4*>(p.dists + o) = make_float4(od[0], od[1], od[2], od[3]);
   }
   if (wsum < 0.25f && sl.s[0] >= 0) {
     // ill-conditioned normalisation (every hit sits near the rim of its splat): redo these few
@@ -595,16 +595,16 @@ __device__ __forceinline__ void spec_epilogue(const RasterParams& p, const Slots
   const float ones_acc = __fmul_rn(wsum, inv_t);
   const bool is_bg = sl.s[0] < 0;
   const float m = (ones_acc > 0.0f) ? 1.0f : 0.0f;
-  if (PLAIN || p.mask) p.mask[pix] = m;
-  if (!PLAIN && p.mask_u8) p.mask_u8[pix] = (uint8_t)(m * 255.0f);
+  if (p.mask) p.mask[pix] = m;
+  if (p.mask_u8) p.mask_u8[pix] = (uint8_t)(m * 255.0f);
   if (want_depth) p.depth[pix] = is_bg ? 0.0f : zacc;
   if (want_image) {
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       float v = is_bg ? p.bg[ch] : out[ch];
       if (blend) v = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, m), st[ch]), __fmul_rn(m, v));
-      if (PLAIN || p.image) p.image[pix * 3 + ch] = v;
-      if (!PLAIN && p.image_u8) {
+      if (p.image) p.image[pix * 3 + ch] = v;
+      if (p.image_u8) {
         const float cl = (v != v) ? 0.0f : fminf(fmaxf(v, 0.0f), 1.0f);
         p.image_u8[pix * 3 + ch] = (uint8_t)(int)(cl * 255.0f);
       }
@@ -2130,7 +2130,7 @@ extern "C" int pgdvs_rasterize_composite_ex(void* workspace, size_t workspace_by
         for (int dx = -L.halo; dx <= L.halo; ++dx) inner_cells += ((float)(dx * dx + dy * dy) <= p.inner2) ? 1 : 0;
     if (2 * inner_cells < 3 * K) p.inner2 = -1.0f;
   }
-  p.plain = (idx && zbuf && dists && image && mask && !p.depth && !p.image_u8 && !p.mask_u8) ? 1 : 0;
+  p.plain = ((image || p.image_u8) && !p.depth) ? 1 : 0;
   p.zrange = reinterpret_cast<const uint32_t*>(ws + L.off_zrange);
   p.pair_bin_scale = 1.0f;
   p.force_generic = (debug_switch(kSwForceGeneric) == 1) ? 1 : 0;

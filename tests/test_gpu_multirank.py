@@ -35,26 +35,44 @@ def _worker(rank, world, port, n_gpus, n_views, ok):
     nccl = n_gpus >= world
     dev = torch.device("cuda", rank if nccl else 0)
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl" if nccl else "gloo", rank=rank, world_size=world)
+    if nccl:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     from pgdvs_b200 import synthetic
     from pgdvs_b200.dist import gather_frames, shard_views
     wl = synthetic.make_workload("tiny_track", dev, n_views=n_views, seed=5)  # the same job on every rank
     mine = shard_views(n_views, rank, world, pad=True)
     out = _render(wl, mine, dev)
     got = {}
+
+    def local_idx(o):
+        # idx is an index into the packed cloud of the LAUNCH (pytorch3d semantics): make it relative
+        # to its own view's first point so that shards and the full batch can be compared
+        first = o["first_idx"].to(torch.int32)[:, None, None, None]
+        return torch.where(o["idx"] >= 0, o["idx"] - first, o["idx"])
+
+    out["idx"] = local_idx(out)
     for k in ("image", "image_u8", "mask", "idx", "zbuf", "dists"):
         t = out[k].contiguous()
         g = gather_frames(t if nccl else t.cpu(), n_views, dst=0)
         if rank == 0:
             got[k] = g.cpu()
+    failure = None
     if rank == 0:
-        full = _render(wl, range(n_views), dev)
-        for k, g in got.items():
-            assert g.shape[0] == n_views
-            assert torch.equal(g, full[k].cpu()), f"{k}: union of shards differs from the single-GPU render"
-        ok.value = 1
+        try:
+            full = _render(wl, range(n_views), dev)
+            full["idx"] = local_idx(full)
+            for k, g in got.items():
+                assert g.shape[0] == n_views
+                assert torch.equal(g, full[k].cpu()), f"{k}: union of shards differs from the single-GPU render"
+            ok.value = 1
+        except Exception as e:  # noqa: BLE001  (the other rank must not be left waiting at the barrier)
+            failure = e
     dist.barrier()
     dist.destroy_process_group()
+    if failure is not None:
+        raise failure
 
 
 @pytest.mark.parametrize("n_views", [6, 7])
@@ -67,6 +85,9 @@ def test_union_of_shards_equals_single_gpu_render(n_views):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(300)
-        assert p.exitcode == 0
+        p.join(120)
+    for p in procs:
+        if p.exitcode is None:
+            p.terminate()
+    assert [p.exitcode for p in procs] == [0, 0]
     assert ok.value == 1
