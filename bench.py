@@ -458,11 +458,14 @@ def run_ours(args):
             i = state_g["i"]
             state_g["i"] += 1
             if gather_mode != "f32":
+                if state_g.get(i & 1) is not None:  # the transfer that last read this buffer (step i - 2) is done
+                    torch.cuda.current_stream().wait_event(state_g[i & 1])
                 out["image_u8"] = ops.quantize_u8(out["image"], out=frames_u8[i & 1])
             done = torch.cuda.Event()
             done.record()
             if sink is not None:
                 sink.push(out["image_u8"], i, after=done)
+                state_g[i & 1] = sink.stream.record_event()
                 sink.commit()
             else:
                 payload = out["image"] if gather_mode == "f32" else out["image_u8"]
@@ -470,6 +473,7 @@ def run_ours(args):
                 with torch.cuda.stream(comm_stream):
                     payload.record_stream(comm_stream)
                     dist.gather(payload, gather_list, dst=0)
+                state_g[i & 1] = comm_stream.record_event()
         return out
 
     def barrier():
