@@ -115,3 +115,42 @@ def test_softsplat_metric_matches_reference(golden_dir):
     _, metric = ref.softsplat_img(rgb_src1=rgb1, flow_src1_to_tgt=torch.zeros_like(flow12), rgb_src2=rgb2,
                                   flow_src1_to_src2=flow12)
     assert np.array_equal(metric.numpy(), g["metric"])
+
+
+def test_pytorch3d_pin_hook():
+    """tools/pin_oracle_against_pytorch3d.py: without pytorch3d it reports "unpinned" (exit 3) and
+    its oracle leg runs on the very cases it would compare; if a fixture written by `--write` on a
+    machine WITH pytorch3d is present, the oracle must reproduce the real outputs bit for bit."""
+    import importlib.util
+    import sys
+    from pathlib import Path
+    GOLDEN = Path(__file__).resolve().parent / "golden"
+    root = GOLDEN.parent.parent
+    spec = importlib.util.spec_from_file_location("_pin", root / "tools" / "pin_oracle_against_pytorch3d.py")
+    pin = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pin)
+    cases = pin.synthetic_cases()
+    outs = [pin.run_oracle(c) for c in cases]
+    for c, o in zip(cases, outs):
+        N = c["first"].shape[0]
+        assert o["idx"].shape == (N, c["H"], c["W"], c["K"]) and o["img_norm"].shape == (N, 3, c["H"], c["W"])
+        assert (o["idx"][1] == -1).all()                     # the empty cloud of every batch
+        assert (o["idx"][0] >= 0).any() and (o["idx"][2] >= c["first"][2]).any()
+    assert len(pin.fixture_cases()) >= 1                      # the clouds the real reference hands to pytorch3d
+    try:
+        import pytorch3d  # noqa: F401
+        have = True
+    except Exception:
+        have = False
+    if not have:
+        argv, sys.argv = sys.argv, ["pin"]
+        try:
+            assert pin.main() == 3
+        finally:
+            sys.argv = argv
+    fx = GOLDEN / "pytorch3d_pin.npz"
+    if fx.exists():
+        g = np.load(fx)
+        for i, o in enumerate(outs):
+            for k, v in o.items():
+                assert np.array_equal(g[f"case{i}_{k}"], v), f"oracle differs from the recorded pytorch3d output: case {i} {k}"
