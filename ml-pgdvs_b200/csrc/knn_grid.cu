@@ -243,9 +243,12 @@ __global__ void __launch_bounds__(256) k_knn_fill(const float* __restrict__ ref,
   }
 }
 
-// SELF: queries are the reference points themselves, processed in cell order (coherent warps)
-template <bool SELF>
-__global__ void __launch_bounds__(128) k_knn_query(const float* __restrict__ query, int64_t Q,
+// SELF: queries are the reference points themselves, processed in cell order (coherent warps).
+// KT > 0: K is the compile-time constant KT (the list is exactly K registers, kept sorted with a
+// min/max chain, its last element is the K-th distance) — instantiated for the reference's default
+// dyn_pcl_outlier_knn = 50 (K = 51); KT = 0: any K <= 64 at run time.
+template <bool SELF, int KT>
+__global__ void __launch_bounds__(128, (KT > 0 && KT <= 52) ? 5 : 1) k_knn_query(const float* __restrict__ query, int64_t Q,
                                                    const KnnGrid* __restrict__ gp, const int* __restrict__ cell_end,
                                                    const float4* __restrict__ sorted, int64_t R_sorted_hint,
                                                    int K, int skip, float* __restrict__ mean_out) {
@@ -269,9 +272,10 @@ __global__ void __launch_bounds__(128) k_knn_query(const float* __restrict__ que
     qz = __ldg(query + qi * 3 + 2);
   }
   (void)R_sorted_hint;
-  float best[kGridMaxK];
+  constexpr int NB = (KT > 0) ? KT : kGridMaxK;
+  float best[NB];
 #pragma unroll
-  for (int i = 0; i < kGridMaxK; ++i) best[i] = kInfF();
+  for (int i = 0; i < NB; ++i) best[i] = kInfF();
   float kth = kInfF();
   const int3 c = grid_coord(g, qx, qy, qz);
   const int rmax = max(g.n[0], max(g.n[1], g.n[2]));
@@ -302,20 +306,30 @@ __global__ void __launch_bounds__(128) k_knn_query(const float* __restrict__ que
             const float d = dx * dx + dy * dy + dz * dz;
             if (d < kth) {
               float cd = d;
+              if (KT > 0) {
 #pragma unroll
-              for (int t = 0; t < kGridMaxK; ++t) {
-                if (t < K) {
+                for (int t = 0; t < NB; ++t) {  // sorted insertion: two min/max per slot
                   const float b = best[t];
-                  const bool lt = cd < b;
-                  best[t] = lt ? cd : b;
-                  cd = lt ? b : cd;
+                  best[t] = fminf(b, cd);
+                  cd = fmaxf(b, cd);
                 }
-              }
-              float k2 = best[0];
+                kth = best[NB - 1];
+              } else {
 #pragma unroll
-              for (int t = 1; t < kGridMaxK; ++t)
-                if (t == K - 1) k2 = best[t];
-              kth = k2;
+                for (int t = 0; t < NB; ++t) {
+                  if (t < K) {
+                    const float b = best[t];
+                    const bool lt = cd < b;
+                    best[t] = lt ? cd : b;
+                    cd = lt ? b : cd;
+                  }
+                }
+                float k2 = best[0];
+#pragma unroll
+                for (int t = 1; t < NB; ++t)
+                  if (t == K - 1) k2 = best[t];
+                kth = k2;
+              }
             }
           }
         }
@@ -338,11 +352,11 @@ __global__ void __launch_bounds__(128) k_knn_query(const float* __restrict__ que
   const int kk = K;  // (the caller guarantees R >= K on this path)
   float sum = 0.f;
 #pragma unroll
-  for (int t = 0; t < kGridMaxK; ++t)
+  for (int t = 0; t < NB; ++t)
     if (t >= skip && t < kk && best[t] < kInfF()) sum += best[t];
   int cnt = 0;
 #pragma unroll
-  for (int t = 0; t < kGridMaxK; ++t)
+  for (int t = 0; t < NB; ++t)
     if (t >= skip && t < kk && best[t] < kInfF()) ++cnt;
   mean_out[out_i] = cnt > 0 ? sum / (float)cnt : 0.f;
 }
@@ -378,9 +392,15 @@ int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t 
     // points with NaN coordinates are not in the sorted array: like the brute-force kernel they
     // get +inf (no finite neighbour distance)
     k_fill_f32<<<blocks, 256, 0, stream>>>(mean_out, Q, kInfF());
-    k_knn_query<true><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
+    if (K == 51)
+      k_knn_query<true, 51><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
+    else
+      k_knn_query<true, 0><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
   } else {
-    k_knn_query<false><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
+    if (K == 51)
+      k_knn_query<false, 51><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
+    else
+      k_knn_query<false, 0><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
   }
   return check_launch();
 }

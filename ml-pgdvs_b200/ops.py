@@ -60,14 +60,17 @@ def parse_image_size(image_size) -> Tuple[int, int]:
 
 
 class _Workspace:
-    """Per-device scratch arena, grown geometrically and reused across calls (no per-call
-    cudaMalloc on the hot path)."""
+    """Scratch arenas, grown geometrically and reused across calls (no per-call cudaMalloc on the
+    hot path).  One arena per (device, CUDA stream, purpose): the binned state lives in it between
+    the binning and the rasterizer call and is reordered in place, so two streams (or two Python
+    threads, each on its own stream) rendering on one device must not share it."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, device, nbytes: int, tag: str = "bin") -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (dev_index, torch.cuda.current_stream(device).cuda_stream, tag)
         buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             cap = max(nbytes, int(1.25 * buf.numel()) if buf is not None else 0)
