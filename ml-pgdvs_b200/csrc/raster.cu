@@ -114,8 +114,12 @@ __device__ __forceinline__ bool cand_less(float z, int idx, float ze, int se,
 // included) are redone by rescan_exact() in the full (z, idx) order of the CPU rasterizer's
 // priority queue.  Everything else is provably identical to that order.
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+// Lists up to this length take every candidate through the branch-free chain, two at a time
+// (insert2); longer ones test "can it enter?" first.  16 since round 2: on C3 (K = 16, 139
+// candidates per pixel) the pre-test diverges — some lane always enters — so the warp pays the chain
+// anyway, one candidate at a time: 1.147 -> ~1.0 ms per 8 views with the pair insertion.
 #ifndef PGDVS_RASTER_BRANCHFREE_MAXK
-#define PGDVS_RASTER_BRANCHFREE_MAXK 8
+#define PGDVS_RASTER_BRANCHFREE_MAXK 16
 #endif
 
 struct KeyCode {
