@@ -740,6 +740,8 @@ __device__ __forceinline__ void walk_bounded(const RasterParams& p, const PixelC
     }
     return;
   }
+  // (Tried instead of the queue: one bit mask per window row and lane, walked with ffs — no
+  //  overflow case, three instructions fewer per probe — but 12 % slower, 3.37 vs 2.99 ms on C5.)
   // pass 2b: every lane walks its own queue; a trip of the loop opens a cell or reads a record
   int qi = 0, j = 0, e = 0;
   bool sorted = false;
