@@ -1,8 +1,9 @@
 """pgdvs_b200 — B200-native (sm_100a) implementation of the PGDVS dynamic-content point-splat
 hot path: unproject -> flow-warp -> project -> K-nearest z-buffer splat -> composite -> blend.
 
-The directory is named `ml-pgdvs_b200/` after the reference repository; since that is not a
-valid Python identifier the importable alias is `pgdvs_b200` (see ../pgdvs_b200/__init__.py).
+The directory is named `ml-pgdvs_b200/` after the reference repository; since a hyphen cannot
+appear in a Python module name, `pgdvs_b200` at the repository root is a symbolic link to it:
+`import pgdvs_b200` imports this package directly (no exec shim).
 
 CUDA-only: importing the operator modules requires the built C-ABI library
 (ml-pgdvs_b200/lib/libpgdvs_b200.so); there is no CPU fallback.
