@@ -33,6 +33,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace pgdvs {
 
 struct RasterParams {
@@ -68,6 +70,8 @@ struct RasterParams {
   int plain;         // 1: an image (fp32 and / or 8-bit) wanted, no composited depth
   const uint32_t* zrange;  // [2 N] per view: max(~bits(z)), max(bits(z)) over the filed points (common.cuh)
   float pair_bin_scale;    // k_raster_pair: work -> work-sort bin (64 bins span 2.5x the mean work)
+  uint32_t one, two;       // the constants 1 and 2 as run-time values: multipliers of the IMAD / IMAD.HI forms
+                           // that keep selects of the pair walk on the FMA pipe (walk_pair_flat4)
 };
 
 // Cells holding up to kSortCap records can be put in ascending z order (k_sort_cells, run by the
@@ -1288,13 +1292,25 @@ constexpr int kPairNull = 8;  // record slots reserved at the front of the stagi
 #ifndef PGDVS_PAIR_MINBLOCKS
 #define PGDVS_PAIR_MINBLOCKS 3
 #endif
-// Measured defaults (profiles/r02_pair_ab.md): the flattened four-row walk and the walker-side
-// epilogue; -DPGDVS_PAIR_WALK_PHASED / -DPGDVS_PAIR_EXCHANGE build the alternatives.
+// distance (in CTAs of the launch order) of the L2 prefetch a CTA issues for its successors on the
+// same residency slot: 148 SMs x 3 resident CTAs; 0 = no prefetch
+#ifndef PGDVS_PAIR_PF_DIST
+#define PGDVS_PAIR_PF_DIST 0
+#endif
+// Measured defaults (gpurun_out/s21_ab.md, s22_ab.md): the flattened four-row walk in
+// batches of four (sort4 + merge4) and the raster-order epilogue behind a winner exchange.  Neither
+// pays alone (the batches cut warp instructions 1.08 G -> 1.00 G, the exchange cuts L1 data-pipe
+// wavefronts 362 M -> 302 M, each at 1.62 ms): the kernel sits on issue slots AND the L1 data pipe,
+// together they give 1.62 -> 1.55 ms.  -DPGDVS_PAIR_WALK_PHASED / -DPGDVS_PAIR_WALKER_EPILOGUE /
+// -DPGDVS_PAIR_NO_B4 build the alternatives.
 #if !defined(PGDVS_PAIR_WALK_PHASED) && !defined(PGDVS_PAIR_WALK_FLAT)
 #define PGDVS_PAIR_WALK_FLAT
 #endif
 #if !defined(PGDVS_PAIR_EXCHANGE) && !defined(PGDVS_PAIR_WALKER_EPILOGUE)
-#define PGDVS_PAIR_WALKER_EPILOGUE
+#define PGDVS_PAIR_EXCHANGE
+#endif
+#if !defined(PGDVS_PAIR_B4) && !defined(PGDVS_PAIR_NO_B4)
+#define PGDVS_PAIR_B4
 #endif
 
 // one pixel through the global records: tiles whose runs do not fit the staging buffer
@@ -1441,6 +1457,171 @@ __device__ __forceinline__ void walk_pair_flat(const StagedRecords rec, const Ke
   }
 }
 
+// Batched variant of the flattened walk for 8-key lists (-DPGDVS_PAIR_B4, the default since round 2,
+// session 3): FOUR records per trip.  Their keys are put in order by a 5-exchange sorting network and
+// merged into the sorted list by a half-cleaner (the 8 smallest of list + batch are
+// min(k[4 + i], b[3 - i]) next to k[0..3], a bitonic sequence) and a 12-exchange bitonic merge:
+// 44 min / max per four candidates and list (rejects included) where the pair insertion needs 54, and
+// nothing at all for the first batch, which simply becomes the list.  The ALU pipe is what bounds
+// this kernel (profiles/r02_ncu_summary.md), so the two selects per candidate move to the FMA pipe:
+//   hit -> key      h = hi32(bits(d2 - r2) * 2) = [d2 < r2]      (IMAD.HI with the 2 from the parameters,
+//                   key' = h * (key + 1) - 1 = key or kEmpty       so that ptxas cannot turn it into a shift)
+//   ordinal -> run  j = t + o3 + [t < c012] (o2 - o3) + [t < c01] (o1 - o2) + [t < c0] (s0 - o1), every
+//                   [t < c] again the top bit of t - c taken by IMAD.HI
+// Same keys, same order of candidates, same ambiguity test: same bits as walk_pair_flat.
+__device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+__device__ __forceinline__ void sort4(uint32_t (&b)[4]) {
+  cex(b[0], b[1]);
+  cex(b[2], b[3]);
+  cex(b[0], b[2]);
+  cex(b[1], b[3]);
+  cex(b[1], b[2]);
+}
+// b ascending; the list keeps the 8 smallest of list + b, rej the smallest key that ever fell off
+__device__ __forceinline__ void merge4(KeyList<8>& q, const uint32_t (&b)[4]) {
+  uint32_t (&k)[8] = q.k;
+  const uint32_t r4 = max(k[4], b[3]), r5 = max(k[5], b[2]), r6 = max(k[6], b[1]), r7 = max(k[7], b[0]);
+  k[4] = min(k[4], b[3]);
+  k[5] = min(k[5], b[2]);
+  k[6] = min(k[6], b[1]);
+  k[7] = min(k[7], b[0]);
+  q.rej = min(min(min(q.rej, r4), r5), min(r6, r7));
+  cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
+  cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
+  cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
+}
+__device__ __forceinline__ uint32_t imad_hi(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t imad_lo(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ void walk_pair_flat4(const StagedRecords rec, const KeyCode kc, const float xf,
+                                                const float yfa, const float yfb, const float r2, const int s0,
+                                                const int l0, const int s1, const int l1, const int s2,
+                                                const int l2, const int s3, const int l3, const uint32_t one,
+                                                const uint32_t two, KeyList<8>& qa, KeyList<8>& qb) {
+  const uint32_t mul = 1u << kc.bits;
+  const int c0 = l0, c01 = l0 + l1, c012 = c01 + l2, total = c012 + l3;
+  const int o1 = s1 - c0, o2 = s2 - c01, o3 = s3 - c012;
+#ifdef PGDVS_PAIR_FMA_JSEL
+  const uint32_t d0 = (uint32_t)(s0 - o1), d1 = (uint32_t)(o1 - o2), d2 = (uint32_t)(o2 - o3);
+  const uint32_t n0 = 0u - (uint32_t)c0, n01 = 0u - (uint32_t)c01, n012 = 0u - (uint32_t)c012;
+#endif
+  const uint32_t tk0 = 0u - kc.base * mul;
+  // record of candidate t (t clamped to the last record: the load is always valid)
+  auto fetch = [&](const int t) -> float4 {
+    const int tt = min(t, total - 1);
+#ifdef PGDVS_PAIR_FMA_JSEL
+    uint32_t ju = (uint32_t)(tt + o3);
+    ju = imad_lo(imad_hi(imad_lo((uint32_t)tt, one, n012), two), d2, ju);
+    ju = imad_lo(imad_hi(imad_lo((uint32_t)tt, one, n01), two), d1, ju);
+    ju = imad_lo(imad_hi(imad_lo((uint32_t)tt, one, n0), two), d0, ju);
+    const int j = (int)ju;
+#else
+    const int j = tt + (tt < c01 ? (tt < c0 ? s0 : o1) : (tt < c012 ? o2 : o3));
+#endif
+    return rec.a(j);
+  };
+  // candidate t = record a: its two keys (kEmpty = miss).  MASKED: t may lie behind the last record
+  auto cand = [&](const int t, const float4 a, uint32_t& ka, uint32_t& kb, auto masked) {
+    constexpr bool MASKED = decltype(masked)::value;
+    const float dx = __fsub_rn(a.x, xf);
+    const float dx2 = __fmul_rn(dx, dx);
+    const float dya = __fsub_rn(a.y, yfa), dyb = __fsub_rn(a.y, yfb);
+    const float da = __fadd_rn(dx2, __fmul_rn(dya, dya));
+    const float db = __fadd_rn(dx2, __fmul_rn(dyb, dyb));
+    const uint32_t zb = __float_as_uint(__fadd_rn(a.z, 0.0f));
+#ifdef PGDVS_PAIR_FMA_SEL
+    if (EXACT && !MASKED) {
+      // key + 1 as one multiply-add; the sign of d - r2 is exact (d - r2 rounds to -0 / +0 only when equal)
+      const uint32_t key1 = imad_lo(zb, mul, tk0 + 1u + (uint32_t)t);
+      const uint32_t ha = imad_hi(__float_as_uint(__fsub_rn(da, r2)), two);
+      const uint32_t hb = imad_hi(__float_as_uint(__fsub_rn(db, r2)), two);
+      ka = imad_lo(ha, key1, kEmpty);
+      kb = imad_lo(hb, key1, kEmpty);
+      return;
+    }
+#endif
+    uint32_t key;
+    if (EXACT)
+      key = imad_lo(zb, mul, tk0 + (uint32_t)t);
+    else
+      key = (((zb - kc.base) >> kc.sh) << kc.bits) | (uint32_t)t;
+    const bool ok = !MASKED || (t < total);
+    ka = (ok && da < r2) ? key : kEmpty;
+    kb = (ok && db < r2) ? key : kEmpty;
+  };
+  auto batch = [&](const int t, const float4 (&a)[4], uint32_t (&ba)[4], uint32_t (&bb)[4], auto masked) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cand(t + i, a[i], ba[i], bb[i], masked);
+    sort4(ba);
+    sort4(bb);
+  };
+  if (total <= 0) return;
+  // the records of the NEXT batch are fetched before the keys of the current one are merged: the
+  // shared-memory latency (random 128-bit gathers, ~2.5 bank-conflict replays each) sits under
+  // the min / max network instead of in front of it
+  float4 cur[4], nxt[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cur[i] = fetch(i);
+  int t = 0;
+  if (total >= 4) {  // the first batch becomes the list
+#ifdef PGDVS_PAIR_B4_PREFETCH
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nxt[i] = fetch(4 + i);
+#endif
+    uint32_t ba[4], bb[4];
+    batch(0, cur, ba, bb, std::false_type{});
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      qa.k[i] = ba[i];
+      qb.k[i] = bb[i];
+    }
+    t = 4;
+#ifdef PGDVS_PAIR_B4_PREFETCH
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+#else
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = fetch(4 + i);
+#endif
+  }
+  for (; t + 3 < total; t += 4) {
+#ifdef PGDVS_PAIR_B4_PREFETCH
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nxt[i] = fetch(t + 4 + i);
+#endif
+    uint32_t ba[4], bb[4];
+    batch(t, cur, ba, bb, std::false_type{});
+    merge4(qa, ba);
+    merge4(qb, bb);
+#ifdef PGDVS_PAIR_B4_PREFETCH
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+#else
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = fetch(t + 4 + i);
+#endif
+  }
+  if (t < total) {
+    uint32_t ba[4], bb[4];
+    batch(t, cur, ba, bb, std::true_type{});
+    merge4(qa, ba);
+    merge4(qb, bb);
+  }
+}
+
 // the pair kernel's epilogue for everything but the benchmark configuration: out of line, so the
 // hot kernel carries one inlined copy of spec_epilogue per pixel and nothing else
 template <int KP>
@@ -1491,6 +1672,37 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
     }
   }
   const uint32_t z_nlo = __ldg(p.zrange + 2 * n), z_hi = __ldg(p.zrange + 2 * n + 1);
+#if PGDVS_PAIR_PF_DIST > 0
+  // ---- L2 prefetch for the tiles that will run on this slot next (warp 7, nothing waits on it):
+  //      the cell table of the CTA 2 * PF_DIST ahead, and — from the table entries of the CTA PF_DIST
+  //      ahead, which its predecessor prefetched — that CTA's record rows.  Both of that CTA's
+  //      dependent DRAM round trips (table, then records) become L2 hits.
+  int pf_gs = 0, pf_len = 0;
+  if (warp == 7 && lane < kPairRows) {
+    const int gx = gridDim.x, gy = gridDim.y;
+    const int lin = (blockIdx.z * gy + blockIdx.y) * gx + blockIdx.x;
+    const int n_ctas = gx * gy * (int)gridDim.z;
+    const int nb1 = lin + PGDVS_PAIR_PF_DIST, nb2 = lin + 2 * PGDVS_PAIR_PF_DIST;
+    if (nb2 < n_ctas) {
+      const int bx = nb2 % gx, by = (nb2 / gx) % gy, bz = nb2 / (gx * gy);
+      const int row = by * kPairH + lane;
+      if (row < p.GH) {
+        const int* t0 = p.cell_end + ((int64_t)bz * p.GH + row) * p.GW + max(bx * kPairW - 1, 0);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(t0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(t0 + 32));
+      }
+    }
+    if (nb1 < n_ctas) {
+      const int bx = nb1 % gx, by = (nb1 / gx) % gy, bz = nb1 / (gx * gy);
+      const int row = by * kPairH + lane;
+      if (row < p.GH) {
+        const int* t0 = p.cell_end + ((int64_t)bz * p.GH + row) * p.GW;
+        pf_gs = __ldg(t0 + bx * kPairW - 1);
+        pf_len = __ldg(t0 + min(bx * kPairW - 1 + kPairCols - 1, p.GW - 1)) - pf_gs;
+      }
+    }
+  }
+#endif
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1601,6 +1813,12 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
   }
   __syncthreads();  // (3) permutation
 
+#if PGDVS_PAIR_PF_DIST > 0
+  if (pf_len > 0) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.recA + (int64_t)2 * pf_gs), "r"((uint32_t)pf_len * 32u)
+                 : "memory");
+  }
+#endif
   // ---- the pair this thread walks
   const int mine = s_perm[tid];
   const int q = mine >> 5, lx = mine & 31;
@@ -1638,6 +1856,14 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
 #define PGDVS_WALK_PAIR walk_pair_flat
 #else
 #define PGDVS_WALK_PAIR walk_pair
+#endif
+#if defined(PGDVS_PAIR_B4) && defined(PGDVS_PAIR_WALK_FLAT)
+  if constexpr (KP == 8) {
+    if (kc.sh == 0)
+      walk_pair_flat4<true>(staged_rec, kc, xf, yfa, yfb, p.r2, rs[0], rl[0], rs[1], rl[1], rs[2], rl[2], rs[3], rl[3], p.one, p.two, qa, qb);
+    else
+      walk_pair_flat4<false>(staged_rec, kc, xf, yfa, yfb, p.r2, rs[0], rl[0], rs[1], rl[1], rs[2], rl[2], rs[3], rl[3], p.one, p.two, qa, qb);
+  } else
 #endif
   if (kc.sh == 0)
     PGDVS_WALK_PAIR<KP, true>(staged_rec, kc, xf, yfa, yfb, p.r2, rs[0], rl[0], rs[1], rl[1], rs[2], rl[2], rs[3], rl[3], qa, qb);
@@ -2139,6 +2365,8 @@ extern "C" int pgdvs_rasterize_composite_ex(void* workspace, size_t workspace_by
   p.plain = ((image || p.image_u8) && !p.depth) ? 1 : 0;
   p.zrange = reinterpret_cast<const uint32_t*>(ws + L.off_zrange);
   p.pair_bin_scale = 1.0f;
+  p.one = 1u;
+  p.two = 2u;
   p.force_generic = (debug_switch(kSwForceGeneric) == 1) ? 1 : 0;
   p.no_pair = debug_switch(kSwNoPair);  // 1: never, 0: whenever applicable (also small launches), -1: automatic
   // mean points per pixel of the batch (P is the capacity of the packed cloud: an upper bound)
