@@ -30,9 +30,17 @@ int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_
 int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state, int* ticket,
                            cudaStream_t stream);
 
-constexpr int kUwpThreads = 256;
-constexpr int kUwpPix = 4;                               // pixels per thread
+#ifndef PGDVS_UWP_THREADS
+#define PGDVS_UWP_THREADS 256
+#endif
+#ifndef PGDVS_UWP_PIX
+#define PGDVS_UWP_PIX 4
+#endif
+constexpr int kUwpThreads = PGDVS_UWP_THREADS;
+constexpr int kUwpPix = PGDVS_UWP_PIX;                   // pixels per thread
 constexpr int kUwpTile = kUwpThreads * kUwpPix;          // pixels per tile
+static_assert((kUwpThreads / 32) * kUwpPix == 32 && (kUwpPix % 2) == 0,
+              "one warp scans the (pixel slot, warp) survivor counts: 32 of them; pixels are processed in pairs");
 
 struct UwpParams {
   const PgdvsUwpJob* jobs;
@@ -127,6 +135,34 @@ __device__ __forceinline__ int group_member(const UwpParams& p, int g, int m) {
   return p.group_first ? p.group_members[p.group_first[g] + m] : g;
 }
 
+constexpr int kZChunk = 32;  // members of a job group staged / z ranges flushed at a time
+
+// what one member of a job group adds to the shared source pair
+struct UwpMember {
+  PgdvsCamera cam;  // 16 floats
+  int view, job, tile_base, pad;
+};
+constexpr int kMemberWords = sizeof(UwpMember) / 4;
+static_assert(sizeof(PgdvsCamera) == 64 && sizeof(UwpMember) == 80, "word-wise staging below");
+
+// members [m0, m0 + nc) of group g -> shared memory, one word per thread and step
+__device__ __forceinline__ void stage_members(const UwpParams& p, int g, int jt, int m0, int nc, UwpMember* s_mem) {
+  for (int idx = threadIdx.x; idx < nc * kMemberWords; idx += kUwpThreads) {
+    const int mi = idx / kMemberWords, w = idx - mi * kMemberWords;
+    const int job_m = group_member(p, g, m0 + mi);
+    uint32_t val = 0u;
+    if (w < 17) {
+      const int view = __ldg(&p.jobs[job_m].view);
+      val = (w < 16) ? __ldg(reinterpret_cast<const uint32_t*>(p.cams + view) + w) : (uint32_t)view;
+    } else if (w == 17) {
+      val = (uint32_t)job_m;
+    } else if (w == 18) {
+      val = (uint32_t)__ldg(p.tile_off + (int64_t)job_m * p.tiles_per_job + jt);
+    }
+    reinterpret_cast<uint32_t*>(s_mem + mi)[w] = val;
+  }
+}
+
 __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant__ UwpParams p) {
   __shared__ int s_warp[kUwpThreads / 32];
   const int g = blockIdx.x / p.tiles_per_job;
@@ -150,21 +186,20 @@ __global__ void __launch_bounds__(kUwpThreads) k_uwp_count(const __grid_constant
 #ifndef PGDVS_UWP_MINBLOCKS
 #define PGDVS_UWP_MINBLOCKS 3
 #endif
-template <bool FUSED>
-__global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const __grid_constant__ UwpParams p) {
+// PACKED: frame 2 comes as (r, g, b, depth) float4 (pgdvs_pack_rgbd): four 128-bit taps per pixel.
+// The two tap paths are two instantiations of the whole body behind one CTA-uniform branch, so
+// neither carries the other's (predicated-off) instructions.
+template <bool FUSED, bool PACKED>
+__device__ __forceinline__ void uwp_body(const UwpParams& p, const int g, const int jt, const int n_members,
+                                         int* s_cnt, uint32_t (*s_z)[2], const PgdvsUwpJob& J, UwpMember* s_mem) {
   constexpr int kWarps = kUwpThreads / 32;
-  __shared__ int s_cnt[kUwpPix * kWarps];  // survivors of (k, warp), k-major == pixel order
-  // fused mode: range of the z patterns this CTA files under each member's view (common.cuh),
-  // kZChunk members at a time: (max ~bits, max bits), zero == empty
-  constexpr int kZChunk = 32;
-  __shared__ uint32_t s_z[kZChunk][2];
-  if (FUSED && threadIdx.x < 2 * kZChunk) (&s_z[0][0])[threadIdx.x] = 0u;  // (published by the barrier below)
-  const int g = blockIdx.x / p.tiles_per_job;
-  const int jt = blockIdx.x - g * p.tiles_per_job;
-  const PgdvsUwpJob& J = p.jobs[group_member(p, g, 0)];
 
   PixelSet s;
   pixel_validity(p, J, (int64_t)jt * kUwpTile, s);
+  // (frame-1 depth: issued with the validity reads, consumed after the ordering barrier)
+  float d1[kUwpPix];
+#pragma unroll
+  for (int k = 0; k < kUwpPix; ++k) d1[k] = ((s.valid >> k) & 1u) ? __ldg(J.depth1 + s.pix[k]) : 0.0f;
 
   // ------------------------------------------------------------ order inside the tile:
   // warp ballots give each survivor its rank inside (k, warp); a 32-entry prefix over the
@@ -193,25 +228,27 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
   }
   // (no early exit for threads without survivors: in the fused mode the CTA meets again at the
   //  barriers of the z-range flush; every load and store below is guarded by the validity bits)
-  if (!FUSED && s.valid == 0) return;
+  if (!FUSED && s.valid == 0 && n_members <= kZChunk) return;  // (larger groups meet again at the restaging barriers)
 
   // ------------------------------------------------------------ world point + colour, once
   const bool lerp = (J.same_time == 0);
   const float4* __restrict__ rgbd2 = reinterpret_cast<const float4*>(J.rgbd2);
-  float d1[kUwpPix];
-#pragma unroll
-  for (int k = 0; k < kUwpPix; ++k) d1[k] = ((s.valid >> k) & 1u) ? __ldg(J.depth1 + s.pix[k]) : 0.0f;
   float wx[kUwpPix], wy[kUwpPix], wz[kUwpPix], cr[kUwpPix], cg[kUwpPix], cb[kUwpPix];
-  // two pixels at a time: their 8 frame-2 taps are issued back to back before any is consumed
+  // two pixels at a time: their 8 frame-2 taps are issued back to back before any is consumed.
+  // The taps are NAMED scalars, not an array: with tap[kk][t] the compiler turns the nearest-tap
+  // select into a dynamically indexed load and parks all eight float4 in local memory (16 STL.128 +
+  // LDL per pixel pair in the round-2 build).
 #pragma unroll
   for (int k0 = 0; k0 < kUwpPix; k0 += 2) {
-    float u2a[2], v2a[2], wgt[2][4];
-    float4 tap[2][4];
-    int near_tap[2];
+    float u2a[2], v2a[2];
+    float wg0[2], wg1[2], wg2[2], wg3[2];
+    float4 ta0[2], ta1[2], ta2[2], ta3[2];
+    bool nx1[2], ny1[2];  // nearest pixel = right column / lower row of the 2x2 taps
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
       const int k = k0 + kk;
-      near_tap[kk] = 0;
+      nx1[kk] = ny1[kk] = false;
+      ta0[kk] = ta1[kk] = ta2[kk] = ta3[kk] = make_float4(0.f, 0.f, 0.f, 0.f);  // zeros padding
       if (lerp) {
         const bool ok = (s.valid >> k) & 1u;
         const float u2 = __fadd_rn((float)s.u[k], s.flow[k].x), v2 = __fadd_rn((float)s.v[k], s.flow[k].y);
@@ -226,26 +263,25 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
         const float tw = __fsub_rn(ix, x0f), te = __fsub_rn(1.0f, tw);
         const float tn = __fsub_rn(iy, y0f), ts = __fsub_rn(1.0f, tn);
         const int x0 = (int)x0f, y0 = (int)y0f;
-        wgt[kk][0] = __fmul_rn(ts, te);
-        wgt[kk][1] = __fmul_rn(ts, tw);
-        wgt[kk][2] = __fmul_rn(tn, te);
-        wgt[kk][3] = __fmul_rn(tn, tw);
+        wg0[kk] = __fmul_rn(ts, te);
+        wg1[kk] = __fmul_rn(ts, tw);
+        wg2[kk] = __fmul_rn(tn, te);
+        wg3[kk] = __fmul_rn(tn, tw);
         // the nearest pixel is one of the 4 bilinear taps
-        near_tap[kk] = ((ny != y0f) ? 2 : 0) + ((nx != x0f) ? 1 : 0);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int xs = x0 + (t & 1), ys = y0 + (t >> 1);
-          const bool inb = ok && xs >= 0 && xs < p.W && ys >= 0 && ys < p.H;
-          tap[kk][t] = make_float4(0.f, 0.f, 0.f, 0.f);  // zeros padding
-          if (inb) {
-            const int64_t o = (int64_t)ys * p.W + xs;
-            if (rgbd2 != nullptr)
-              tap[kk][t] = __ldg(rgbd2 + o);
-            else
-              tap[kk][t] = make_float4(__ldg(J.rgb2 + o * 3), __ldg(J.rgb2 + o * 3 + 1),
-                                       __ldg(J.rgb2 + o * 3 + 2), __ldg(J.depth2 + o));
-          }
-        }
+        nx1[kk] = (nx != x0f);
+        ny1[kk] = (ny != y0f);
+        const bool xin0 = x0 >= 0 && x0 < p.W, xin1 = x0 + 1 >= 0 && x0 + 1 < p.W;
+        const bool yin0 = ok && y0 >= 0 && y0 < p.H, yin1 = ok && y0 + 1 >= 0 && y0 + 1 < p.H;
+        const int64_t o00 = (int64_t)y0 * p.W + x0;
+        auto fetch = [&](bool inb, int64_t o) -> float4 {
+          if (!inb) return make_float4(0.f, 0.f, 0.f, 0.f);
+          if (PACKED) return __ldg(rgbd2 + o);
+          return make_float4(__ldg(J.rgb2 + o * 3), __ldg(J.rgb2 + o * 3 + 1), __ldg(J.rgb2 + o * 3 + 2), __ldg(J.depth2 + o));
+        };
+        ta0[kk] = fetch(yin0 && xin0, o00);
+        ta1[kk] = fetch(yin0 && xin1, o00 + 1);
+        ta2[kk] = fetch(yin1 && xin0, o00 + p.W);
+        ta3[kk] = fetch(yin1 && xin1, o00 + p.W + 1);
       }
     }
 #pragma unroll
@@ -264,14 +300,15 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
         cg[k] = __ldg(c1 + 1);
         cb[k] = __ldg(c1 + 2);
       } else {
-        float dep2 = 0.0f;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          cr[k] = __fadd_rn(cr[k], __fmul_rn(tap[kk][t].x, wgt[kk][t]));
-          cg[k] = __fadd_rn(cg[k], __fmul_rn(tap[kk][t].y, wgt[kk][t]));
-          cb[k] = __fadd_rn(cb[k], __fmul_rn(tap[kk][t].z, wgt[kk][t]));
-          if (t == near_tap[kk]) dep2 = tap[kk][t].w;
-        }
+        // (same order of additions as the tap loop t = 0..3 it replaces)
+        cr[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(ta0[kk].x, wg0[kk])), __fmul_rn(ta1[kk].x, wg1[kk])),
+                                    __fmul_rn(ta2[kk].x, wg2[kk])), __fmul_rn(ta3[kk].x, wg3[kk]));
+        cg[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(ta0[kk].y, wg0[kk])), __fmul_rn(ta1[kk].y, wg1[kk])),
+                                    __fmul_rn(ta2[kk].y, wg2[kk])), __fmul_rn(ta3[kk].y, wg3[kk]));
+        cb[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(ta0[kk].z, wg0[kk])), __fmul_rn(ta1[kk].z, wg1[kk])),
+                                    __fmul_rn(ta2[kk].z, wg2[kk])), __fmul_rn(ta3[kk].z, wg3[kk]));
+        const float dtop = nx1[kk] ? ta1[kk].w : ta0[kk].w, dbot = nx1[kk] ? ta3[kk].w : ta2[kk].w;
+        const float dep2 = ny1[kk] ? dbot : dtop;
         // pcl_2 = o_2 + (R_2 @ (K_2^-1 @ [u2, v2, 1])) * depth_2
         const float u2 = u2a[kk], v2 = v2a[kk];
         const float kx = J.K2inv[0] * u2 + J.K2inv[1] * v2 + J.K2inv[2];
@@ -288,83 +325,124 @@ __global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const 
   }
 
   // ------------------------------------------------------------ per member: project, file, store
-  const int n_members = group_size(p, g);
-  for (int m = 0; m < n_members; ++m) {
-    const int job_m = group_member(p, g, m);
-    const int view = p.jobs[job_m].view;
-    const PgdvsCamera cam = p.cams[view];
-    const int tile_base = __ldg(p.tile_off + (int64_t)job_m * p.tiles_per_job + jt);
-    uint32_t z_nlo = 0u, z_hi = 0u;
+  for (int m0 = 0; m0 < n_members; m0 += kZChunk) {
+    const int nc = min(kZChunk, n_members - m0);
+    if (m0 > 0) {  // (the barriers of the previous chunk's flush protect s_mem)
+      stage_members(p, g, jt, m0, nc, s_mem);
+      __syncthreads();
+    }
+    for (int mi = 0; mi < nc; ++mi) {
+      const UwpMember& M = s_mem[mi];
+      const int job_m = M.job;
+      const int view = M.view;
+      const PgdvsCamera& cam = M.cam;
+      const int tile_base = M.tile_base;
+      uint32_t z_nlo = 0u, z_hi = 0u;
 #pragma unroll
-    for (int k = 0; k < kUwpPix; ++k) {
-      if (!((s.valid >> k) & 1u)) continue;
-      const float3 ndc = world_to_ndc(cam, wx[k], wy[k], wz[k]);
-      const int64_t out = (int64_t)tile_base + rank[k];
-      if (FUSED) {
-        const int cell = point_cell(p.g, view, ndc.x, ndc.y, ndc.z);
-        if (cell >= 0) {
-          atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
-          const uint32_t zb = z_pattern(ndc.z);
-          z_nlo = max(z_nlo, ~zb);
-          z_hi = max(z_hi, zb);
+      for (int k = 0; k < kUwpPix; ++k) {
+        if (!((s.valid >> k) & 1u)) continue;
+        const float3 ndc = world_to_ndc(cam, wx[k], wy[k], wz[k]);
+        const int64_t out = (int64_t)tile_base + rank[k];
+        if (FUSED) {
+          const int cell = point_cell(p.g, view, ndc.x, ndc.y, ndc.z);
+          if (cell >= 0) {
+            atomicAdd(p.cell_count + cell, 1);  // result unused -> RED
+            const uint32_t zb = z_pattern(ndc.z);
+            z_nlo = max(z_nlo, ~zb);
+            z_hi = max(z_hi, zb);
+          }
+          // packed-order record: (x, y, z, cell) + (r, g, b); the packed index is the position itself
+          p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float(cell));
+          float* pb = reinterpret_cast<float*>(p.preB) + out * 3;
+          pb[0] = cr[k];
+          pb[1] = cg[k];
+          pb[2] = cb[k];
         }
-        // packed-order record: (x, y, z, cell) + (r, g, b); the packed index is the position itself
-        p.preA[out] = make_float4(ndc.x, ndc.y, ndc.z, __int_as_float(cell));
-        float* pb = reinterpret_cast<float*>(p.preB) + out * 3;
-        pb[0] = cr[k];
-        pb[1] = cg[k];
-        pb[2] = cb[k];
+        if (p.xyz_ndc) {
+          p.xyz_ndc[out * 3 + 0] = ndc.x;
+          p.xyz_ndc[out * 3 + 1] = ndc.y;
+          p.xyz_ndc[out * 3 + 2] = ndc.z;
+        }
+        if (p.rgb) {
+          p.rgb[out * 3 + 0] = cr[k];
+          p.rgb[out * 3 + 1] = cg[k];
+          p.rgb[out * 3 + 2] = cb[k];
+        }
+        if (p.xyz_world) {
+          p.xyz_world[out * 3 + 0] = wx[k];
+          p.xyz_world[out * 3 + 1] = wy[k];
+          p.xyz_world[out * 3 + 2] = wz[k];
+        }
+        if (p.src_pix) p.src_pix[out] = (int32_t)s.pix[k];
+        if (p.world_by_pixel) {
+          float* wp = p.world_by_pixel + ((int64_t)job_m * p.H * p.W + s.pix[k]) * 3;
+          wp[0] = wx[k];
+          wp[1] = wy[k];
+          wp[2] = wz[k];
+        }
       }
-      if (p.xyz_ndc) {
-        p.xyz_ndc[out * 3 + 0] = ndc.x;
-        p.xyz_ndc[out * 3 + 1] = ndc.y;
-        p.xyz_ndc[out * 3 + 2] = ndc.z;
-      }
-      if (p.rgb) {
-        p.rgb[out * 3 + 0] = cr[k];
-        p.rgb[out * 3 + 1] = cg[k];
-        p.rgb[out * 3 + 2] = cb[k];
-      }
-      if (p.xyz_world) {
-        p.xyz_world[out * 3 + 0] = wx[k];
-        p.xyz_world[out * 3 + 1] = wy[k];
-        p.xyz_world[out * 3 + 2] = wz[k];
-      }
-      if (p.src_pix) p.src_pix[out] = (int32_t)s.pix[k];
-      if (p.world_by_pixel) {
-        float* wp = p.world_by_pixel + ((int64_t)job_m * p.H * p.W + s.pix[k]) * 3;
-        wp[0] = wx[k];
-        wp[1] = wy[k];
-        wp[2] = wz[k];
+      if (FUSED) {
+        // z range of this member's view: warp reduction -> shared-memory max
+        z_nlo = __reduce_max_sync(0xffffffffu, z_nlo);
+        z_hi = __reduce_max_sync(0xffffffffu, z_hi);
+        if ((threadIdx.x & 31) == 0 && (z_nlo | z_hi) != 0u) {
+          atomicMax(&s_z[mi][0], z_nlo);
+          atomicMax(&s_z[mi][1], z_hi);
+        }
       }
     }
     if (FUSED) {
-      // z range of this member's view: warp reduction -> shared-memory max; the CTA publishes its
-      // ranges kZChunk members at a time (a look at the current value, an atomic only if wider)
-      const int slot = m % kZChunk;
-      z_nlo = __reduce_max_sync(0xffffffffu, z_nlo);
-      z_hi = __reduce_max_sync(0xffffffffu, z_hi);
-      if ((threadIdx.x & 31) == 0 && (z_nlo | z_hi) != 0u) {
-        atomicMax(&s_z[slot][0], z_nlo);
-        atomicMax(&s_z[slot][1], z_hi);
-      }
-      if (slot == kZChunk - 1 || m == n_members - 1) {
-        __syncthreads();
-        if ((int)threadIdx.x <= slot) {
-          const int vm = p.jobs[group_member(p, g, m - slot + (int)threadIdx.x)].view;
-          const uint32_t nlo = s_z[threadIdx.x][0], hi = s_z[threadIdx.x][1];
-          if ((nlo | hi) != 0u) {
-            const uint2 cur = __ldcg(reinterpret_cast<const uint2*>(p.zrange) + vm);
-            if (nlo > cur.x) atomicMax(p.zrange + 2 * vm, nlo);
-            if (hi > cur.y) atomicMax(p.zrange + 2 * vm + 1, hi);
-          }
-          s_z[threadIdx.x][0] = 0u;
-          s_z[threadIdx.x][1] = 0u;
+      // the CTA publishes the ranges of the chunk's views (a look at the current value, an atomic
+      // only if wider)
+      __syncthreads();
+      if ((int)threadIdx.x < nc) {
+        const int vm = s_mem[threadIdx.x].view;
+        const uint32_t nlo = s_z[threadIdx.x][0], hi = s_z[threadIdx.x][1];
+        if ((nlo | hi) != 0u) {
+          const uint2 cur = __ldcg(reinterpret_cast<const uint2*>(p.zrange) + vm);
+          if (nlo > cur.x) atomicMax(p.zrange + 2 * vm, nlo);
+          if (hi > cur.y) atomicMax(p.zrange + 2 * vm + 1, hi);
         }
-        __syncthreads();
+        s_z[threadIdx.x][0] = 0u;
+        s_z[threadIdx.x][1] = 0u;
       }
+      __syncthreads();
+    } else if (m0 + kZChunk < n_members) {
+      __syncthreads();  // s_mem is about to be restaged
     }
   }
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kUwpThreads, PGDVS_UWP_MINBLOCKS) k_uwp(const __grid_constant__ UwpParams p) {
+  __shared__ int s_cnt[kUwpPix * (kUwpThreads / 32)];  // survivors of (k, warp), k-major == pixel order
+  // fused mode: range of the z patterns this CTA files under each member's view (common.cuh),
+  // kZChunk members at a time: (max ~bits, max bits), zero == empty
+  __shared__ uint32_t s_z[kZChunk][2];
+  // The job (pointers, pair geometry, lerp weights: 55 words) and, kZChunk members at a time, what
+  // each member of the group adds (target camera, view index, output offset of this tile) are
+  // fetched ONCE per CTA by as many threads as there are words and read back as shared-memory
+  // broadcasts: one memory round trip instead of a chain of dependent uniform loads per use (job
+  // -> view -> camera -> offset, per member), and the 35 geometry constants no longer sit in
+  // registers for the whole kernel.
+  __shared__ __align__(16) PgdvsUwpJob s_job;
+  __shared__ __align__(16) UwpMember s_mem[kZChunk];
+  if (FUSED && threadIdx.x < 2 * kZChunk) (&s_z[0][0])[threadIdx.x] = 0u;  // (published by the barrier below)
+  const int g = blockIdx.x / p.tiles_per_job;
+  const int jt = blockIdx.x - g * p.tiles_per_job;
+  const int n_members = group_size(p, g);
+  {
+    static_assert(sizeof(PgdvsUwpJob) % 4 == 0 && sizeof(PgdvsUwpJob) / 4 <= kUwpThreads, "one word per thread");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.jobs + group_member(p, g, 0));
+    if (threadIdx.x < sizeof(PgdvsUwpJob) / 4)
+      reinterpret_cast<uint32_t*>(&s_job)[threadIdx.x] = __ldg(src + threadIdx.x);
+  }
+  stage_members(p, g, jt, 0, min(kZChunk, n_members), s_mem);
+  __syncthreads();
+  if (s_job.rgbd2 != nullptr)  // (CTA-uniform)
+    uwp_body<FUSED, true>(p, g, jt, n_members, s_cnt, s_z, s_job, s_mem);
+  else
+    uwp_body<FUSED, false>(p, g, jt, n_members, s_cnt, s_z, s_job, s_mem);
 }
 
 // per-view first index / count / total from the scanned tile offsets (jobs sorted by view)
