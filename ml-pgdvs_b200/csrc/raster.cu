@@ -216,6 +216,49 @@ struct KeyList {
   }
 };
 
+// Four candidates at a time (k_raster_pair's batched walk, the wide-window walk of k_raster_tile):
+// their keys are put in order by a 5-exchange network (sort4) and merged into the sorted list by a
+// half-cleaner — the KP smallest of list + batch are k[0 .. KP-5] next to min(k[KP-4+i], b[3-i]), a
+// bitonic sequence — and a bitonic merge (KP/2 log2 KP exchanges): 44 min / max per four candidates
+// for KP = 8 (84 for KP = 16), rejects included, where the pair insertion needs 54 (106), and nothing
+// at all for the first batch of a walk, which simply becomes the list.
+__device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+__device__ __forceinline__ void sort4(uint32_t (&b)[4]) {
+  cex(b[0], b[1]);
+  cex(b[2], b[3]);
+  cex(b[0], b[2]);
+  cex(b[1], b[3]);
+  cex(b[1], b[2]);
+}
+// b ascending; the list keeps the KP smallest of list + b, rej the smallest key that ever fell off
+template <int KP>
+__device__ __forceinline__ void merge4(KeyList<KP>& q, const uint32_t (&b)[4]) {
+  static_assert(KP >= 4 && (KP & (KP - 1)) == 0, "bitonic merge: a power of two, at least the batch");
+  uint32_t (&k)[KP] = q.k;
+  const uint32_t r0 = max(k[KP - 4], b[3]), r1 = max(k[KP - 3], b[2]), r2 = max(k[KP - 2], b[1]), r3 = max(k[KP - 1], b[0]);
+  k[KP - 4] = min(k[KP - 4], b[3]);
+  k[KP - 3] = min(k[KP - 3], b[2]);
+  k[KP - 2] = min(k[KP - 2], b[1]);
+  k[KP - 1] = min(k[KP - 1], b[0]);
+  q.rej = min(min(min(q.rej, r0), r1), min(r2, r3));
+#pragma unroll
+  for (int stride = KP / 2; stride >= 1; stride >>= 1) {
+#pragma unroll
+    for (int i = 0; i < KP; ++i)
+      if ((i & stride) == 0) cex(k[i], k[i + stride]);
+  }
+}
+// the first batch of a walk: the list is still empty
+template <int KP>
+__device__ __forceinline__ void assign4(KeyList<KP>& q, const uint32_t (&b)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q.k[i] = b[i];
+}
+
 // General path (long lists, unknown z range): (z, record slot) pairs ordered by z alone with a
 // compare-exchange chain that only runs for candidates nearer than the current last element.
 // Exact fp32 z ties that could change the result are DETECTED, not resolved: `tie` is set when a
@@ -852,12 +895,20 @@ constexpr int kTileW = 32, kTileH = 8;
 #ifndef PGDVS_TILE_KEYS_MAXK
 #define PGDVS_TILE_KEYS_MAXK 32
 #endif
+// resident CTAs per SM the tile kernel is compiled for: K <= 8 with a 3x3 window, K <= 8 with a wider
+// window (the batched walk wants 64 registers: C4 1.005 -> 0.909 ms per 16 views), K <= 16
 #ifndef PGDVS_TILE_MINBLOCKS_K8
 #define PGDVS_TILE_MINBLOCKS_K8 5
 #endif
+#ifndef PGDVS_TILE_MINBLOCKS_K8_WIDE
+#define PGDVS_TILE_MINBLOCKS_K8_WIDE 4
+#endif
+#ifndef PGDVS_TILE_MINBLOCKS_K16
+#define PGDVS_TILE_MINBLOCKS_K16 2
+#endif
 
 template <int KP, int HALO>
-__global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((KP <= 16) ? 2 : 1)) k_raster_tile(const __grid_constant__ RasterParams p) {
+__global__ void __launch_bounds__(256, (KP <= 8) ? (HALO == 1 ? PGDVS_TILE_MINBLOCKS_K8 : PGDVS_TILE_MINBLOCKS_K8_WIDE) : ((KP <= 16) ? PGDVS_TILE_MINBLOCKS_K16 : 1)) k_raster_tile(const __grid_constant__ RasterParams p) {
   constexpr int SPAN = 2 * HALO + 1;     // window rows / cells per pixel
   constexpr int ROWS = kTileH + 2 * HALO;  // extended-grid rows the tile's pixels can touch
   static_assert(ROWS <= 32, "one lane per tile row");
@@ -1148,6 +1199,38 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? PGDVS_TILE_MINBLOCKS_K8 : ((K
         return kc.encode(hit_test<false>(c, a, nullptr, j), a.z, (uint32_t)t);
       };
       int t = 0;
+#ifndef PGDVS_TILE_NO_B4
+      if constexpr (KP == 8 || KP == 16) {
+        // batches of four through sort4 + merge4 (see merge4); the last, partial batch reads the
+        // last record again for the ordinals behind it and discards those keys
+        auto batch = [&](int t0, uint32_t (&kb)[4], bool masked) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ti = t0 + i;
+            const uint32_t key = key_at(masked ? min(ti, total - 1) : ti);
+            kb[i] = (!masked || ti < total) ? key : kEmpty;
+          }
+          sort4(kb);
+        };
+        if (total >= 4) {
+          uint32_t kb[4];
+          batch(0, kb, false);
+          assign4(q, kb);
+          t = 4;
+        }
+        for (; t + 3 < total; t += 4) {
+          uint32_t kb[4];
+          batch(t, kb, false);
+          merge4(q, kb);
+        }
+        if (t < total) {
+          uint32_t kb[4];
+          batch(t, kb, true);
+          merge4(q, kb);
+        }
+        t = total;
+      }
+#endif
       if constexpr (KP >= 2 && KP <= PGDVS_RASTER_BRANCHFREE_MAXK) {
         for (; t + 1 < total; t += 2) q.insert2(key_at(t), key_at(t + 1));
       }
@@ -1469,31 +1552,6 @@ __device__ __forceinline__ void walk_pair_flat(const StagedRecords rec, const Ke
 //   ordinal -> run  j = t + o3 + [t < c012] (o2 - o3) + [t < c01] (o1 - o2) + [t < c0] (s0 - o1), every
 //                   [t < c] again the top bit of t - c taken by IMAD.HI
 // Same keys, same order of candidates, same ambiguity test: same bits as walk_pair_flat.
-__device__ __forceinline__ void cex(uint32_t& a, uint32_t& b) {
-  const uint32_t lo = min(a, b), hi = max(a, b);
-  a = lo;
-  b = hi;
-}
-__device__ __forceinline__ void sort4(uint32_t (&b)[4]) {
-  cex(b[0], b[1]);
-  cex(b[2], b[3]);
-  cex(b[0], b[2]);
-  cex(b[1], b[3]);
-  cex(b[1], b[2]);
-}
-// b ascending; the list keeps the 8 smallest of list + b, rej the smallest key that ever fell off
-__device__ __forceinline__ void merge4(KeyList<8>& q, const uint32_t (&b)[4]) {
-  uint32_t (&k)[8] = q.k;
-  const uint32_t r4 = max(k[4], b[3]), r5 = max(k[5], b[2]), r6 = max(k[6], b[1]), r7 = max(k[7], b[0]);
-  k[4] = min(k[4], b[3]);
-  k[5] = min(k[5], b[2]);
-  k[6] = min(k[6], b[1]);
-  k[7] = min(k[7], b[0]);
-  q.rej = min(min(min(q.rej, r4), r5), min(r6, r7));
-  cex(k[0], k[4]); cex(k[1], k[5]); cex(k[2], k[6]); cex(k[3], k[7]);
-  cex(k[0], k[2]); cex(k[1], k[3]); cex(k[4], k[6]); cex(k[5], k[7]);
-  cex(k[0], k[1]); cex(k[2], k[3]); cex(k[4], k[5]); cex(k[6], k[7]);
-}
 __device__ __forceinline__ uint32_t imad_hi(uint32_t a, uint32_t b) {
   uint32_t r;
   asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -1583,11 +1641,8 @@ __device__ __forceinline__ void walk_pair_flat4(const StagedRecords rec, const K
 #endif
     uint32_t ba[4], bb[4];
     batch(0, cur, ba, bb, std::false_type{});
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      qa.k[i] = ba[i];
-      qb.k[i] = bb[i];
-    }
+    assign4(qa, ba);
+    assign4(qb, bb);
     t = 4;
 #ifdef PGDVS_PAIR_B4_PREFETCH
 #pragma unroll
