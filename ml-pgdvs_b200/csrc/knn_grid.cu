@@ -153,7 +153,27 @@ __global__ void __launch_bounds__(256) k_knn_sample(const float* __restrict__ re
   }
 }
 
-__global__ void k_knn_setup(const int* bbox, int64_t R, const float* est, KnnGrid* g) {
+// one CTA of kGridSamples threads: the median of the calibrated radii by rank counting (every thread
+// ranks its own sample), then thread 0 sizes the grid
+__global__ void __launch_bounds__(kGridSamples) k_knn_setup(const int* bbox, int64_t R, const float* est, KnnGrid* g) {
+  __shared__ float s_v[kGridSamples];
+  __shared__ float s_median;
+  {
+    const int t = threadIdx.x;
+    const float v = est[t];
+    s_v[t] = v;
+    if (t == 0) s_median = 0.0f;
+    const int m = __syncthreads_count(v > 0.0f);  // zeros = unusable samples
+    if (v > 0.0f) {
+      int rank = 0;
+      for (int j = 0; j < kGridSamples; ++j) {
+        const float w = s_v[j];
+        rank += (w > 0.0f && (w < v || (w == v && j < t))) ? 1 : 0;
+      }
+      if (rank == m / 2) s_median = v;  // element m / 2 of the ascending order
+    }
+    __syncthreads();
+  }
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float lo[3], e[3];
   for (int a = 0; a < 3; ++a) {
@@ -173,23 +193,7 @@ __global__ void k_knn_setup(const int* bbox, int64_t R, const float* est, KnnGri
   if (!(area > 0.0f)) area = emax * emax;
   float h = sqrtf(kGridTargetPerCell * area / (float)(R > 0 ? R : 1));  // fallback: thin-surface model
   if (!(h > 0.0f)) h = 1.0f;
-  {
-    // median of the calibrated K-neighbourhood radii (zeros = unusable samples)
-    float v[kGridSamples];
-    int m = 0;
-    for (int i = 0; i < kGridSamples; ++i)
-      if (est[i] > 0.0f) v[m++] = est[i];
-    for (int i = 1; i < m; ++i) {  // insertion sort, 128 values
-      const float x = v[i];
-      int j = i - 1;
-      while (j >= 0 && v[j] > x) {
-        v[j + 1] = v[j];
-        --j;
-      }
-      v[j + 1] = x;
-    }
-    if (m > 0 && v[m / 2] > 0.0f) h = v[m / 2];
-  }
+  if (s_median > 0.0f) h = s_median;  // median of the calibrated K-neighbourhood radii
   int n[3];
   for (int it = 0; it < 64; ++it) {
     double cells = 1.0;
@@ -361,6 +365,234 @@ __global__ void __launch_bounds__(128, (KT > 0 && KT <= 52) ? 5 : 1) k_knn_query
   mean_out[out_i] = cnt > 0 ? sum / (float)cnt : 0.f;
 }
 
+// ---------------------------------------------------------------------------------------
+// Few queries against a large cloud (the track branch: a few hundred track points against the
+// closest-pair cloud, pgdvs_renderer_dyn_track.py "track2base" filter): one WARP per query.
+// A query that lies off the surface walks r shells of mostly empty cells before it meets K points —
+// O(r^3) cells, 9.3 ms per call with one thread per query.  Here the lanes share that walk:
+//   * the points inside the cube of cells [c - r, c + r] are COUNTED from the cell table alone (every
+//     (z, y) row of the cube is one run: two table reads), rows spread over the lanes, and r grows
+//     until the cube holds K points;
+//   * their squared distances go to a per-warp shared-memory array (or are re-read from the sorted
+//     array when the cube holds more than kWarpCap of them), and the K-th smallest is found by
+//     bisection on the bit pattern (d2 >= 0: patterns order like values): 31 counting passes;
+//   * if the K-th lies within the distance to the cube's boundary the K nearest are all inside and
+//     mean = (sum of d2 below the K-th + (K - their number) * K-th - the `skip` smallest) / (K - skip);
+//     otherwise the cube grows by exactly the missing distance and the step repeats.
+// Exact like k_knn_query (same stopping bound); the sum is formed in lane order + shuffle tree
+// (deterministic), not in ascending order, so it can differ from the thread kernel in the last ulps.
+// ---------------------------------------------------------------------------------------
+constexpr int kWarpCap = 2048;       // cached squared distances per warp
+constexpr int kWarpQueryWarps = 4;   // warps (queries) per CTA
+constexpr int64_t kWarpQueryMaxQ = (int64_t)1 << 20;  // cross queries (query != reference)
+constexpr int64_t kWarpSelfMaxQ = 40000;             // self queries
+
+struct KnnCube {
+  int x0, x1, y0, y1, z0, z1, ny, nrows;
+  float bound;      // every point outside the cube is at least this far from the query
+  bool covers_all;  // nothing lies outside
+};
+
+__device__ __forceinline__ KnnCube knn_cube(const KnnGrid& g, const int3 c, const int r, const float qx, const float qy,
+                                            const float qz) {
+  KnnCube C;
+  C.z0 = max(c.z - r, 0), C.z1 = min(c.z + r, g.n[2] - 1);
+  C.y0 = max(c.y - r, 0), C.y1 = min(c.y + r, g.n[1] - 1);
+  C.x0 = max(c.x - r, 0), C.x1 = min(c.x + r, g.n[0] - 1);
+  C.ny = C.y1 - C.y0 + 1;
+  C.nrows = (C.z1 - C.z0 + 1) * C.ny;
+  float bound = kInfF();
+  const float q[3] = {qx, qy, qz};
+  const int cc[3] = {c.x, c.y, c.z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {  // (sides on the grid boundary are open)
+    if (cc[a] - r > 0) bound = fminf(bound, q[a] - (g.lo[a] + (float)(cc[a] - r) * g.h));
+    if (cc[a] + r < g.n[a] - 1) bound = fminf(bound, (g.lo[a] + (float)(cc[a] + r + 1) * g.h) - q[a]);
+  }
+  C.covers_all = (bound == kInfF());
+  C.bound = fmaxf(bound - 1e-4f * g.h, 0.0f);  // slack for the rounding of the cell assignment
+  return C;
+}
+
+// SELF: the queries are the reference points themselves, taken in cell order from the sorted array
+template <bool SELF>
+__global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
+    const float* __restrict__ query, int64_t Q, const KnnGrid* __restrict__ gp, const int* __restrict__ cell_end,
+    const float4* __restrict__ sorted, int K, int skip, float* __restrict__ mean_out) {
+  __shared__ float s_d2[kWarpQueryWarps][kWarpCap];
+  const KnnGrid g = *gp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t qi = (int64_t)blockIdx.x * kWarpQueryWarps + warp;
+  if (qi >= Q) return;
+  float* cache = s_d2[warp];
+  float qx, qy, qz;
+  if (SELF) {
+    // sorted holds only the finite points: the tail of an array with NaN points is unused
+    const int total_sorted = __ldg(cell_end + (int64_t)g.n[0] * g.n[1] * g.n[2] - 1);
+    if (qi >= total_sorted) return;
+    const float4 p = __ldg(sorted + qi);
+    qx = p.x;
+    qy = p.y;
+    qz = p.z;
+    qi = __float_as_int(p.w);
+  } else {
+    qx = __ldg(query + qi * 3);
+    qy = __ldg(query + qi * 3 + 1);
+    qz = __ldg(query + qi * 3 + 2);
+  }
+  if (!(qx == qx && qy == qy && qz == qz)) {  // NaN query: no distance compares below anything (k_knn_query: 0)
+    if (lane == 0) mean_out[qi] = 0.f;
+    return;
+  }
+  const int3 c = grid_coord(g, qx, qy, qz);
+  const int rmax = max(g.n[0], max(g.n[1], g.n[2]));
+
+  // f(d2) over every point of cube C, each point visited by exactly one lane (rows spread over lanes)
+  auto for_each_point = [&](const KnnCube& C, auto&& f) {
+    for (int i = lane; i < C.nrows; i += 32) {
+      const int z = C.z0 + i / C.ny, y = C.y0 + i % C.ny;
+      const int row = (z * g.n[1] + y) * g.n[0];
+      const int s = __ldg(cell_end + row + C.x0 - 1), e = __ldg(cell_end + row + C.x1);
+      for (int j = s; j < e; ++j) {
+        const float4 p = __ldg(sorted + j);
+        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+        f(dx * dx + dy * dy + dz * dz);
+      }
+    }
+  };
+  auto warp_sum = [](int v) { return __reduce_add_sync(0xffffffffu, v); };
+
+  // ---- A: the first cube (geometric growth) that holds K points, counted from the table alone
+  int r = 0;
+  KnnCube C;
+  int cnt;
+  while (true) {
+    C = knn_cube(g, c, r, qx, qy, qz);
+    int n = 0;
+    for (int i = lane; i < C.nrows; i += 32) {
+      const int z = C.z0 + i / C.ny, y = C.y0 + i % C.ny;
+      const int row = (z * g.n[1] + y) * g.n[0];
+      n += __ldg(cell_end + row + C.x1) - __ldg(cell_end + row + C.x0 - 1);
+    }
+    cnt = warp_sum(n);
+    if (cnt >= K || C.covers_all || r >= rmax) break;
+    r += max(1, r >> 1);
+  }
+  const int kk = min(K, cnt);
+  if (kk <= skip) {
+    if (lane == 0) mean_out[qi] = 0.f;
+    return;
+  }
+
+  // the candidates of cube C whose d2 <= limit, appended to the cache by warp-prefix offsets; returns
+  // how many there are (more than kWarpCap: the cache is not valid)
+  auto collect = [&](const KnnCube& Cc, const float limit) -> int {
+    int base = 0;
+    for (int i0 = 0; i0 < Cc.nrows; i0 += 32) {
+      const int i = i0 + lane;
+      int s = 0, e = 0;
+      if (i < Cc.nrows) {
+        const int z = Cc.z0 + i / Cc.ny, y = Cc.y0 + i % Cc.ny;
+        const int row = (z * g.n[1] + y) * g.n[0];
+        s = __ldg(cell_end + row + Cc.x0 - 1);
+        e = __ldg(cell_end + row + Cc.x1);
+      }
+      if (!__any_sync(0xffffffffu, e > s)) continue;  // 32 empty rows
+      // (two passes over this lane's run: count the survivors, then write them behind the prefix)
+      int mine = 0;
+      for (int j = s; j < e; ++j) {
+        const float4 p = __ldg(sorted + j);
+        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+        mine += (dx * dx + dy * dy + dz * dz <= limit) ? 1 : 0;
+      }
+      int inc = mine;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      int dst = base + inc - mine;
+      const int total = base + __shfl_sync(0xffffffffu, inc, 31);
+      if (total <= kWarpCap) {
+        for (int j = s; j < e; ++j) {
+          const float4 p = __ldg(sorted + j);
+          const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 <= limit) cache[dst++] = d2;
+        }
+      }
+      base = total;
+    }
+    __syncwarp();
+    return base;
+  };
+  // n-th smallest (1-based) of the candidate set: the least pattern T with #{d2 <= T} >= n.
+  // d2 >= 0, so the bit patterns order like the values.
+  auto nth_smallest = [&](const KnnCube& Cc, const int n_cand, const bool cached, const float limit, const int n) -> float {
+    uint32_t lo = 0u, hi = 0x7f800000u;
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      int n_le = 0;
+      if (cached) {
+        for (int i = lane; i < n_cand; i += 32) n_le += (__float_as_uint(cache[i]) <= mid) ? 1 : 0;
+      } else {
+        for_each_point(Cc, [&](float d) { n_le += (d <= limit && __float_as_uint(d) <= mid) ? 1 : 0; });
+      }
+      n_le = warp_sum(n_le);
+      if (n_le >= n)
+        hi = mid;
+      else
+        lo = mid + 1u;
+    }
+    return __uint_as_float(lo);
+  };
+
+  // ---- B: the kk-th smallest of cube A; it bounds the true kk-th from above
+  int n_cand = collect(C, kInfF());
+  bool cached = n_cand <= kWarpCap;
+  float limit = kInfF();
+  float kth = nth_smallest(C, n_cand, cached, limit, kk);
+  if (!C.covers_all && !(kth <= C.bound * C.bound)) {
+    // ---- C: the cube whose boundary is at least sqrt(kth) away holds every point with d2 <= kth,
+    //      the true kk nearest among them: collect only those
+    const float miss = sqrtf(kth) - C.bound;
+    r = min(r + max(1, (int)ceilf(miss * g.inv_h)), rmax);
+    C = knn_cube(g, c, r, qx, qy, qz);
+    if (!C.covers_all && !(kth <= C.bound * C.bound)) {  // (rounding of the step: one more shell)
+      r = min(r + 1, rmax);
+      C = knn_cube(g, c, r, qx, qy, qz);
+    }
+    limit = kth;
+    n_cand = collect(C, limit);
+    cached = n_cand <= kWarpCap;
+    kth = nth_smallest(C, n_cand, cached, limit, kk);
+  }
+  // ---- mean of the kk smallest without the `skip` smallest
+  float sum = 0.f, dmin = kInfF();
+  int n_lt = 0;
+  auto acc = [&](float d) {
+    if (d < kth) {
+      sum += d;
+      ++n_lt;
+    }
+    dmin = fminf(dmin, d);
+  };
+  if (cached) {
+    for (int i = lane; i < n_cand; i += 32) acc(cache[i]);
+  } else {
+    for_each_point(C, [&](float d) { if (d <= limit) acc(d); });
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+  }
+  n_lt = warp_sum(n_lt);
+  sum += (float)(kk - n_lt) * kth;
+  if (skip == 1) sum -= dmin;
+  if (lane == 0) mean_out[qi] = sum / (float)(kk - skip);
+}
+
 // Host driver used by pgdvs_knn_mean_dist (knn.cu) when the caller provides the workspace.
 size_t knn_grid_workspace_bytes(int64_t R) { return make_knn_grid_layout(R).total; }
 
@@ -380,7 +612,7 @@ int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t 
   k_knn_bbox<<<blocks, 256, 0, stream>>>(ref, R, bbox);
   float* est = reinterpret_cast<float*>(ws + L.off_est);
   k_knn_sample<<<kGridSamples, 256, 0, stream>>>(ref, R, K, est);
-  k_knn_setup<<<1, 32, 0, stream>>>(bbox, R, est, grid);
+  k_knn_setup<<<1, kGridSamples, 0, stream>>>(bbox, R, est, grid);
   k_knn_count<<<blocks, 256, 0, stream>>>(ref, R, grid, cells, cell_of);
   if (int rc = check_launch()) return rc;
   if (int rc = scan_exclusive_inplace(cells, L.scan_tiles, reinterpret_cast<unsigned long long*>(ws + L.off_state),
@@ -392,10 +624,18 @@ int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t 
     // points with NaN coordinates are not in the sorted array: like the brute-force kernel they
     // get +inf (no finite neighbour distance)
     k_fill_f32<<<blocks, 256, 0, stream>>>(mean_out, Q, kInfF());
-    if (K == 51)
+    // small clouds (the track branch: 10 - 35 k track points): the warp kernel is ahead up to ~60 k
+    // queries (20 k: 0.29 vs 0.47 ms, 60 k: 0.71 vs 0.79 ms, 157 k: 1.77 vs 1.20 ms with the grid build)
+    if (Q <= kWarpSelfMaxQ && skip <= 1) {
+      const unsigned wb = (unsigned)((Q + kWarpQueryWarps - 1) / kWarpQueryWarps);
+      k_knn_query_warp<true><<<wb, 32 * kWarpQueryWarps, 0, stream>>>(query, Q, grid, cells, sorted, K, skip, mean_out);
+    } else if (K == 51)
       k_knn_query<true, 51><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
     else
       k_knn_query<true, 0><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
+  } else if (Q <= kWarpQueryMaxQ && skip <= 1) {
+    const unsigned wb = (unsigned)((Q + kWarpQueryWarps - 1) / kWarpQueryWarps);
+    k_knn_query_warp<false><<<wb, 32 * kWarpQueryWarps, 0, stream>>>(query, Q, grid, cells, sorted, K, skip, mean_out);
   } else {
     if (K == 51)
       k_knn_query<false, 51><<<qb, 128, 0, stream>>>(query, Q, grid, cells, sorted, R, K, skip, mean_out);
