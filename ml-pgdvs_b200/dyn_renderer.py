@@ -449,6 +449,9 @@ class FilteredViews:
         filtered.sort(key=lambda t: t[0])
         self.prep = PreparedViews([q for _, q in filtered], cams_p3d, H, W, device)
 
+    KNN_STREAMS = 3
+    _knn_streams = None
+
     def filter(self):
         """world clouds -> KNN statistics -> keep masks (all stream-ordered, nothing returns to the host)."""
         if self.n_groups == 0:
@@ -465,8 +468,23 @@ class FilteredViews:
                 self.rep_prep.n_views, H, W, self.world.data_ptr(), ops._aligned_ptr(ws), nbytes.value,
                 ops._stream_ptr(dev)), "pgdvs_uwp_world_by_pixel")
             ops.LAUNCHES["count"] += 1
+            # the clouds are independent: spread them over a few side streams (each with its own grid
+            # scratch: the arena is keyed by stream) so that one cloud's small build kernels and the
+            # tail of its query kernel run under the next cloud's query
+            main = torch.cuda.current_stream(dev)
+            if self._knn_streams is None:
+                self._knn_streams = [torch.cuda.Stream(dev) for _ in range(min(self.KNN_STREAMS, self.n_groups))]
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for s in self._knn_streams:
+                s.wait_event(ready)
             for g in range(self.n_groups):
-                ops.knn_mean_dist(self.world[g], self.world[g], self.knn + 1, skip_first=1, out=self.avg[g])
+                with torch.cuda.stream(self._knn_streams[g % len(self._knn_streams)]):
+                    ops.knn_mean_dist(self.world[g], self.world[g], self.knn + 1, skip_first=1, out=self.avg[g])
+            for s in self._knn_streams:
+                done = torch.cuda.Event()
+                done.record(s)
+                main.wait_event(done)
             _cabi.check(L.pgdvs_outlier_keep(self.avg.data_ptr(), self.n_groups, H * W, self.std_thres,
                                              self.keep.data_ptr(), self.thres.data_ptr(), ops._stream_ptr(dev)),
                         "pgdvs_outlier_keep")
