@@ -20,7 +20,11 @@ EXTRA = ['launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_me
          'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct',
          'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum',
          'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
-         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio']
+         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+         'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.sum',
+         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+         'l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum', 'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_fma.sum',
+         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active']
 
 
 def tables(rep):
