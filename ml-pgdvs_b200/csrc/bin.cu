@@ -14,6 +14,8 @@
 //             are kept in flight because the cell -> cursor -> scatter chain is latency-bound.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace pgdvs {
 
 struct BinParams {
@@ -122,6 +124,57 @@ __global__ void __launch_bounds__(256) k_fill_pre(BinParams p) {
   }
 }
 
+// The same move in TILE-MAJOR order over the jobs of a view: CTA o takes the packed range of one
+// (job, 1024-pixel source tile) — the scanned tile offsets of the uwp pass give it — and consecutive
+// CTAs take the same source tile of all the jobs of a view before moving on to the next tile.  Source
+// pairs of a view cover the same image region, so the cell lines a tile touches are completed while they
+// are still in L2.  In packed (job-major) order every job sweeps the whole record array of its view;
+// at C5 (8 source pairs, 530 MB of records per view) the lines leave L2 one-eighth full and DRAM sees
+// eight partial writes per line: k_fill_pre ran at 40 % of the copy peak there, at 72 % on C2.
+__global__ void __launch_bounds__(256) k_fill_pre_tiles(BinParams p, const PgdvsUwpJob* __restrict__ jobs, int n_jobs,
+                                                        int tiles_per_job, const int* __restrict__ tile_off) {
+  static_assert(kFillUnroll * 256 >= kUwpTilePixels, "one CTA moves one tile of the uwp pass");
+  __shared__ int s_range[2];
+  if (threadIdx.x == 0) {
+    const int o = blockIdx.x, jb = o / tiles_per_job;
+    const int v = jobs[jb].view;
+    int f = jb, l = jb;
+    while (f > 0 && jobs[f - 1].view == v) --f;
+    while (l + 1 < n_jobs && jobs[l + 1].view == v) ++l;
+    const int c = l - f + 1, local = o - f * tiles_per_job;
+    const int jt = local / c, j = f + local % c;
+    const int64_t t = (int64_t)j * tiles_per_job + jt;
+    s_range[0] = __ldg(tile_off + t);
+    s_range[1] = __ldg(tile_off + t + 1);
+  }
+  __syncthreads();
+  const int q0 = s_range[0], q1 = s_range[1];
+  int cell[kFillUnroll];
+  float4 a[kFillUnroll], b[kFillUnroll];
+#pragma unroll
+  for (int u = 0; u < kFillUnroll; ++u) {
+    const int q = q0 + u * 256 + (int)threadIdx.x;
+    cell[u] = -1;
+    if (q < q1) {
+      a[u] = __ldg(p.preA + q);
+      const float* pb = reinterpret_cast<const float*>(p.preB) + (int64_t)q * 3;
+      b[u] = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), 0.0f);
+      cell[u] = __float_as_int(a[u].w);
+      a[u].w = __int_as_float(q);  // the packed index is the position itself
+    }
+  }
+  int pos[kFillUnroll];
+#pragma unroll
+  for (int u = 0; u < kFillUnroll; ++u) pos[u] = (cell[u] >= 0) ? atomicAdd(p.cells + cell[u], 1) : -1;
+#pragma unroll
+  for (int u = 0; u < kFillUnroll; ++u) {
+    if (pos[u] >= 0) {
+      p.recA[rec_a(pos[u])] = a[u];
+      p.recA[rec_b(pos[u])] = b[u];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // In-place exclusive scan, single pass with decoupled look-back.
 // state[t] = (flag << 32) | value; flag 1 = tile aggregate, 2 = inclusive prefix.
@@ -209,10 +262,20 @@ int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state
   return check_launch();
 }
 
+// developer switch, read once: PGDVS_FILL_TILES=0 never / 1 always the tile-major fill; unset: automatic
+static int debug_fill_tiles() {
+  static const int v = [] {
+    const char* e = getenv("PGDVS_FILL_TILES");
+    return (e && *e) ? (atoi(e) != 0 ? 1 : 0) : -1;
+  }();
+  return v;
+}
+
 // Second half of the fused path (called by pgdvs_uwp_bin in uwp.cu): scan the cell counters
 // the uwp kernel accumulated, then scatter its packed-order records into cell order.
 int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,
-                        const int64_t* total_dev, cudaStream_t stream) {
+                        const int64_t* total_dev, const PgdvsUwpJob* jobs, int n_jobs, int n_views,
+                        int tiles_per_job, const int* tile_off, cudaStream_t stream) {
   BinParams p = {};
   p.cells = reinterpret_cast<int*>(ws + L.off_cells);
   p.cell_of = reinterpret_cast<int*>(ws + L.off_cell_of);
@@ -227,8 +290,15 @@ int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_
       reinterpret_cast<int*>(ws + L.off_ticket));
   if (int rc = check_launch()) return rc;
   if (capacity > 0) {
-    const int64_t g = (capacity + 256 * kFillUnroll - 1) / (256 * kFillUnroll);
-    k_fill_pre<<<(unsigned)g, 256, 0, stream>>>(p);
+    // tile-major when the records of one view are too many to stay in L2 while its jobs take turns
+    const bool tile_major = debug_fill_tiles() != 0 && jobs != nullptr && n_views > 0 &&
+                            (debug_fill_tiles() > 0 || (capacity / n_views) * 32 > ((int64_t)64 << 20));
+    if (tile_major) {
+      k_fill_pre_tiles<<<(unsigned)((int64_t)n_jobs * tiles_per_job), 256, 0, stream>>>(p, jobs, n_jobs, tiles_per_job, tile_off);
+    } else {
+      const int64_t g = (capacity + 256 * kFillUnroll - 1) / (256 * kFillUnroll);
+      k_fill_pre<<<(unsigned)g, 256, 0, stream>>>(p);
+    }
     if (int rc = check_launch()) return rc;
   }
   return 0;

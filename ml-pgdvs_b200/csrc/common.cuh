@@ -83,6 +83,7 @@ struct BinLayout {
 };
 
 constexpr int kScanTile = 4096;  // ints per scan tile (1024 threads x int4)
+constexpr int kUwpTilePixels = 1024;  // source pixels per tile of the uwp pass (uwp.cu); k_fill_pre_tiles moves one per CTA
 #ifndef PGDVS_REC_STRIDE
 #define PGDVS_REC_STRIDE 2
 #endif

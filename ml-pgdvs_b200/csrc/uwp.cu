@@ -26,7 +26,8 @@
 namespace pgdvs {
 
 int bin_scan_fill_fused(char* ws, const BinLayout& L, const FusedTail& T, int64_t capacity,
-                        const int64_t* total_dev, cudaStream_t stream);
+                        const int64_t* total_dev, const PgdvsUwpJob* jobs, int n_jobs, int n_views,
+                        int tiles_per_job, const int* tile_off, cudaStream_t stream);
 int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state, int* ticket,
                            cudaStream_t stream);
 
@@ -39,6 +40,7 @@ int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state
 constexpr int kUwpThreads = PGDVS_UWP_THREADS;
 constexpr int kUwpPix = PGDVS_UWP_PIX;                   // pixels per thread
 constexpr int kUwpTile = kUwpThreads * kUwpPix;          // pixels per tile
+static_assert(kUwpTile == kUwpTilePixels, "bin.cu's tile-major fill assumes this tile size");
 static_assert((kUwpThreads / 32) * kUwpPix == 32 && (kUwpPix % 2) == 0,
               "one warp scans the (pixel slot, warp) survivor counts: 32 of them; pixels are processed in pairs");
 
@@ -654,7 +656,8 @@ extern "C" int pgdvs_uwp_bin(const PgdvsUwpJob* jobs, int n_jobs, const PgdvsCam
                    reinterpret_cast<float4*>(ws + T.off_preA), reinterpret_cast<float4*>(ws + T.off_preB),
                    group_first, group_members, n_groups, stream);
   if (rc) return rc;
-  return bin_scan_fill_fused(ws, B, T, cap, total_points, stream);
+  return bin_scan_fill_fused(ws, B, T, cap, total_points, jobs, n_jobs, n_views, U.tiles_per_job,
+                             reinterpret_cast<const int*>(ws + T.total + U.off_tile_off), stream);
 }
 
 extern "C" int pgdvs_pack_rgbd(const PgdvsFramePack* frames_dev, int n_frames, int H, int W,

@@ -204,6 +204,35 @@ def test_job_groups_do_not_change_results():
             assert torch.equal(a[k], x[k]), k
 
 
+def test_job_groups_larger_than_one_member_chunk():
+    """k_uwp stages the members of a group in shared memory 32 at a time: a group of 48 target views
+    (the 12 cameras of a time step, four times over) takes two chunks and must still equal the
+    ungrouped run bit for bit."""
+    from pgdvs_b200 import synthetic
+    from pgdvs_b200.dyn_renderer import prepare_views, render_prepared
+    dev = _dev()
+    wl = synthetic.make_workload("c2_nvidia_seq", dev, n_views=12, mask_mode="ellipse")
+    views = list(range(12)) * 4
+    pairs, cams = wl.jobs(views)
+    a_prep = prepare_views(pairs, cams, wl.H, wl.W, dev, group_jobs=True)
+    b_prep = prepare_views(pairs, cams, wl.H, wl.W, dev, group_jobs=False)
+    assert a_prep.n_groups == 2 and b_prep.n_groups == 0  # (fwd, bwd) pair of the one time step, 48 members each
+    kw = dict(radius=wl.radius, points_per_pixel=wl.K, compositor="norm", static_rgb=wl.static_rgb[views],
+              return_fragments=True, return_cloud=True)
+    a = render_prepared(a_prep, **kw)
+    b = render_prepared(b_prep, **kw)
+    torch.cuda.synchronize()
+    P = int(a["cloud"]["total"])
+    assert P == int(b["cloud"]["total"]) and P > 0
+    assert torch.equal(a["first_idx"], b["first_idx"]) and torch.equal(a["num_points"], b["num_points"])
+    assert torch.equal(a["cloud"]["xyz_ndc"][:P], b["cloud"]["xyz_ndc"][:P])
+    assert torch.equal(a["cloud"]["rgb"][:P], b["cloud"]["rgb"][:P])
+    for k in ("idx", "zbuf", "dists", "image", "mask"):
+        assert torch.equal(a[k], b[k]), k
+    # the four replicas of a camera render the same frame
+    assert torch.equal(a["image"][:12], a["image"][36:48])
+
+
 @pytest.mark.parametrize("mode,fn", [("alpha", "alpha_composite"), ("norm", "norm_weighted_sum"), ("wsum", "weighted_sum")])
 def test_standalone_compositors(mode, fn):
     import pgdvs_b200
