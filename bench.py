@@ -268,7 +268,7 @@ def run_matrix(dev, flush, peak, args):
     import torch
     from types import SimpleNamespace
     from pgdvs_b200 import synthetic, track
-    from pgdvs_b200.dyn_renderer import render_views_filtered
+    from pgdvs_b200.dyn_renderer import CapturedRender, prepare_views, render_views_filtered
     rows = []
     ms = max(3, min(args.matrix_steps, args.steps))
 
@@ -281,6 +281,36 @@ def run_matrix(dev, flush, peak, args):
         torch.cuda.empty_cache()
 
     batched("c1_nvidia_1view", "c1_nvidia_1view")
+    # the same single view replayed from a CUDA graph (dyn_renderer.CapturedRender): one launch per step
+    wl = synthetic.make_workload("c1_nvidia_1view", dev)
+    pairs, cams = wl.jobs(range(wl.n_views))
+    cap = CapturedRender(prepare_views(pairs, cams, wl.H, wl.W, dev), radius=wl.radius, points_per_pixel=wl.K,
+                         compositor="norm", static_rgb=wl.static_rgb, return_fragments=True)
+    for _ in range(2):
+        cap.replay()
+    torch.cuda.synchronize()
+    ev = _events(ms)
+    for a, b in ev:
+        a.record()
+        flush.zero_()
+        cap.replay()
+        b.record()
+    torch.cuda.synchronize()
+    t_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    ev = _events(ms)
+    for a, b in ev:  # back to back, no flush: the latency of a launch-bound call
+        a.record()
+        cap.replay()
+        b.record()
+    torch.cuda.synchronize()
+    t_hot = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    rows.append({"config": "c1_nvidia_1view (CUDA graph replay)", "views_per_step": 1, "image": [wl.H, wl.W],
+                 "points_per_view": wl.points_per_view(), "points_per_pixel": wl.K, "radius": wl.radius, "step_ms": t_ms,
+                 "views_per_s": 1.0 / (t_ms / 1e3), "step_ms_no_flush": t_hot,
+                 "note": "render_prepared captured once (dyn_renderer.CapturedRender), one graph launch per step; "
+                         "step_ms includes the 256 MiB L2 flush like every other row, step_ms_no_flush does not"})
+    del wl, pairs, cams, cap
+    torch.cuda.empty_cache()
     # C2 with dyn_pcl_remove_outlier: KNN (K = 50) statistics per source pair on the device, no host sync
     wl = synthetic.make_workload("c2_nvidia_seq", dev)
     pairs, cams = wl.jobs(range(wl.n_views))

@@ -402,6 +402,49 @@ def render_views(pairs: Sequence[SourcePair], tgt_cams: Sequence, H: int, W: int
                            return_cloud=return_cloud, return_depth=return_depth, return_u8=return_u8)
 
 
+class CapturedRender:
+    """`render_prepared(prep, **kw)` captured once in a CUDA graph and replayed: the whole step (memsets,
+    pack, uwp count / scan / uwp, scan, fill, rasterize-and-composite: ~10 launches) becomes one launch.
+    That is what a launch-bound call wants — a single target view (BASELINE configs[0]) is 0.096 ms as
+    separate launches and 0.071 ms replayed on a B200; a 144-view step is bound by its kernels and gains
+    nothing.  The outputs are the SAME tensors at every replay (copy what must survive the next one); the
+    source frames, cameras and `static_rgb` are read through the pointers captured with `prep`, so
+    writing new content into those tensors in place and replaying renders it.  Bit-identical to the
+    eager call."""
+
+    def __init__(self, prep: PreparedViews, **kw):
+        if kw.get("raster_events") is not None:
+            raise ValueError("raster_events cannot be recorded inside a captured graph")
+        dev = prep.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up off the capture: library handle, workspaces, smem opt-ins
+            for _ in range(2):
+                render_prepared(prep, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.prep = prep
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = render_prepared(prep, **kw)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
+_KNN_STREAMS: Dict[int, list] = {}
+
+
+def _knn_side_streams(dev, n):
+    """The side streams of the outlier filter, one set per device for the life of the process (the
+    scratch arenas are keyed by stream: fresh streams per call would mean fresh scratch per call)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    pool = _KNN_STREAMS.setdefault(idx, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:n]
+
+
 class FilteredViews:
     """The batched hot path WITH the statistical outlier filter of compute_dyn_pcl
     (pgdvs_renderer_dyn.py:401-457; `dyn_pcl_remove_outlier`, on in every published run:
@@ -450,7 +493,6 @@ class FilteredViews:
         self.prep = PreparedViews([q for _, q in filtered], cams_p3d, H, W, device)
 
     KNN_STREAMS = 3
-    _knn_streams = None
 
     def filter(self):
         """world clouds -> KNN statistics -> keep masks (all stream-ordered, nothing returns to the host)."""
@@ -472,16 +514,15 @@ class FilteredViews:
             # scratch: the arena is keyed by stream) so that one cloud's small build kernels and the
             # tail of its query kernel run under the next cloud's query
             main = torch.cuda.current_stream(dev)
-            if self._knn_streams is None:
-                self._knn_streams = [torch.cuda.Stream(dev) for _ in range(min(self.KNN_STREAMS, self.n_groups))]
+            streams = _knn_side_streams(dev, min(self.KNN_STREAMS, self.n_groups))
             ready = torch.cuda.Event()
             ready.record(main)
-            for s in self._knn_streams:
+            for s in streams:
                 s.wait_event(ready)
             for g in range(self.n_groups):
-                with torch.cuda.stream(self._knn_streams[g % len(self._knn_streams)]):
+                with torch.cuda.stream(streams[g % len(streams)]):
                     ops.knn_mean_dist(self.world[g], self.world[g], self.knn + 1, skip_first=1, out=self.avg[g])
-            for s in self._knn_streams:
+            for s in streams:
                 done = torch.cuda.Event()
                 done.record(s)
                 main.wait_event(done)

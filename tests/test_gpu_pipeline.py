@@ -204,6 +204,33 @@ def test_job_groups_do_not_change_results():
             assert torch.equal(a[k], x[k]), k
 
 
+def test_captured_render_replays_the_eager_step():
+    """CapturedRender: the step as one CUDA graph; replays give the eager bits and follow in-place
+    updates of the inputs."""
+    from pgdvs_b200 import synthetic
+    from pgdvs_b200.dyn_renderer import CapturedRender, prepare_views, render_prepared
+    dev = _dev()
+    wl = synthetic.make_workload("tiny", dev, n_views=2)
+    pairs, cams = wl.jobs(range(2))
+    prep = prepare_views(pairs, cams, wl.H, wl.W, dev)
+    kw = dict(radius=wl.radius, points_per_pixel=wl.K, compositor="norm", static_rgb=wl.static_rgb,
+              return_fragments=True)
+    eager = {k: v.clone() for k, v in render_prepared(prep, **kw).items() if torch.is_tensor(v)}
+    cap = CapturedRender(prep, **kw)
+    for _ in range(2):
+        out = cap.replay()
+        torch.cuda.synchronize()
+        for k in ("idx", "zbuf", "dists", "image", "mask"):
+            assert torch.equal(out[k], eager[k]), k
+    # new content behind the captured pointers: the static frame is blended in the epilogue
+    wl.static_rgb.mul_(0.5)
+    out = cap.replay()
+    again = render_prepared(prep, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(out["image"], again["image"]) and not torch.equal(out["image"], eager["image"])
+    assert torch.equal(out["idx"], eager["idx"])
+
+
 def test_job_groups_larger_than_one_member_chunk():
     """k_uwp stages the members of a group in shared memory 32 at a time: a group of 48 target views
     (the 12 cameras of a time step, four times over) takes two chunks and must still equal the
