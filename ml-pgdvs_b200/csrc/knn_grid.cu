@@ -22,6 +22,8 @@
 // Everything stays on the device (the grid geometry is a device struct), no host sync.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace pgdvs {
 
 int scan_exclusive_inplace(int* data, int64_t n_tiles, unsigned long long* state, int* ticket,
@@ -39,6 +41,7 @@ constexpr int kGridMaxCells = 1 << 22;
 constexpr int kGridMaxK = 64;
 constexpr float kGridTargetPerCell = 4.0f;
 constexpr int kGridSamples = 128;  // sample queries that calibrate the cell size
+constexpr float kGridCellScale = 1.0f;
 
 struct KnnGrid {
   float lo[3];
@@ -155,7 +158,8 @@ __global__ void __launch_bounds__(256) k_knn_sample(const float* __restrict__ re
 
 // one CTA of kGridSamples threads: the median of the calibrated radii by rank counting (every thread
 // ranks its own sample), then thread 0 sizes the grid
-__global__ void __launch_bounds__(kGridSamples) k_knn_setup(const int* bbox, int64_t R, const float* est, KnnGrid* g) {
+__global__ void __launch_bounds__(kGridSamples) k_knn_setup(const int* bbox, int64_t R, const float* est, float cell_scale,
+                                                           KnnGrid* g) {
   __shared__ float s_v[kGridSamples];
   __shared__ float s_median;
   {
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(kGridSamples) k_knn_setup(const int* bbox, int
   if (!(area > 0.0f)) area = emax * emax;
   float h = sqrtf(kGridTargetPerCell * area / (float)(R > 0 ? R : 1));  // fallback: thin-surface model
   if (!(h > 0.0f)) h = 1.0f;
-  if (s_median > 0.0f) h = s_median;  // median of the calibrated K-neighbourhood radii
+  if (s_median > 0.0f) h = s_median * cell_scale;  // median of the calibrated K-neighbourhood radii, scaled
   int n[3];
   for (int it = 0; it < 64; ++it) {
     double cells = 1.0;
@@ -593,6 +597,17 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
   if (lane == 0) mean_out[qi] = sum / (float)(kk - skip);
 }
 
+// Cell size relative to the calibrated K-neighbourhood radius.  Developer override, read once:
+// PGDVS_KNN_CELL_SCALE=<float>.
+static float knn_cell_scale() {
+  static const float v = [] {
+    const char* e = getenv("PGDVS_KNN_CELL_SCALE");
+    const float f = (e && *e) ? (float)atof(e) : kGridCellScale;
+    return (f > 0.01f && f < 100.0f) ? f : kGridCellScale;
+  }();
+  return v;
+}
+
 // Host driver used by pgdvs_knn_mean_dist (knn.cu) when the caller provides the workspace.
 size_t knn_grid_workspace_bytes(int64_t R) { return make_knn_grid_layout(R).total; }
 
@@ -612,7 +627,7 @@ int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t 
   k_knn_bbox<<<blocks, 256, 0, stream>>>(ref, R, bbox);
   float* est = reinterpret_cast<float*>(ws + L.off_est);
   k_knn_sample<<<kGridSamples, 256, 0, stream>>>(ref, R, K, est);
-  k_knn_setup<<<1, kGridSamples, 0, stream>>>(bbox, R, est, grid);
+  k_knn_setup<<<1, kGridSamples, 0, stream>>>(bbox, R, est, knn_cell_scale(), grid);
   k_knn_count<<<blocks, 256, 0, stream>>>(ref, R, grid, cells, cell_of);
   if (int rc = check_launch()) return rc;
   if (int rc = scan_exclusive_inplace(cells, L.scan_tiles, reinterpret_cast<unsigned long long*>(ws + L.off_state),
