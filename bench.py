@@ -615,20 +615,25 @@ def run_ours(args):
         state["inputs_free"][b] = cur.record_event()
 
     def e2e_run(u8):
+        # wall clock of n steps, max over ranks; the MEDIAN of three such runs (the leg is bound by PCIe
+        # and host memory, which other tenants of the box share: single runs scatter by +-20 %)
         n = max(4, min(args.steps, 20))
         e2e_step(u8)
         e2e_step(u8)
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(n):
-            e2e_step(u8)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - w0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return views_total * n / dt, n
+        vals = []
+        for _ in range(3):
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(n):
+                e2e_step(u8)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - w0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            vals.append(views_total * n / dt)
+        return sorted(vals)[1], n
 
     e2e_value, e2e_steps = e2e_run(False)
     e2e8_value, _ = e2e_run(True)
@@ -707,7 +712,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + cam_bytes),
                     "d2h_bytes_per_step": int(V * H * W * 16), "steps": e2e_steps,
                     "note": ("host pinned inputs + target cameras -> H2D -> uwp/bin/raster -> D2H of fp32 frames+masks, wall "
-                             f"clock; {n_chunks} view chunks pipelined on 3 streams, device inputs double-buffered")},
+                             f"clock, median of 3 runs of {e2e_steps} steps; {n_chunks} view chunks pipelined on 3 streams, "
+                             "device inputs double-buffered")},
             "e2e_u8_frames": {"value": e2e8_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + cam_bytes),
                               "d2h_bytes_per_step": int(V * H * W * 4),
                               "note": "same loop, 8-bit frames and masks written by the rasterizer's epilogue "
