@@ -491,6 +491,7 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
   // the candidates of cube C whose d2 <= limit, appended to the cache by warp-prefix offsets; returns
   // how many there are (more than kWarpCap: the cache is not valid)
   auto collect = [&](const KnnCube& Cc, const float limit) -> int {
+    __syncwarp();  // (the reads of an earlier selection pass are done before the cache is rewritten)
     int base = 0;
     for (int i0 = 0; i0 < Cc.nrows; i0 += 32) {
       const int i = i0 + lane;
