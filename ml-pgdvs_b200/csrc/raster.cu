@@ -1369,11 +1369,20 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? (HALO == 1 ? PGDVS_TILE_MINBL
 //   * winners travel to the epilogue threads as 16-bit float4 indices (StagedAddr).
 // Fragments are bit-identical to k_raster_tile's (same keys, same ambiguity test, same rescan).
 // ---------------------------------------------------------------------------------------
-constexpr int kPairW = 32, kPairH = 16, kPairRows = kPairH + 2, kPairTabW = 36, kPairCols = 35;
+// tile height: 8 pixel rows (128 threads, 96 registers without spills, 5 resident CTAs of 36 KB) since
+// session 3; -DPGDVS_PAIR_H=16 builds the 32x16 tiles of session 2 (256 threads, 80 registers, 3 resident
+// CTAs).  C2: 1.567 (32x16) -> 1.531 ms; six resident 32x8 CTAs at 80 registers need the staging headroom
+// cut to 1.25 (1.520 ms, 0.5 % of the tiles unstaged) and are not the default (gpurun_out/s38_ab.md, s40_ab.md).
+#ifndef PGDVS_PAIR_H
+#define PGDVS_PAIR_H 8
+#endif
+constexpr int kPairW = 32, kPairH = PGDVS_PAIR_H, kPairRows = kPairH + 2, kPairTabW = 36, kPairCols = 35;
+constexpr int kPairWarps = kPairH / 2, kPairThreads = 32 * kPairWarps;
+static_assert(kPairH == 16 || kPairH == 8, "the prologue's thread ranges assume 128 or 256 threads");
 constexpr int kPairNull = 8;  // record slots reserved at the front of the staging buffer (zeroed)
 
 #ifndef PGDVS_PAIR_MINBLOCKS
-#define PGDVS_PAIR_MINBLOCKS 3
+#define PGDVS_PAIR_MINBLOCKS (PGDVS_PAIR_H == 16 ? 3 : 5)
 #endif
 // distance (in CTAs of the launch order) of the L2 prefetch a CTA issues for its successors on the
 // same residency slot: 148 SMs x 3 resident CTAs; 0 = no prefetch
@@ -1694,7 +1703,7 @@ __device__ __noinline__ void pair_epilogue_generic(const RasterParams& p, const 
 }
 
 template <int KP>
-__global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const __grid_constant__ RasterParams p) {
+__global__ void __launch_bounds__(kPairThreads, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const __grid_constant__ RasterParams p) {
   static_assert(KP >= 2 && KP <= 8 && (KP % 2) == 0, "pair kernel: K-lists of 2, 4 or 8 keys");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4* s_rec = reinterpret_cast<float4*>(smem_raw);
@@ -1704,7 +1713,7 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
   __shared__ int s_delta[kPairRows];           // smem record index = global record index + s_delta[row]
   __shared__ int s_staged, s_max;
   __shared__ int s_hist[64];
-  __shared__ unsigned char s_perm[256];
+  __shared__ unsigned char s_perm[kPairThreads];
   __shared__ float s_xf[kPairW], s_yf[kPairH];
   __shared__ __align__(16) uint16_t s_win[kPairW * kPairH * KP];  // per pixel its K winners (float4 indices)
 
@@ -1718,7 +1727,7 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
   int tabv[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const int i = tid + k * 256;
+    const int i = tid + k * kPairThreads;
     tabv[k] = 0;
     if (i < kPairRows * kPairCols) {
       const int r = i / kPairCols, c = i - r * kPairCols;
@@ -1733,7 +1742,7 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
   //      ahead, which its predecessor prefetched — that CTA's record rows.  Both of that CTA's
   //      dependent DRAM round trips (table, then records) become L2 hits.
   int pf_gs = 0, pf_len = 0;
-  if (warp == 7 && lane < kPairRows) {
+  if (warp == kPairWarps - 1 && lane < kPairRows) {
     const int gx = gridDim.x, gy = gridDim.y;
     const int lin = (blockIdx.z * gy + blockIdx.y) * gx + blockIdx.x;
     const int n_ctas = gx * gy * (int)gridDim.z;
@@ -1766,10 +1775,10 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
   if (tid < 64) s_hist[tid] = 0;
   if (tid >= 64 && tid < 64 + 2 * kPairNull) s_rec[tid - 64] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid >= 96 && tid < 96 + kPairW) s_xf[tid - 96] = pixel_center_ndc(p.ax, x0 + tid - 96);
-  if (tid >= 128 && tid < 128 + kPairH) s_yf[tid - 128] = pixel_center_ndc(p.ay, y0 + tid - 128);
+  if (tid >= 80 && tid < 80 + kPairH) s_yf[tid - 80] = pixel_center_ndc(p.ay, y0 + tid - 80);  // (lanes 16.. of warp 2)
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const int i = tid + k * 256;
+    const int i = tid + k * kPairThreads;
     if (i < kPairRows * kPairCols) {
       const int r = i / kPairCols;
       s_tab[r][i - r * kPairCols] = tabv[k];
@@ -1811,7 +1820,7 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
         }
       }
     }
-    if (fits && lane < kPairRows && (lane & 7) == warp && len > 0) {
+    if (fits && lane < kPairRows && (lane % kPairWarps) == warp && len > 0) {
       const float4* src = p.recA + (int64_t)2 * gs;
       float4* dst = s_rec + 2 * dst_slot;
       const uint32_t bytes = (uint32_t)len * 32u;
@@ -1861,7 +1870,7 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
     const int x = x0 + lane;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
-      const int y = y0 + warp + 8 * h;
+      const int y = y0 + warp + kPairWarps * h;
       if (x < p.W && y < p.H) pixel_via_global<KP>(p, n, x, y);
     }
     return;
@@ -2035,7 +2044,7 @@ __global__ void __launch_bounds__(256, PGDVS_PAIR_MINBLOCKS) k_raster_pair(const
   if (ex >= p.W) return;
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
-    const int ly = warp + 8 * h;
+    const int ly = warp + kPairWarps * h;
     const int ey = y0 + ly;
     if (ey >= p.H) break;
     const uint16_t* src = s_win + (ly * kPairW + lane) * KP;
@@ -2186,6 +2195,10 @@ static int raise_smem_limit(Kernel kernel, int (&granted)[kMaxDevices], int smem
   if (dev < 0 || dev >= kMaxDevices || smem > granted[dev]) {
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
+    // the staged kernels size their buffers so that N CTAs fill the SM's shared memory: ask for the
+    // largest carve-out (the default heuristic may leave one CTA's worth to L1)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
     if (dev >= 0 && dev < kMaxDevices) granted[dev] = smem;
   }
   return 0;
@@ -2217,6 +2230,11 @@ static int launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, c
   return 1;
 }
 
+// staging capacity of k_raster_pair relative to the mean records of a tile (a tile that overflows it
+// takes the unstaged path)
+#ifndef PGDVS_PAIR_HEADROOM
+#define PGDVS_PAIR_HEADROOM PGDVS_RASTER_HEADROOM
+#endif
 #ifndef PGDVS_PAIR_SMEM_MAX
 #define PGDVS_PAIR_SMEM_MAX (64 * 1024)
 #endif
@@ -2224,14 +2242,15 @@ static int launch_tile(RasterParams& p, dim3 grid, dim3 block, double density, c
 template <int KP>
 static int launch_pair(RasterParams& p, cudaStream_t stream) {
   const double tile_cells = (double)(kPairW + 2) * kPairRows;
-  double need = PGDVS_RASTER_HEADROOM * p.density * tile_cells * 32.0;
+  double need = PGDVS_PAIR_HEADROOM * p.density * tile_cells * 32.0;
   if (need > (double)PGDVS_PAIR_SMEM_MAX) {
     need = PGDVS_RASTER_HEADROOM_DENSE * p.density * tile_cells * 32.0;
     if (need > (double)PGDVS_PAIR_SMEM_MAX) return 0;  // too dense to stage 32x16 tiles
     need = (double)PGDVS_PAIR_SMEM_MAX;
   }
   int smem = (int)need + 32 * (kPairNull + 8 * kPairRows);  // null slots + per-row alignment padding
-  if (smem < 32 * 1024) smem = 32 * 1024;
+  const int smem_min = (kPairH == 16 ? 32 : 20) * 1024;
+  if (smem < smem_min) smem = smem_min;
   if (smem > PGDVS_PAIR_SMEM_MAX) smem = PGDVS_PAIR_SMEM_MAX;
   smem = (smem + 1023) & ~1023;
   p.smem_records = smem / 32;
@@ -2248,7 +2267,7 @@ static int launch_pair(RasterParams& p, cudaStream_t stream) {
   if ((int64_t)grid.x * grid.y * grid.z < (int64_t)2 * 148 * PGDVS_PAIR_MINBLOCKS && p.no_pair < 0) return 0;
   static int granted[kMaxDevices] = {};
   if (int rc = raise_smem_limit(k_raster_pair<KP>, granted, smem)) return -rc;
-  k_raster_pair<KP><<<grid, 256, smem, stream>>>(p);
+  k_raster_pair<KP><<<grid, kPairThreads, smem, stream>>>(p);
   return 1;
 }
 
