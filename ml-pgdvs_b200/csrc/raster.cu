@@ -1355,7 +1355,8 @@ __global__ void __launch_bounds__(256, (KP <= 8) ? (HALO == 1 ? PGDVS_TILE_MINBL
 // Same ingredients as k_raster_tile (TMA-staged row runs, work sort, sorted 32-bit keys, winner
 // exchange, raster-order epilogue) re-cut so that the fixed costs are paid once per 512 pixels
 // and neighbouring pixels share their candidates:
-//   * a CTA covers 32x16 pixels with 256 threads; every thread walks a VERTICAL PIXEL PAIR
+//   * a CTA covers 32 x kPairH pixels (32x8 with 128 threads since session 3, 32x16 with 256 before);
+//     every thread walks a VERTICAL PIXEL PAIR
 //     (x, 2q) / (x, 2q+1).  Their windows overlap in two of three rows: the shared rows are walked
 //     once (one LDS.128, one dx*dx, one key per candidate, inserted into both lists), the two
 //     exclusive rows side by side (row 0 -> upper pixel, row 3 -> lower pixel in the same step).
