@@ -24,7 +24,9 @@ EXTRA = ['launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_me
          'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts.sum',
          'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
          'l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum', 'sm__inst_executed_pipe_alu.sum', 'sm__inst_executed_pipe_fma.sum',
-         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active']
+         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+         'lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed', 'lts__t_requests_srcunit_tex_op_red.sum',
+         'lts__t_requests_srcunit_tex_op_atom_dot_alu.sum', 'lts__t_sectors_srcunit_tex_op_atom.sum']
 
 
 def tables(rep):
