@@ -268,8 +268,8 @@ def _tile_case(rng, H, W, P, z_mode, cluster=0.0):
 ])
 @pytest.mark.parametrize("kernel", ["tile", "pair"])
 def test_tile_kernel_paths_bit_exact(z_mode, cluster, K, P, kernel):
-    """Both staged kernels (k_raster_tile: 32x8 tiles, one pixel per thread; k_raster_pair: 32x16
-    tiles, a vertical pixel pair per thread, K in {2, 4, 8}) on every special path."""
+    """Both staged kernels (k_raster_tile: 32x8 tiles, one pixel per thread; k_raster_pair: 32x8
+    tiles (32x16 before session 3), a vertical pixel pair per thread, K in {2, 4, 8}) on every special path."""
     from pgdvs_b200 import _cabi
     _cabi.debug_switch("no_pair", 1 if kernel == "tile" else 0)
     try:
@@ -278,9 +278,22 @@ def test_tile_kernel_paths_bit_exact(z_mode, cluster, K, P, kernel):
         _cabi.debug_switch("no_pair", -1)
 
 
-def _tile_kernel_case(z_mode, cluster, K, P):
+@pytest.mark.parametrize("H,W", [(93, 121), (50, 70), (17, 33)])
+@pytest.mark.parametrize("kernel", ["tile", "pair"])
+def test_staged_kernels_on_ragged_images(H, W, kernel):
+    """Image sizes that are no multiple of the tile (32 x 8) or of the pixel pair: the last tile
+    row / column is partial and the last pixel row may have no partner."""
+    from pgdvs_b200 import _cabi
+    _cabi.debug_switch("no_pair", 1 if kernel == "tile" else 0)
+    try:
+        _tile_kernel_case("smooth", 0.0, 8, 12000, H=H, W=W, r=1.45 / (min(H, W) / 2))
+        _tile_kernel_case("ties", 0.2, 4, 9000, H=H, W=W, r=1.45 / (min(H, W) / 2))
+    finally:
+        _cabi.debug_switch("no_pair", -1)
+
+
+def _tile_kernel_case(z_mode, cluster, K, P, H=96, W=128, r=0.029):
     rng = np.random.default_rng(sum(map(ord, z_mode)) * 1000 + K * 10 + int(cluster * 10))
-    H, W, r = 96, 128, 0.029
     pts = _tile_case(rng, H, W, P, z_mode, cluster)
     feats = rng.uniform(0, 1, (P, 3)).astype(np.float32)
     fi = np.array([0, P // 3], np.int64)
