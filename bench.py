@@ -480,25 +480,29 @@ def run_ours(args):
             if rank == 0:
                 gather_list = [torch.empty((V, H, W, 3), dtype=gdtype, device=dev) for _ in range(world)]
     state_g = {"i": 0}
-    # 8-bit frames for the gather: the stand-alone quantiser (0.06 ms per 144 frames) — writing them
-    # from the rasterizer's epilogue costs more there (scattered byte stores: +0.14 ms, measured)
-    frames_u8 = [torch.empty((V, H, W, 3), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    # 8-bit frames for the gather come from the rasterizer's epilogue: with the raster-order epilogue
+    # their stores are coalesced (+0.02 ms per 144 frames; the stand-alone quantiser is 0.075 ms and,
+    # with the work-sorted epilogue of session 2, the fused output cost +0.14 ms)
+    want_u8 = world > 1 and gather_mode != "f32"
 
     def step(ev=None):
         out = render_prepared(prep, radius=radius, points_per_pixel=K, compositor="norm",
-                              static_rgb=wl.static_rgb, raster_events=ev, return_fragments=args.fragments)
+                              static_rgb=wl.static_rgb, raster_events=ev, return_fragments=args.fragments,
+                              return_u8=want_u8)
         if world > 1:
             i = state_g["i"]
             state_g["i"] += 1
-            if gather_mode != "f32":
-                if state_g.get(i & 1) is not None:  # the transfer that last read this buffer (step i - 2) is done
-                    torch.cuda.current_stream().wait_event(state_g[i & 1])
-                out["image_u8"] = ops.quantize_u8(out["image"], out=frames_u8[i & 1])
             done = torch.cuda.Event()
             done.record()
             if sink is not None:
+                # the frames are a fresh tensor every step: hold it until the copy that reads it (two steps
+                # back by the time the reference is dropped) has finished — no record_stream, whose deferred
+                # frees make the caching allocator grow (a 35 ms cudaMalloc stall in the timed region)
+                if state_g.get(("ev", i & 1)) is not None:
+                    torch.cuda.current_stream().wait_event(state_g[("ev", i & 1)])
+                state_g[("keep", i & 1)] = out["image_u8"]
                 sink.push(out["image_u8"], i, after=done)
-                state_g[i & 1] = sink.stream.record_event()
+                state_g[("ev", i & 1)] = sink.stream.record_event()
                 sink.commit()
             else:
                 payload = out["image"] if gather_mode == "f32" else out["image_u8"]
