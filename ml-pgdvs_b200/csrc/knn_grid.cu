@@ -388,8 +388,16 @@ __global__ void __launch_bounds__(128, (KT > 0 && KT <= 52) ? 5 : 1) k_knn_query
 // ---------------------------------------------------------------------------------------
 constexpr int kWarpCap = 2048;       // cached squared distances per warp
 constexpr int kWarpQueryWarps = 4;   // warps (queries) per CTA
+constexpr int kCollectUnroll = 4;    // points per lane and trip of the candidate collection
 constexpr int64_t kWarpQueryMaxQ = (int64_t)1 << 20;  // cross queries (query != reference)
-constexpr int64_t kWarpSelfMaxQ = 40000;             // self queries
+#ifndef PGDVS_KNN_WARP_SELF_MAXQ
+#define PGDVS_KNN_WARP_SELF_MAXQ (1 << 20)
+#endif
+constexpr int64_t kWarpSelfMaxQ = PGDVS_KNN_WARP_SELF_MAXQ;  // self queries
+
+#ifdef PGDVS_KNN_STATS
+__device__ unsigned long long g_knn_wstats[8];
+#endif
 
 struct KnnCube {
   int x0, x1, y0, y1, z0, z1, ny, nrows;
@@ -424,11 +432,15 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
     const float* __restrict__ query, int64_t Q, const KnnGrid* __restrict__ gp, const int* __restrict__ cell_end,
     const float4* __restrict__ sorted, int K, int skip, float* __restrict__ mean_out) {
   __shared__ float s_d2[kWarpQueryWarps][kWarpCap];
+  __shared__ int s_hist[kWarpQueryWarps][256];
+  __shared__ float s_sel[kWarpQueryWarps][32];
   const KnnGrid g = *gp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int64_t qi = (int64_t)blockIdx.x * kWarpQueryWarps + warp;
   if (qi >= Q) return;
   float* cache = s_d2[warp];
+  int* hist = s_hist[warp];
+  float* selbuf = s_sel[warp];
   float qx, qy, qz;
   if (SELF) {
     // sorted holds only the finite points: the tail of an array with NaN points is unused
@@ -490,6 +502,12 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
 
   // the candidates of cube C whose d2 <= limit, appended to the cache by warp-prefix offsets; returns
   // how many there are (more than kWarpCap: the cache is not valid)
+  // The candidates of cube C whose d2 <= limit, appended to the cache; returns how many there are (more
+  // than kWarpCap: the cache is not valid).  Rows are taken 32 at a time (one per lane); their POINTS are
+  // then spread over the lanes — point t of the chunk belongs to the first row whose inclusive count
+  // exceeds t, found by a 5-step shuffle search — so that every lane has one independent load in flight
+  // per trip (a lane walking its own row alone waits for each of its ~15 loads in turn: 25 - 50 k cycles
+  // per query), and survivors are compacted with a ballot.
   auto collect = [&](const KnnCube& Cc, const float limit) -> int {
     __syncwarp();  // (the reads of an earlier selection pass are done before the cache is rewritten)
     int base = 0;
@@ -502,31 +520,51 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
         s = __ldg(cell_end + row + Cc.x0 - 1);
         e = __ldg(cell_end + row + Cc.x1);
       }
-      if (!__any_sync(0xffffffffu, e > s)) continue;  // 32 empty rows
-      // (two passes over this lane's run: count the survivors, then write them behind the prefix)
-      int mine = 0;
-      for (int j = s; j < e; ++j) {
-        const float4 p = __ldg(sorted + j);
-        const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-        mine += (dx * dx + dy * dy + dz * dz <= limit) ? 1 : 0;
-      }
-      int inc = mine;
+      const int len = e - s;
+      if (!__any_sync(0xffffffffu, len > 0)) continue;  // 32 empty rows
+      int inc = len;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const int o = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += o;
       }
-      int dst = base + inc - mine;
-      const int total = base + __shfl_sync(0xffffffffu, inc, 31);
-      if (total <= kWarpCap) {
-        for (int j = s; j < e; ++j) {
-          const float4 p = __ldg(sorted + j);
-          const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-          const float d2 = dx * dx + dy * dy + dz * dz;
-          if (d2 <= limit) cache[dst++] = d2;
+      const int T = __shfl_sync(0xffffffffu, inc, 31);
+      // kCollectUnroll points per lane and trip: their loads are issued back to back
+      for (int t0 = 0; t0 < T; t0 += 32 * kCollectUnroll) {
+        float d2[kCollectUnroll];
+        bool keep[kCollectUnroll];
+#pragma unroll
+        for (int u = 0; u < kCollectUnroll; ++u) {
+          const int t = t0 + 32 * u + lane, tt = min(t, T - 1);
+          int lo = 0, hi = 31;  // the smallest lane whose inclusive count exceeds tt
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int mid = (lo + hi) >> 1;
+            const int v = __shfl_sync(0xffffffffu, inc, mid);
+            if (v > tt)
+              hi = mid;
+            else
+              lo = mid + 1;
+          }
+          const int inc_o = __shfl_sync(0xffffffffu, inc, lo), len_o = __shfl_sync(0xffffffffu, len, lo);
+          const int s_o = __shfl_sync(0xffffffffu, s, lo);
+          keep[u] = t < T;
+          d2[u] = 0.f;
+          if (keep[u]) {
+            const float4 p = __ldg(sorted + s_o + (tt - (inc_o - len_o)));
+            const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+            d2[u] = dx * dx + dy * dy + dz * dz;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kCollectUnroll; ++u) {
+          const bool k = keep[u] && d2[u] <= limit;
+          const unsigned m = __ballot_sync(0xffffffffu, k);
+          const int dst = base + __popc(m & ((1u << lane) - 1u));
+          if (k && dst < kWarpCap) cache[dst] = d2[u];
+          base += __popc(m);
         }
       }
-      base = total;
     }
     __syncwarp();
     return base;
@@ -535,14 +573,39 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
   // d2 >= 0, so the bit patterns order like the values.
   auto nth_smallest = [&](const KnnCube& Cc, const int n_cand, const bool cached, const float limit, const int n) -> float {
     uint32_t lo = 0u, hi = 0x7f800000u;
-    while (lo < hi) {
+    if (cached) {
+      // four-way search: three thresholds per pass over the cache, 16 dependent passes instead of 31
+      while (lo < hi) {
+        const uint32_t span = hi - lo;
+        const uint32_t q2 = lo + (span >> 1), q1 = lo + (span >> 2), q3 = q2 + (span >> 2);  // lo <= q1 <= q2 <= q3 < hi
+        int c1 = 0, c2 = 0, c3 = 0;
+        for (int i = lane; i < n_cand; i += 32) {
+          const uint32_t v = __float_as_uint(cache[i]);
+          c1 += (v <= q1) ? 1 : 0;
+          c2 += (v <= q2) ? 1 : 0;
+          c3 += (v <= q3) ? 1 : 0;
+        }
+        c1 = warp_sum(c1);
+        c2 = warp_sum(c2);
+        c3 = warp_sum(c3);
+        if (c1 >= n) {
+          hi = q1;
+        } else if (c2 >= n) {
+          lo = q1 + 1u;
+          hi = q2;
+        } else if (c3 >= n) {
+          lo = q2 + 1u;
+          hi = q3;
+        } else {
+          lo = q3 + 1u;
+        }
+      }
+      return __uint_as_float(lo);
+    }
+    while (lo < hi) {  // (the cache overflowed: bisection over the cube's points themselves)
       const uint32_t mid = lo + ((hi - lo) >> 1);
       int n_le = 0;
-      if (cached) {
-        for (int i = lane; i < n_cand; i += 32) n_le += (__float_as_uint(cache[i]) <= mid) ? 1 : 0;
-      } else {
-        for_each_point(Cc, [&](float d) { n_le += (d <= limit && __float_as_uint(d) <= mid) ? 1 : 0; });
-      }
+      for_each_point(Cc, [&](float d) { n_le += (d <= limit && __float_as_uint(d) <= mid) ? 1 : 0; });
       n_le = warp_sum(n_le);
       if (n_le >= n)
         hi = mid;
@@ -552,11 +615,108 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
     return __uint_as_float(lo);
   };
 
+  // The n smallest of the cached candidates by COUNTING: a 256-bin histogram over [0, max d2] (shared-memory
+  // atomics), the bin b* of the n-th by a scan of the bins (8 per lane), the sum of everything below b*, and
+  // the at most 32 candidates inside b* ranked against each other with shuffles.  ~350 warp instructions
+  // where the four-way search over all candidates takes ~2 000.  ok = false (b* holds more than 32
+  // candidates: clouds with many duplicates): the caller falls back to the search.
+  struct Sel {
+    bool ok;
+    float kth, sum, dmin;
+  };
+  auto select_hist = [&](const int n_cand, const int n) -> Sel {
+    float dmax = 0.f, dmin = kInfF();
+    for (int i = lane; i < n_cand; i += 32) {
+      const float v = cache[i];
+      dmax = fmaxf(dmax, v);
+      dmin = fminf(dmin, v);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, d));
+      dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+    }
+    if (!(dmax > 0.f)) return Sel{true, 0.f, 0.f, dmin};  // every candidate at distance 0
+    const float scale = 255.0f / dmax;
+    auto bin_of = [&](float v) { return min((int)(v * scale), 255); };  // monotone in v
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hist[lane + 32 * k] = 0;
+    __syncwarp();
+    for (int i = lane; i < n_cand; i += 32) atomicAdd(&hist[bin_of(cache[i])], 1);
+    __syncwarp();
+    int h[8], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      h[k] = hist[lane * 8 + k];
+      tot += h[k];
+    }
+    int inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    const int excl = inc - tot;
+    const bool mine = (excl < n) && (n <= inc);  // exactly one lane: n <= n_cand
+    int bstar = 0, below = 0, m = 0;
+    if (mine) {
+      int cum = excl;
+      bool found = false;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (!found && cum + h[k] >= n) {
+          bstar = lane * 8 + k;
+          below = cum;
+          m = h[k];
+          found = true;
+        }
+        cum += h[k];
+      }
+    }
+    const unsigned owner = __ballot_sync(0xffffffffu, mine);
+    if (owner == 0u) return Sel{false, 0.f, 0.f, dmin};  // (cannot happen for n <= n_cand)
+    const int src = __ffs(owner) - 1;
+    bstar = __shfl_sync(0xffffffffu, bstar, src);
+    below = __shfl_sync(0xffffffffu, below, src);
+    m = __shfl_sync(0xffffffffu, m, src);
+    if (m > 32) return Sel{false, 0.f, 0.f, dmin};
+    // sum below b*, and the candidates of b* one per lane
+    float sum = 0.f;
+    int filled = 0;
+    for (int i0 = 0; i0 < n_cand; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < n_cand;
+      const float v = valid ? cache[i] : 0.f;
+      const int b = bin_of(v);
+      if (valid && b < bstar) sum += v;
+      const bool in = valid && b == bstar;
+      const unsigned msk = __ballot_sync(0xffffffffu, in);
+      if (in) selbuf[filled + __popc(msk & ((1u << lane) - 1u))] = v;
+      filled += __popc(msk);
+    }
+    __syncwarp();
+    const float mv = (lane < m) ? selbuf[lane] : kInfF();
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const float vj = __shfl_sync(0xffffffffu, mv, j);
+      rank += (vj < mv || (vj == mv && j < lane)) ? 1 : 0;
+    }
+    const int need = n - below;  // 1 .. m
+    const unsigned kmask = __ballot_sync(0xffffffffu, lane < m && rank == need - 1);
+    const float kth = __shfl_sync(0xffffffffu, mv, __ffs(kmask) - 1);
+    if (lane < m && rank < need) sum += mv;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    __syncwarp();  // (selbuf / hist are reused by the next selection)
+    return Sel{true, kth, sum, dmin};
+  };
+
   // ---- B: the kk-th smallest of cube A; it bounds the true kk-th from above
   int n_cand = collect(C, kInfF());
   bool cached = n_cand <= kWarpCap;
   float limit = kInfF();
-  float kth = nth_smallest(C, n_cand, cached, limit, kk);
+  Sel sel = cached ? select_hist(n_cand, kk) : Sel{false, 0.f, 0.f, 0.f};
+  float kth = sel.ok ? sel.kth : nth_smallest(C, n_cand, cached, limit, kk);
   if (!C.covers_all && !(kth <= C.bound * C.bound)) {
     // ---- C: the cube whose boundary is at least sqrt(kth) away holds every point with d2 <= kth,
     //      the true kk nearest among them: collect only those
@@ -570,32 +730,50 @@ __global__ void __launch_bounds__(32 * kWarpQueryWarps) k_knn_query_warp(
     limit = kth;
     n_cand = collect(C, limit);
     cached = n_cand <= kWarpCap;
-    kth = nth_smallest(C, n_cand, cached, limit, kk);
+    sel = cached ? select_hist(n_cand, kk) : Sel{false, 0.f, 0.f, 0.f};
+    kth = sel.ok ? sel.kth : nth_smallest(C, n_cand, cached, limit, kk);
   }
   // ---- mean of the kk smallest without the `skip` smallest
   float sum = 0.f, dmin = kInfF();
-  int n_lt = 0;
-  auto acc = [&](float d) {
-    if (d < kth) {
-      sum += d;
-      ++n_lt;
-    }
-    dmin = fminf(dmin, d);
-  };
-  if (cached) {
-    for (int i = lane; i < n_cand; i += 32) acc(cache[i]);
+  if (sel.ok) {
+    sum = sel.sum;
+    dmin = sel.dmin;
   } else {
-    for_each_point(C, [&](float d) { if (d <= limit) acc(d); });
-  }
+    int n_lt = 0;
+    auto acc = [&](float d) {
+      if (d < kth) {
+        sum += d;
+        ++n_lt;
+      }
+      dmin = fminf(dmin, d);
+    };
+    if (cached) {
+      for (int i = lane; i < n_cand; i += 32) acc(cache[i]);
+    } else {
+      for_each_point(C, [&](float d) { if (d <= limit) acc(d); });
+    }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+    for (int d = 16; d > 0; d >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, d));
+    }
+    n_lt = warp_sum(n_lt);
+    sum += (float)(kk - n_lt) * kth;
   }
-  n_lt = warp_sum(n_lt);
-  sum += (float)(kk - n_lt) * kth;
   if (skip == 1) sum -= dmin;
   if (lane == 0) mean_out[qi] = sum / (float)(kk - skip);
+#ifdef PGDVS_KNN_STATS
+  if (lane == 0) {
+    atomicAdd(&g_knn_wstats[0], 1ull);
+    atomicAdd(&g_knn_wstats[1], (unsigned long long)r);
+    atomicAdd(&g_knn_wstats[2], (unsigned long long)C.nrows);
+    atomicAdd(&g_knn_wstats[3], (unsigned long long)n_cand);
+    if (r > 8) atomicAdd(&g_knn_wstats[4], 1ull);
+    if (r > 32) atomicAdd(&g_knn_wstats[5], 1ull);
+    if (!cached) atomicAdd(&g_knn_wstats[6], 1ull);
+    atomicMax(&g_knn_wstats[7], (unsigned long long)C.nrows);
+  }
+#endif
 }
 
 // Cell size relative to the calibrated K-neighbourhood radius.  Developer override, read once:
@@ -640,8 +818,9 @@ int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t 
     // points with NaN coordinates are not in the sorted array: like the brute-force kernel they
     // get +inf (no finite neighbour distance)
     k_fill_f32<<<blocks, 256, 0, stream>>>(mean_out, Q, kInfF());
-    // small clouds (the track branch: 10 - 35 k track points): the warp kernel is ahead up to ~60 k
-    // queries (20 k: 0.29 vs 0.47 ms, 60 k: 0.71 vs 0.79 ms, 157 k: 1.77 vs 1.20 ms with the grid build)
+    // the warp kernel (count-then-select) against the sorted-list thread kernel, grid build included:
+    // 20 k points 0.20 vs 0.47 ms, 60 k 0.47 vs 0.79 ms, 157 k 1.13 vs 1.19 ms (before the lane-spread
+    // candidate collection and the four-way search it lost above 60 k: 1.77 ms at 157 k)
     if (Q <= kWarpSelfMaxQ && skip <= 1) {
       const unsigned wb = (unsigned)((Q + kWarpQueryWarps - 1) / kWarpQueryWarps);
       k_knn_query_warp<true><<<wb, 32 * kWarpQueryWarps, 0, stream>>>(query, Q, grid, cells, sorted, K, skip, mean_out);
@@ -662,3 +841,12 @@ int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t 
 }
 
 }  // namespace pgdvs
+
+#ifdef PGDVS_KNN_STATS
+extern "C" int pgdvs_debug_knn_wstats(unsigned long long* out8) {
+  cudaError_t e = cudaMemcpyFromSymbol(out8, pgdvs::g_knn_wstats, sizeof(unsigned long long) * 8);
+  if (e != cudaSuccess) return (int)e;
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  return (int)cudaMemcpyToSymbol(pgdvs::g_knn_wstats, z, sizeof(z));
+}
+#endif
