@@ -128,14 +128,16 @@ __global__ void __launch_bounds__(256) k_knn_bbox(const float* __restrict__ ref,
 // points gives the radius that holds K + 1 of them (within a factor sqrt(2)).  The median of
 // those radii becomes the cell size, so a typical query is done after the first or second shell
 // whatever the local shape of the cloud (thin surface, rough surface, volume).
-__global__ void __launch_bounds__(256) k_knn_sample(const float* __restrict__ ref, int64_t R, int K,
+// Large clouds are read with a stride (every `stride`-th reference point, the count threshold scaled with
+// it): the estimate only has to land in the right power-of-two bin.
+__global__ void __launch_bounds__(256) k_knn_sample(const float* __restrict__ ref, int64_t R, int K, int stride,
                                                     float* __restrict__ est) {
   __shared__ int s_hist[256];  // bin = biased exponent of d2 (0..255)
   s_hist[threadIdx.x] = 0;
   __syncthreads();
   const int64_t si = (int64_t)blockIdx.x * R / kGridSamples;
   const float qx = __ldg(ref + si * 3), qy = __ldg(ref + si * 3 + 1), qz = __ldg(ref + si * 3 + 2);
-  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) {
+  for (int64_t i = (int64_t)threadIdx.x * stride; i < R; i += (int64_t)blockDim.x * stride) {
     const float dx = qx - __ldg(ref + i * 3), dy = qy - __ldg(ref + i * 3 + 1), dz = qz - __ldg(ref + i * 3 + 2);
     const float d = dx * dx + dy * dy + dz * dz;
     if (d == d) atomicAdd(&s_hist[(__float_as_uint(d) >> 23) & 255], 1);
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256) k_knn_sample(const float* __restrict__ re
     int cum = 0, bin = 255;
     for (int b = 0; b < 256; ++b) {
       cum += s_hist[b];
-      if (cum >= K + 1) {
+      if (cum * stride >= K + 1) {
         bin = b;
         break;
       }
@@ -805,7 +807,7 @@ int knn_grid_mean_dist(const float* query, int64_t Q, const float* ref, int64_t 
   k_knn_bbox_init<<<1, 32, 0, stream>>>(bbox);
   k_knn_bbox<<<blocks, 256, 0, stream>>>(ref, R, bbox);
   float* est = reinterpret_cast<float*>(ws + L.off_est);
-  k_knn_sample<<<kGridSamples, 256, 0, stream>>>(ref, R, K, est);
+  k_knn_sample<<<kGridSamples, 256, 0, stream>>>(ref, R, K, R > 32768 ? 4 : 1, est);
   k_knn_setup<<<1, kGridSamples, 0, stream>>>(bbox, R, est, knn_cell_scale(), grid);
   k_knn_count<<<blocks, 256, 0, stream>>>(ref, R, grid, cells, cell_of);
   if (int rc = check_launch()) return rc;
