@@ -44,7 +44,8 @@ def main():
     print("### launch list (C2 bench)\n")
     print(launch_table(d / "launches_c2.csv"))
     for label, rep in (("C2 (bench.py, 144 views)", "c2_full"), ("C4 (16 views)", "c4_tile"), ("C3 (8 views)", "c3_tile"),
-                       ("C5 K=8 r=0.01 (2 views)", "c5_k8"), ("C5 K=32 r=0.02 (2 views)", "c5_k32")):
+                       ("C5 K=8 r=0.01 (2 views)", "c5_k8"), ("C5 K=32 r=0.02 (2 views)", "c5_k32"),
+                       ("KNN outlier statistic (K = 51, tools/knn_time.py; the launch with -s 12)", "knn_warp")):
         p = d / (rep + ".ncu-rep")
         if not p.exists():
             continue
