@@ -580,15 +580,25 @@ def run_ours(args):
     # set, chunk) — they only hold pointers into the device input buffers and source-camera
     # constants; the target cameras, which change from step to step in a real run, are uploaded
     # from pinned memory every step.
-    n_chunks = 4 if (V % 48 == 0) else 1
-    per = V // n_chunks
-    preps = [[prepare_views(*w.jobs(range(c * per, (c + 1) * per)), H, W, dev) for c in range(n_chunks)] for w in (wl, wl_b)]
-    host_cams = [[p.cams_dev.cpu().pin_memory() for p in ps] for ps in preps]
-    cam_bytes = sum(t.numel() for t in host_cams[0])
+    # Chunks per step: 4 for fp32 frames (361 MB of D2H per step: small copies keep the link busy from the
+    # first chunk on), 2 for 8-bit frames (90 MB: the copy hides behind one chunk, larger launches run closer
+    # to the device-resident rate; measured 2 / 3 / 4 / 6 / 8 chunks: 49.7 / 48.0 / 45.3 / 42.1 / 39.5 k views/s).
+    def chunks_for(u8):
+        want = args.e2e_chunks if args.e2e_chunks > 0 else (2 if u8 else 4)
+        return want if V % want == 0 and (want != 4 or V % 48 == 0) else 1
+
+    pipes = {}
+    for nc in sorted({chunks_for(False), chunks_for(True)}):
+        pp = [[prepare_views(*w.jobs(range(c * (V // nc), (c + 1) * (V // nc))), H, W, dev) for c in range(nc)] for w in (wl, wl_b)]
+        pipes[nc] = (pp, [[q.cams_dev.cpu().pin_memory() for q in ps] for ps in pp])
+    cam_bytes = sum(t.numel() for t in pipes[chunks_for(False)][1][0])
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     state = {"inputs_free": [None, None], "step": 0}
 
     def e2e_step(u8=False):
+        n_chunks = chunks_for(u8)
+        per = V // n_chunks
+        preps, host_cams = pipes[n_chunks]
         cur = torch.cuda.current_stream(dev)
         b = state["step"] & 1
         state["step"] += 1
@@ -684,7 +694,7 @@ def run_ours(args):
         del oc
 
     # -------------------------------------------------- the other configs / the strong-scaling leg
-    del wl_b, preps, in_sets, host_img, host_mask, out
+    del wl_b, pipes, in_sets, host_img, host_mask, out
     torch.cuda.empty_cache()
     matrix = run_matrix(dev, flush, peak, args) if (world == 1 and rank == 0 and args.matrix) else None
     strong = run_strong(dev, rank, world, flush, args) if args.strong else None
@@ -716,12 +726,12 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + cam_bytes),
                     "d2h_bytes_per_step": int(V * H * W * 16), "steps": e2e_steps,
                     "note": ("host pinned inputs + target cameras -> H2D -> uwp/bin/raster -> D2H of fp32 frames+masks, wall "
-                             f"clock, median of 3 runs of {e2e_steps} steps; {n_chunks} view chunks pipelined on 3 streams, "
+                             f"clock, median of 3 runs of {e2e_steps} steps; {chunks_for(False)} view chunks pipelined on 3 streams, "
                              "device inputs double-buffered")},
             "e2e_u8_frames": {"value": e2e8_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d + cam_bytes),
                               "d2h_bytes_per_step": int(V * H * W * 4),
-                              "note": "same loop, 8-bit frames and masks written by the rasterizer's epilogue "
-                                      "(evaluator_pgdvs.py:51-77) instead of fp32"},
+                              "note": f"same loop in {chunks_for(True)} chunks, 8-bit frames and masks written by the rasterizer's "
+                                      "epilogue (evaluator_pgdvs.py:51-77) instead of fp32"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
@@ -747,6 +757,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_nvidia_seq")
     ap.add_argument("--views", type=int, default=None, help="views per GPU (default: the config's)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="view chunks of the pipelined end-to-end leg (default: 4 when they divide the views)")
     ap.add_argument("--K", type=int, default=None, help="points per pixel (default: the config's)")
     ap.add_argument("--radius", type=float, default=None, help="splat radius in NDC (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
