@@ -484,23 +484,24 @@ def run_ours(args):
     # their stores are coalesced (+0.02 ms per 144 frames; the stand-alone quantiser is 0.075 ms and,
     # with the work-sorted epilogue of session 2, the fused output cost +0.14 ms)
     want_u8 = world > 1 and gather_mode != "f32"
+    # caller-owned double buffer for them: the transfer of step i reads buffer i & 1 while step i + 1 renders
+    # into the other one (freshly allocated tensors held across steps made the caching allocator grow
+    # inside the timed region: 13 - 49 ms cudaMalloc stalls in the first ten steps)
+    frames_u8 = ([(torch.empty((V, H, W, 3), dtype=torch.uint8, device=dev), torch.empty((V, H, W, 1), dtype=torch.uint8, device=dev))
+                  for _ in range(2)] if want_u8 else None)
 
     def step(ev=None):
+        i = state_g["i"]
+        if want_u8 and state_g.get(("ev", i & 1)) is not None:  # the transfer that last read this buffer (step i - 2) is done
+            torch.cuda.current_stream().wait_event(state_g[("ev", i & 1)])
         out = render_prepared(prep, radius=radius, points_per_pixel=K, compositor="norm",
                               static_rgb=wl.static_rgb, raster_events=ev, return_fragments=args.fragments,
-                              return_u8=want_u8)
+                              return_u8=want_u8, u8_out=frames_u8[i & 1] if want_u8 else None)
         if world > 1:
-            i = state_g["i"]
             state_g["i"] += 1
             done = torch.cuda.Event()
             done.record()
             if sink is not None:
-                # the frames are a fresh tensor every step: hold it until the copy that reads it (two steps
-                # back by the time the reference is dropped) has finished — no record_stream, whose deferred
-                # frees make the caching allocator grow (a 35 ms cudaMalloc stall in the timed region)
-                if state_g.get(("ev", i & 1)) is not None:
-                    torch.cuda.current_stream().wait_event(state_g[("ev", i & 1)])
-                state_g[("keep", i & 1)] = out["image_u8"]
                 sink.push(out["image_u8"], i, after=done)
                 state_g[("ev", i & 1)] = sink.stream.record_event()
                 sink.commit()
@@ -510,7 +511,7 @@ def run_ours(args):
                 with torch.cuda.stream(comm_stream):
                     payload.record_stream(comm_stream)
                     dist.gather(payload, gather_list, dst=0)
-                state_g[i & 1] = comm_stream.record_event()
+                state_g[("ev", i & 1)] = comm_stream.record_event()
         return out
 
     def barrier():

@@ -333,12 +333,13 @@ def unproject_warp_project(pairs, cams_p3d=None, H: int = 0, W: int = 0, device=
 def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int, compositor: str = "norm",
                     static_rgb: Optional[torch.Tensor] = None, return_fragments: bool = False,
                     raster_events=None, fused: bool = True, return_cloud: bool = False,
-                    return_depth: bool = False, return_u8: bool = False, return_f32: bool = True):
+                    return_depth: bool = False, return_u8: bool = False, return_f32: bool = True, u8_out=None):
     """uwp kernel -> binning -> rasterize+composite(+mask, +static blend) for prepared views:
     stream-ordered stages, zero host syncs.  `fused=False` runs the stage-by-stage variant
     (uwp -> packed [P,3] cloud -> pgdvs_bin_points -> rasterize), which gives identical results.
     return_depth adds `depth` [N,H,W,1] (composited view depth), return_u8 adds `image_u8` /
-    `mask_u8` quantised in the rasterizer's epilogue (return_f32=False drops the fp32 copies)."""
+    `mask_u8` quantised in the rasterizer's epilogue (return_f32=False drops the fp32 copies; u8_out =
+    (image_u8, mask_u8) writes them into caller-owned buffers, fused path only)."""
     if not fused:
         cloud = unproject_warp_project(prep)
         out = ops.render_packed(cloud["xyz_ndc"], cloud["rgb"], cloud["first_idx"], cloud["num_points"],
@@ -379,7 +380,7 @@ def render_prepared(prep: PreparedViews, *, radius: float, points_per_pixel: int
     out = ops.rasterize_workspace(ws_ptr, nbytes.value, dev, n_views, cap, H, W, K, float(radius), False, 3,
                                   ops._COMPOSITORS[compositor], float(radius) * float(radius),
                                   (0.0, 0.0, 0.0), static_rgb, return_fragments, True, raster_events,
-                                  return_depth=return_depth, return_u8=return_u8, return_f32=return_f32)
+                                  return_depth=return_depth, return_u8=return_u8, return_f32=return_f32, u8_out=u8_out)
     out["first_idx"], out["num_points"] = first_idx, num_points
     out["cloud"] = {"xyz_ndc": xyz_ndc, "rgb": rgb, "first_idx": first_idx, "num_points": num_points,
                     "total": total, "_keepalive": prep}

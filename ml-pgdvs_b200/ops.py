@@ -162,7 +162,7 @@ def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int,
                         radius_max: float, per_point_radius: bool, C: int, mode: int, rr_weight,
                         background, static_rgb, return_fragments: bool, return_mask: bool,
                         raster_events=None, return_depth: bool = False, return_u8: bool = False,
-                        return_f32: bool = True):
+                        return_f32: bool = True, u8_out=None):
     """Rasterize-and-composite over a workspace that pgdvs_bin_points / pgdvs_uwp_bin left in
     the binned state (N, P, radius_max must repeat what the binning call was given).
 
@@ -170,7 +170,9 @@ def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int,
     "composited depth"; `zbuf[..., 0]` of the fragments is the nearest-hit depth).
     return_u8: also `image_u8` / `mask_u8`, quantised in the same pass exactly like the reference's
     evaluator (engines/evaluator_pgdvs.py:51-77); with return_f32=False the fp32 image / mask are
-    not written at all."""
+    not written at all.  u8_out = (image_u8 [N,H,W,C], mask_u8 [N,H,W,1]): caller-owned uint8 buffers
+    to write the 8-bit outputs into (a per-step consumer such as a frame gather keeps its own
+    double buffer instead of holding freshly allocated tensors alive across steps)."""
     L = _cabi.lib()
     stream = _stream_ptr(dev)
     with torch.cuda.device(dev):
@@ -188,7 +190,13 @@ def rasterize_workspace(ws_ptr: int, ws_bytes: int, dev, N: int, P: int, H: int,
                     mask = torch.empty((N, H, W, 1), dtype=torch.float32, device=dev)
             if return_depth:
                 depth = torch.empty((N, H, W, 1), dtype=torch.float32, device=dev)
-            if return_u8:
+            if return_u8 and u8_out is not None:
+                image_u8, mask_u8 = u8_out
+                for t, shp in ((image_u8, (N, H, W, C)), (mask_u8, (N, H, W, 1))):
+                    if (tuple(t.shape) != shp or t.dtype != torch.uint8 or not t.is_contiguous()
+                            or t.device != torch.device(dev)):
+                        raise ValueError(f"u8_out buffers must be contiguous uint8 {shp} tensors on {dev}")
+            elif return_u8:
                 image_u8 = torch.empty((N, H, W, C), dtype=torch.uint8, device=dev)
                 mask_u8 = torch.empty((N, H, W, 1), dtype=torch.uint8, device=dev)
         elif return_depth or return_u8:

@@ -114,6 +114,13 @@ def test_fused_path_depth_and_u8_outputs(name, views):
     prep = prepare_views(pairs, cams, wl.H, wl.W, d)
     c = render_prepared(prep, return_u8=True, return_f32=False, **kw)
     assert c["image"] is None and torch.equal(c["image_u8"], a["image_u8"]) and torch.equal(c["mask_u8"], a["mask_u8"])
+    # caller-owned 8-bit buffers (what a per-step frame gather double-buffers)
+    img8 = torch.full(tuple(a["image_u8"].shape), 7, dtype=torch.uint8, device=d)
+    msk8 = torch.full(tuple(a["mask_u8"].shape), 7, dtype=torch.uint8, device=d)
+    e = render_prepared(prep, return_u8=True, u8_out=(img8, msk8), **kw)
+    assert e["image_u8"] is img8 and torch.equal(img8, a["image_u8"]) and torch.equal(msk8, a["mask_u8"])
+    with pytest.raises(ValueError):
+        render_prepared(prep, return_u8=True, u8_out=(img8.float(), msk8), **kw)
 
 
 def test_compute_projections_matches_reference_golden(golden_dir):
