@@ -280,3 +280,26 @@ def test_prepare_data_and_resize_match_the_restatement():
     a_rgb, a_mask = PGDVSDynamicRenderer.resize_rgb_mask(rgb, mask, 36, 60)
     e_rgb, e_mask = ref.resize_rgb_mask(rgb, mask, 36, 60)
     assert torch.equal(a_rgb, e_rgb) and torch.equal(a_mask, e_mask) and a_rgb.shape == (2, 3, 36, 60)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port on the host cores) prints
+    ONE JSON line with the keys the driver reads; no GPU, no CUDA library involved."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-step-seconds", "1"], capture_output=True, text=True, timeout=600, cwd=str(root))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rendered_novel_views_per_s" and d["unit"] == "views/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["config"]["workload"] == "c2_nvidia_seq"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "rows" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
